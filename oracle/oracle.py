@@ -1,0 +1,197 @@
+"""ctypes binding of the CPU oracle (oracle/whisper_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs.  The product package (speaksense_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libwhisper_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("whisper_oracle.c", "whisper_oracle.h", "Makefile")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc"})
+    return _LIB_PATH
+
+
+class WoHParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "n_vocab", "n_audio_ctx", "n_audio_state", "n_audio_head", "n_audio_layer", "n_text_ctx",
+        "n_text_state", "n_text_head", "n_text_layer", "n_mels", "ftype")]
+
+
+class WoParams(C.Structure):
+    _fields_ = [("language", C.c_char_p), ("tdrz_enable", C.c_int), ("no_context", C.c_int),
+                ("single_segment", C.c_int), ("best_of", C.c_int), ("beam_size", C.c_int),
+                ("temperature", C.c_float), ("temperature_inc", C.c_float), ("entropy_thold", C.c_float),
+                ("logprob_thold", C.c_float), ("max_initial_ts", C.c_float), ("length_penalty", C.c_float),
+                ("suppress_blank", C.c_int), ("n_max_text_ctx", C.c_int), ("max_tokens", C.c_int),
+                ("n_threads", C.c_int), ("keep_logits", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _LIB_PATH
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    L.wo_load.restype = C.c_void_p
+    L.wo_load.argtypes = [C.c_char_p]
+    L.wo_free.argtypes = [C.c_void_p]
+    L.wo_get_hparams.restype = C.POINTER(WoHParams)
+    L.wo_get_hparams.argtypes = [C.c_void_p]
+    L.wo_last_error.restype = C.c_char_p
+    L.wo_token_id.argtypes = [C.c_void_p, C.c_char_p]
+    L.wo_token_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]
+    L.wo_set_threads.argtypes = [C.c_int]
+    L.wo_default_params.argtypes = [C.POINTER(WoParams)]
+    L.wo_log_mel.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
+                             C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.wo_free_buf.argtypes = [C.c_void_p]
+    L.wo_state_new.restype = C.c_void_p
+    L.wo_state_new.argtypes = [C.c_void_p]
+    L.wo_state_free.argtypes = [C.c_void_p]
+    L.wo_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.wo_encoder_out.restype = C.POINTER(C.c_float)
+    L.wo_encoder_out.argtypes = [C.c_void_p]
+    L.wo_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.wo_full.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(WoParams)]
+    for f in ("wo_n_segments", "wo_n_result_tokens", "wo_n_fallbacks", "wo_n_decoded", "wo_n_windows",
+              "wo_n_kept_logits"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.wo_segment_text.restype = C.c_char_p
+    L.wo_segment_text.argtypes = [C.c_void_p, C.c_int]
+    L.wo_segment_t0.restype = C.c_int64
+    L.wo_segment_t0.argtypes = [C.c_void_p, C.c_int]
+    L.wo_segment_t1.restype = C.c_int64
+    L.wo_segment_t1.argtypes = [C.c_void_p, C.c_int]
+    L.wo_segment_speaker_turn_next.argtypes = [C.c_void_p, C.c_int]
+    L.wo_result_token.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.wo_kept_logits.restype = C.POINTER(C.c_float)
+    L.wo_kept_logits.argtypes = [C.c_void_p, C.c_int]
+    _lib = L
+    return L
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+class OracleModel:
+    def __init__(self, path: str):
+        self.L = lib()
+        self.h = self.L.wo_load(path.encode())
+        if not self.h:
+            raise OracleError(self.L.wo_last_error().decode())
+        hp = self.L.wo_get_hparams(self.h).contents
+        self.hparams = {n: getattr(hp, n) for n, _ in WoHParams._fields_}
+
+    def close(self):
+        if self.h:
+            self.L.wo_free(self.h)
+            self.h = None
+
+    def token_id(self, name: str) -> int:
+        return self.L.wo_token_id(self.h, name.encode())
+
+    def token_bytes(self, i: int) -> bytes:
+        p = C.c_char_p()
+        n = self.L.wo_token_bytes(self.h, i, C.byref(p))
+        return C.string_at(p, n) if n >= 0 else b""
+
+    def log_mel(self, pcm: np.ndarray):
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        out = C.c_void_p()
+        n_len, n_org = C.c_int(), C.c_int()
+        self.L.wo_log_mel(self.h, pcm.ctypes.data, pcm.size, C.byref(out), C.byref(n_len), C.byref(n_org))
+        n_mels = self.hparams["n_mels"]
+        arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_float)), shape=(n_mels, n_len.value)).copy()
+        self.L.wo_free_buf(out)
+        return arr, n_len.value, n_org.value
+
+    def new_state(self) -> "OracleState":
+        return OracleState(self)
+
+
+class OracleState:
+    def __init__(self, model: OracleModel):
+        self.m = model
+        self.L = model.L
+        self.h = self.L.wo_state_new(model.h)
+
+    def close(self):
+        if self.h:
+            self.L.wo_state_free(self.h)
+            self.h = None
+
+    def encode(self, mel: np.ndarray, seek: int = 0) -> np.ndarray:
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        self.L.wo_encode(self.h, mel.ctypes.data, mel.shape[1], seek)
+        hp = self.m.hparams
+        p = self.L.wo_encoder_out(self.h)
+        return np.ctypeslib.as_array(p, shape=(hp["n_audio_ctx"], hp["n_audio_state"])).copy()
+
+    def decode(self, tokens, n_past: int, seq: int = 0) -> np.ndarray:
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(self.m.hparams["n_vocab"], dtype=np.float32)
+        rc = self.L.wo_decode(self.h, seq, t.ctypes.data, t.size, n_past, out.ctypes.data)
+        if rc:
+            raise OracleError(self.L.wo_last_error().decode())
+        return out
+
+    def full(self, pcm: np.ndarray, language=None, stream_mode=False, speaker_diarization=False,
+             keep_logits=False, n_threads=16, beam_size=0, **over):
+        """== reference transcribe_with_state up to (not including) the Rust post-processing:
+        build_params (whisper.rs:131-173) + overrides (:60-71) + state.full (:75)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+        P = WoParams()
+        self.L.wo_default_params(C.byref(P))
+        self._lang = language.encode() if language else None
+        P.language = self._lang
+        P.tdrz_enable = int(speaker_diarization)
+        if stream_mode:
+            P.single_segment = 0
+            P.no_context = 1
+        P.keep_logits = int(keep_logits)
+        P.n_threads = n_threads
+        P.beam_size = beam_size
+        for k, v in over.items():
+            setattr(P, k, v)
+        rc = self.L.wo_full(self.h, pcm.ctypes.data, pcm.size, C.byref(P))
+        if rc:
+            raise OracleError("wo_full rc=%d: %s" % (rc, self.L.wo_last_error().decode()))
+        segs = []
+        for i in range(self.L.wo_n_segments(self.h)):
+            segs.append(dict(text=self.L.wo_segment_text(self.h, i), t0=self.L.wo_segment_t0(self.h, i),
+                             t1=self.L.wo_segment_t1(self.h, i),
+                             speaker_turn_next=bool(self.L.wo_segment_speaker_turn_next(self.h, i))))
+        toks, plogs = [], []
+        p, pl = C.c_float(), C.c_float()
+        for i in range(self.L.wo_n_result_tokens(self.h)):
+            toks.append(self.L.wo_result_token(self.h, i, C.byref(p), C.byref(pl)))
+            plogs.append(pl.value)
+        return dict(segments=segs, tokens=toks, plogs=plogs, n_fallbacks=self.L.wo_n_fallbacks(self.h),
+                    n_decoded=self.L.wo_n_decoded(self.h), n_windows=self.L.wo_n_windows(self.h))
+
+    def kept_logits(self) -> np.ndarray:
+        n = self.L.wo_n_kept_logits(self.h)
+        nv = self.m.hparams["n_vocab"]
+        if n == 0:
+            return np.zeros((0, nv), np.float32)
+        p = self.L.wo_kept_logits(self.h, 0)
+        return np.ctypeslib.as_array(p, shape=(n, nv)).copy()
