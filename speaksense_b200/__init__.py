@@ -1,0 +1,9 @@
+"""speaksense_b200 - B200-native Whisper transcribe path behind SpeakSense's AsrEngine boundary.
+
+Package contents: csrc/ (sm_100a CUDA kernels + C ABI), build.py (nvcc driver), _native.py (ctypes
+binding), asr.py (host mirror of /root/reference/src/asr), synth.py (synthetic ggml models / audio
+for tests and benchmarks)."""
+from .asr import AsrEngine, AsrParams, TranscribeResult, TranscribeSegment, WhisperAsr, WhisperState  # noqa: F401
+from ._native import NativeError  # noqa: F401
+
+__all__ = ["AsrEngine", "AsrParams", "TranscribeResult", "TranscribeSegment", "WhisperAsr", "WhisperState", "NativeError"]

@@ -1,0 +1,246 @@
+"""Host-side mirror of the reference's ASR boundary (/root/reference/src/asr/mod.rs:9-73 and
+src/asr/whisper.rs:16-129), over the C ABI of the B200 engine.
+
+Same names, argument meaning and error behaviour as the Rust trait:
+
+    engine = WhisperAsr(model_path)            # WhisperAsr::new            whisper.rs:21
+    state  = engine.create_state()             # AsrEngine::create_state    mod.rs:60
+    result = engine.transcribe_with_state(state, audio, params)   # mod.rs:62-67
+    result = engine.transcribe(audio, params)  # fresh state per call       mod.rs:69-72
+
+`audio` is mono 16 kHz f32 (the reference's Vec<f32>), `result` a TranscribeResult whose segment
+start/end are whisper's 10 ms ticks as float (whisper.rs:107-108).
+"""
+from __future__ import annotations
+
+import abc
+import ctypes as C
+import threading
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from ._native import NativeError, SsParams
+
+
+@dataclass
+class AsrParams:                      # mod.rs:9-42
+    language: Optional[str] = None
+    speaker_diarization: bool = False
+    stream_mode: bool = False
+    min_segment_length: int = 10
+    # extensions (not in the reference struct)
+    beam_size: int = 0
+    debug_keep_logits: bool = False
+
+    def set_language(self, language: Optional[str]):
+        self.language = language
+
+    def set_speaker_diarization(self, enable: bool):
+        self.speaker_diarization = enable
+
+    def set_stream_mode(self, enable: bool):
+        self.stream_mode = enable
+
+    def set_min_segment_length(self, length: int):
+        self.min_segment_length = length
+
+    def _native(self) -> SsParams:
+        p = SsParams()
+        _native.lib().ss_params_default(C.byref(p))
+        p.language = self.language.encode() if self.language else None
+        p.speaker_diarization = int(self.speaker_diarization)
+        p.stream_mode = int(self.stream_mode)
+        p.min_segment_length = int(self.min_segment_length)
+        p.beam_size = int(self.beam_size)
+        p.debug_keep_logits = int(self.debug_keep_logits)
+        return p
+
+
+@dataclass
+class TranscribeSegment:              # mod.rs:44-50
+    text: str
+    speaker_id: int
+    start: float
+    end: float
+
+
+@dataclass
+class TranscribeResult:               # mod.rs:52-56
+    segments: List[TranscribeSegment] = field(default_factory=list)
+    full_text: str = ""
+
+
+class WhisperState:
+    """== Arc<Mutex<Box<WhisperState>>> (whisper.rs:30-39): caller-owned session; the lock serialises
+    calls on the same state exactly like the reference's Mutex (whisper.rs:51-54)."""
+
+    def __init__(self, engine: "WhisperAsr"):
+        self._engine = engine            # keeps the engine alive (fixes the transmute hazard, whisper.rs:34-36)
+        self._lock = threading.Lock()
+        h = C.c_void_p()
+        _native.check(_native.lib().ss_state_new(engine._h, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _native.lib().ss_state_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # diagnostics of the last call
+    def raw_segments(self):
+        L, h = _native.lib(), self._h
+        return [dict(text=L.ss_segment_text_raw(h, i), t0=L.ss_segment_t0_raw(h, i), t1=L.ss_segment_t1_raw(h, i),
+                     speaker_turn_next=bool(L.ss_segment_speaker_turn_next_raw(h, i)))
+                for i in range(L.ss_n_segments_raw(h))]
+
+    def result_tokens(self):
+        L, h = _native.lib(), self._h
+        p, pl = C.c_float(), C.c_float()
+        toks, plogs = [], []
+        for i in range(L.ss_n_result_tokens(h)):
+            toks.append(L.ss_result_token(h, i, C.byref(p), C.byref(pl)))
+            plogs.append(pl.value)
+        return toks, plogs
+
+    def stats(self):
+        L, h = _native.lib(), self._h
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        L.ss_stage_ms(h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(n_fallbacks=L.ss_n_fallbacks(h), n_decoded=L.ss_n_decoded(h), n_windows=L.ss_n_windows(h),
+                    n_launches=L.ss_n_kernel_launches(h), mel_ms=a.value, encoder_ms=b.value, decode_ms=c.value)
+
+    def debug_logits(self) -> np.ndarray:
+        L, h = _native.lib(), self._h
+        rows = []
+        nv = C.c_int()
+        i = 0
+        while True:
+            p = L.ss_debug_logits(h, i, C.byref(nv))
+            if not p:
+                break
+            rows.append(np.ctypeslib.as_array(p, shape=(nv.value,)).copy())
+            i += 1
+        return np.stack(rows) if rows else np.zeros((0, 0), np.float32)
+
+
+class AsrEngine(abc.ABC):             # mod.rs:58-73
+    @abc.abstractmethod
+    def create_state(self) -> WhisperState: ...
+
+    @abc.abstractmethod
+    def transcribe_with_state(self, state: WhisperState, audio, params: AsrParams) -> TranscribeResult: ...
+
+    def transcribe(self, audio, params: AsrParams) -> TranscribeResult:
+        state = self.create_state()
+        try:
+            return self.transcribe_with_state(state, audio, params)
+        finally:
+            state.close()
+
+
+class WhisperAsr(AsrEngine):          # whisper.rs:16-129
+    def __init__(self, model_path: str, device: int = 0, *, rank: int = 0, world_size: int = 1,
+                 nccl_id: Optional[bytes] = None):
+        L = _native.lib()
+        h = C.c_void_p()
+        path = model_path.encode() if model_path else None
+        if world_size > 1:
+            rc = L.ss_engine_open_dist(path, device, rank, world_size, nccl_id, C.byref(h))
+        else:
+            rc = L.ss_engine_open(path, device, C.byref(h))
+        if rc != 0:   # "failed to open whisper model: {}"  whisper.rs:24
+            raise NativeError(rc, "failed to open whisper model: " + L.ss_last_error().decode("utf-8", "replace"))
+        self._h = h
+        self.device = device
+        nv, d, la, lt, nm = (C.c_int() for _ in range(5))
+        wb = C.c_int64()
+        L.ss_engine_info(h, C.byref(nv), C.byref(d), C.byref(la), C.byref(lt), C.byref(nm), C.byref(wb))
+        self.info = dict(n_vocab=nv.value, n_audio_state=d.value, n_audio_layer=la.value, n_text_layer=lt.value,
+                         n_mels=nm.value, weight_bytes=wb.value)
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _native.check(_native.lib().ss_nccl_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _native.lib().ss_engine_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def create_state(self) -> WhisperState:
+        return WhisperState(self)
+
+    @staticmethod
+    def _read_result(state: WhisperState) -> TranscribeResult:
+        L, h = _native.lib(), state._h
+        segs = [TranscribeSegment(text=L.ss_segment_text(h, i).decode("utf-8"), speaker_id=L.ss_segment_speaker_id(h, i),
+                                  start=L.ss_segment_start(h, i), end=L.ss_segment_end(h, i))
+                for i in range(L.ss_n_segments(h))]
+        return TranscribeResult(segments=segs, full_text=L.ss_full_text(h).decode("utf-8"))
+
+    def transcribe_with_state(self, state: WhisperState, audio, params: AsrParams) -> TranscribeResult:
+        pcm = np.ascontiguousarray(audio, dtype=np.float32)
+        p = params._native()
+        with state._lock:
+            _native.check(_native.lib().ss_transcribe(self._h, state._h, pcm.ctypes.data, pcm.size, C.byref(p)))
+            return self._read_result(state)
+
+    def transcribe_batch(self, states: Sequence[WhisperState], audios: Sequence[np.ndarray], params: AsrParams):
+        """Data-parallel batch inside one GPU (BASELINE configs 3/4): result i belongs to audios[i]."""
+        n = len(states)
+        pcms = [np.ascontiguousarray(a, dtype=np.float32) for a in audios]
+        sp = (C.c_void_p * n)(*[s._h for s in states])
+        pp = (C.c_void_p * n)(*[a.ctypes.data for a in pcms])
+        ns = (C.c_size_t * n)(*[a.size for a in pcms])
+        p = params._native()
+        _native.check(_native.lib().ss_transcribe_batch(self._h, sp, pp, ns, n, C.byref(p)))
+        return [self._read_result(s) for s in states]
+
+    # ---- stage-level entry points (parity tests / roofline measurement)
+    def log_mel(self, state: WhisperState, audio):
+        pcm = np.ascontiguousarray(audio, dtype=np.float32)
+        n_len, n_org = C.c_int(), C.c_int()
+        L = _native.lib()
+        _native.check(L.ss_log_mel(self._h, state._h, pcm.ctypes.data, pcm.size, None, 0, C.byref(n_len), C.byref(n_org)))
+        out = np.empty((self.info["n_mels"], n_len.value), np.float32)
+        _native.check(L.ss_log_mel(self._h, state._h, pcm.ctypes.data, pcm.size, out.ctypes.data, out.size, C.byref(n_len), C.byref(n_org)))
+        return out, n_len.value, n_org.value
+
+    def encode(self, state: WhisperState, seek: int = 0) -> np.ndarray:
+        out = np.empty((1500, self.info["n_audio_state"]), np.float32)
+        _native.check(_native.lib().ss_encode(self._h, state._h, seek, out.ctypes.data, out.size))
+        return out
+
+    def decode(self, state: WhisperState, tokens, n_past: int) -> np.ndarray:
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(self.info["n_vocab"], np.float32)
+        _native.check(_native.lib().ss_decode(self._h, state._h, t.ctypes.data, t.size, n_past, out.ctypes.data))
+        return out
+
+
+def debug_gemm(a: np.ndarray, b: np.ndarray, b_mn_major: bool = False, device: int = 0) -> np.ndarray:
+    """D = A . B^T (B [N][K]) or A . B (B [K][N], b_mn_major) through the tcgen05 GEMM; f16 in, f32 out."""
+    a = np.ascontiguousarray(a, dtype=np.float16)
+    b = np.ascontiguousarray(b, dtype=np.float16)
+    M, K = a.shape
+    N = b.shape[1] if b_mn_major else b.shape[0]
+    d = np.empty((M, N), np.float32)
+    _native.check(_native.lib().ss_debug_gemm(device, a.ctypes.data, b.ctypes.data, d.ctypes.data, M, N, K, int(b_mn_major)))
+    return d

@@ -1,0 +1,217 @@
+// api.cc - the C ABI declared in include/speaksense_whisper.h.
+#include <cstring>
+#include <mutex>
+
+#include "../../include/speaksense_whisper.h"
+#include "engine.h"
+
+using namespace ss;
+
+struct ss_engine { std::shared_ptr<Engine> e; };
+struct ss_state { State *s; };
+
+static thread_local std::string g_err;
+
+template <typename F>
+static int guard(F &&f) {
+    try {
+        return f();
+    } catch (const ss::Error &e) {
+        g_err = e.what(); return e.code;
+    } catch (const std::bad_alloc &) {
+        g_err = "host out of memory"; return SS_ERR_OOM;
+    } catch (const std::exception &e) {
+        g_err = e.what(); return SS_ERR_INTERNAL;
+    }
+}
+
+static FullParams make_params(const ss_params *p) {
+    FullParams fp;   // build_params defaults (whisper.rs:131-173)
+    if (p) {
+        if (p->language && p->language[0]) fp.language = p->language;      // whisper.rs:60-63
+        fp.tdrz_enable = p->speaker_diarization != 0;                        // whisper.rs:137-140
+        if (p->stream_mode) { fp.single_segment = false; fp.no_context = true; }   // whisper.rs:65-69 (audio_ctx 0 == full ctx)
+        fp.beam_size = p->beam_size;
+        fp.keep_logits = p->debug_keep_logits != 0;
+    }
+    return fp;
+}
+
+extern "C" {
+
+void ss_params_default(ss_params *p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->language = nullptr; p->speaker_diarization = 0; p->stream_mode = 0; p->min_segment_length = 10;   // mod.rs:18-25
+}
+int ss_abi_version(void) { return SS_ABI_VERSION; }
+const char *ss_last_error(void) { return g_err.c_str(); }
+const char *ss_build_info(void) { return "speaksense_b200 whisper engine; sm_100a; tcgen05+TMA GEMM; CUDA " SS_STR(CUDART_VERSION); }
+
+int ss_engine_open(const char *path, int device, ss_engine **out) {
+    return guard([&]() -> int {
+        if (!path || !out) SS_THROW(SS_ERR_INVALID, "null argument");
+        auto e = engine_open(path, device);
+        *out = new ss_engine{e};
+        return 0;
+    });
+}
+int ss_nccl_unique_id(unsigned char out[128]) {
+    return guard([&]() -> int { if (!out) SS_THROW(SS_ERR_INVALID, "null argument"); nccl_unique_id(out); return 0; });
+}
+int ss_engine_open_dist(const char *path, int device, int rank, int world, const unsigned char nccl_id[128], ss_engine **out) {
+    return guard([&]() -> int {
+        if (!out || (world > 1 && !nccl_id) || rank < 0 || rank >= (world > 0 ? world : 1)) SS_THROW(SS_ERR_INVALID, "bad argument");
+        auto e = engine_open_dist(path, device, rank, world, nccl_id);
+        *out = new ss_engine{e};
+        return 0;
+    });
+}
+void ss_engine_close(ss_engine *e) { delete e; }
+int ss_engine_info(const ss_engine *e, int *n_vocab, int *n_audio_state, int *n_audio_layer, int *n_text_layer, int *n_mels, int64_t *weight_bytes) {
+    if (!e) { g_err = "null engine"; return SS_ERR_INVALID; }
+    const HParams &hp = e->e->model.hp;
+    if (n_vocab) *n_vocab = hp.n_vocab;
+    if (n_audio_state) *n_audio_state = hp.n_audio_state;
+    if (n_audio_layer) *n_audio_layer = hp.n_audio_layer;
+    if (n_text_layer) *n_text_layer = hp.n_text_layer;
+    if (n_mels) *n_mels = hp.n_mels;
+    if (weight_bytes) *weight_bytes = (int64_t)e->e->model.arena_bytes;
+    return 0;
+}
+
+int ss_state_new(ss_engine *e, ss_state **out) {
+    return guard([&]() -> int {
+        if (!e || !out) SS_THROW(SS_ERR_INVALID, "null argument");
+        *out = new ss_state{state_new(e->e)};
+        return 0;
+    });
+}
+void ss_state_free(ss_state *s) { if (s) { delete s->s; delete s; } }
+
+int ss_transcribe(ss_engine *e, ss_state *s, const float *pcm, size_t n, const ss_params *p) {
+    return guard([&]() -> int {
+        if (!e || !s || (!pcm && n)) SS_THROW(SS_ERR_INVALID, "null argument");
+        if (s->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
+        return transcribe(*s->s, pcm, n, make_params(p), p && p->stream_mode);
+    });
+}
+int ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *const *pcm, const size_t *n, int batch, const ss_params *p) {
+    return guard([&]() -> int {
+        if (!e || !states || !pcm || !n || batch < 0) SS_THROW(SS_ERR_INVALID, "null argument");
+        int rc = 0;
+        for (int i = 0; i < batch; i++) {
+            if (!states[i] || states[i]->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "bad state %d", i);
+            const int r = transcribe(*states[i]->s, pcm[i], n[i], make_params(p), p && p->stream_mode);
+            if (r && !rc) rc = r;
+        }
+        return rc;
+    });
+}
+
+int ss_n_segments_raw(const ss_state *s) { return s ? (int)s->s->raw.size() : 0; }
+const char *ss_segment_text_raw(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->raw.size()) ? s->s->raw[i].text.c_str() : nullptr; }
+int64_t ss_segment_t0_raw(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->raw.size()) ? s->s->raw[i].t0 : -1; }
+int64_t ss_segment_t1_raw(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->raw.size()) ? s->s->raw[i].t1 : -1; }
+int ss_segment_speaker_turn_next_raw(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->raw.size()) ? s->s->raw[i].speaker_turn_next : 0; }
+
+int ss_n_segments(const ss_state *s) { return s ? (int)s->s->out.size() : 0; }
+const char *ss_segment_text(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->out.size()) ? s->s->out[i].text.c_str() : nullptr; }
+double ss_segment_start(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->out.size()) ? s->s->out[i].start : -1.0; }
+double ss_segment_end(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->out.size()) ? s->s->out[i].end : -1.0; }
+int ss_segment_speaker_id(const ss_state *s, int i) { return (s && i >= 0 && i < (int)s->s->out.size()) ? s->s->out[i].speaker_id : 0; }
+const char *ss_full_text(const ss_state *s) { return s ? s->s->full_text.c_str() : nullptr; }
+
+int ss_n_result_tokens(const ss_state *s) { return s ? (int)s->s->result_tokens.size() : 0; }
+int ss_result_token(const ss_state *s, int i, float *p, float *plog) {
+    if (!s || i < 0 || i >= (int)s->s->result_tokens.size()) return -1;
+    const TokData &t = s->s->result_tokens[i];
+    if (p) *p = t.p;
+    if (plog) *plog = t.plog;
+    return t.id;
+}
+int ss_n_fallbacks(const ss_state *s) { return s ? s->s->n_fallbacks : 0; }
+int ss_n_decoded(const ss_state *s) { return s ? s->s->n_decoded : 0; }
+int ss_n_windows(const ss_state *s) { return s ? s->s->n_windows : 0; }
+int ss_n_kernel_launches(const ss_state *s) { return s ? s->s->n_launches : 0; }
+int ss_stage_ms(const ss_state *s, float *mel_ms, float *enc_ms, float *dec_ms) {
+    if (!s) return SS_ERR_INVALID;
+    if (mel_ms) *mel_ms = s->s->ms_mel;
+    if (enc_ms) *enc_ms = s->s->ms_enc;
+    if (dec_ms) *dec_ms = s->s->ms_dec;
+    return 0;
+}
+const float *ss_debug_logits(const ss_state *s, int step, int *n_vocab) {
+    if (!s || step < 0 || step >= s->s->n_keep) return nullptr;
+    const int nv = s->s->engine->model.hp.n_vocab;
+    if (n_vocab) *n_vocab = nv;
+    return s->s->h_keep.data() + (size_t)step * nv;
+}
+
+int ss_log_mel(ss_engine *e, ss_state *s, const float *pcm, size_t n, float *mel_out, size_t mel_cap, int *n_len, int *n_len_org) {
+    return guard([&]() -> int {
+        if (!e || !s || (!pcm && n)) SS_THROW(SS_ERR_INVALID, "null argument");
+        State &st = *s->s;
+        run_log_mel(st, pcm, n);
+        CUDA_CHECK(cudaStreamSynchronize(st.stream));
+        if (n_len) *n_len = st.n_len;
+        if (n_len_org) *n_len_org = st.n_len_org;
+        if (mel_out) {
+            const size_t need = (size_t)st.engine->model.hp.n_mels * st.n_len;
+            if (mel_cap < need) SS_THROW(SS_ERR_INVALID, "mel_out too small: need %zu floats", need);
+            CUDA_CHECK(cudaMemcpy(mel_out, st.d_mel, need * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    });
+}
+int ss_encode(ss_engine *e, ss_state *s, int seek, float *enc_out, size_t enc_cap) {
+    return guard([&]() -> int {
+        if (!e || !s) SS_THROW(SS_ERR_INVALID, "null argument");
+        State &st = *s->s;
+        if (!st.d_mel) SS_THROW(SS_ERR_INVALID, "ss_encode needs a preceding ss_log_mel on this state");
+        run_encode(st, seek);
+        CUDA_CHECK(cudaStreamSynchronize(st.stream));
+        if (enc_out) {
+            const HParams &hp = st.engine->model.hp;
+            const size_t need = (size_t)hp.n_audio_ctx * hp.n_audio_state;
+            if (enc_cap < need) SS_THROW(SS_ERR_INVALID, "enc_out too small: need %zu floats", need);
+            CUDA_CHECK(cudaMemcpy(enc_out, st.enc_out, need * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    });
+}
+int ss_decode(ss_engine *e, ss_state *s, const int *tokens, int n, int n_past, float *logits_out) {
+    return guard([&]() -> int {
+        if (!e || !s || !tokens) SS_THROW(SS_ERR_INVALID, "null argument");
+        run_decode_forced(*s->s, tokens, n, n_past, logits_out);
+        return 0;
+    });
+}
+
+int ss_debug_gemm(int device, const uint16_t *a, const uint16_t *b, float *d, int M, int N, int K, int b_mn_major) {
+    return guard([&]() -> int {
+        if (!a || !b || !d || M <= 0 || N <= 0 || K <= 0) SS_THROW(SS_ERR_INVALID, "bad argument");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) SS_THROW(SS_ERR_NO_DEVICE, "no CUDA device available (no CPU fallback)");
+        CUDA_CHECK(cudaSetDevice(device));
+        gemm_init();
+        __half *da, *db; float *dd;
+        const size_t nb = b_mn_major ? (size_t)K * N : (size_t)N * K;
+        CUDA_CHECK(cudaMalloc(&da, (size_t)M * K * 2)); CUDA_CHECK(cudaMalloc(&db, nb * 2)); CUDA_CHECK(cudaMalloc(&dd, (size_t)M * N * 4));
+        CUDA_CHECK(cudaMemcpy(da, a, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(db, b, nb * 2, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemset(dd, 0xff, (size_t)M * N * 4));
+        GemmOperand A; A.ptr = da; A.rows = M; A.ld = K;
+        GemmOperand B; B.ptr = db;
+        if (b_mn_major) { B.rows = K; B.ld = N; } else { B.rows = N; B.ld = K; }
+        GemmEpilogue ep; ep.out = dd; ep.out_type = GEMM_OUT_F32; ep.out_ld = N;
+        int launches = 0;
+        gemm_enqueue(A, B, M, N, K, b_mn_major != 0, ep, 0, &launches);
+        CUDA_CHECK(cudaDeviceSynchronize());
+        CUDA_CHECK(cudaMemcpy(d, dd, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+        cudaFree(da); cudaFree(db); cudaFree(dd);
+        return 0;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,739 @@
+// engine.cc - sessions, encoder orchestration, the whisper_full decode loop and post-processing.
+//
+// Host-side restatement of `state.full(params, &audio)` (/root/reference/src/asr/whisper.rs:75) for
+// the B200 engine: whisper.cpp's whisper_full_with_state control flow with
+// every arithmetic stage on the device.  The temperature-0 greedy decoder runs entirely on the GPU
+// (CUDA-graph replay, on-device logits filter / argmax / state update); the t>0 fallback decoders are
+// sampled on the host with std::mt19937 + std::discrete_distribution exactly like whisper.cpp.
+#include "engine.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace ss {
+
+namespace {
+
+template <typename T>
+T *dmalloc(size_t n) {
+    T *p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) SS_THROW(-5, "cudaMalloc of %zu bytes failed", n * sizeof(T));
+    return p;
+}
+template <typename T>
+T *hmalloc(size_t n) {
+    T *p = nullptr;
+    if (cudaMallocHost(&p, n * sizeof(T)) != cudaSuccess) SS_THROW(-5, "cudaMallocHost of %zu bytes failed", n * sizeof(T));
+    return p;
+}
+
+void check_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) SS_THROW(-3, "no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= n) SS_THROW(-3, "CUDA device %d out of range (%d visible)", device, n);
+    cudaDeviceProp pr;
+    CUDA_CHECK(cudaGetDeviceProperties(&pr, device));
+    if (pr.major != 10) SS_THROW(-3, "device %d is sm_%d%d; this engine is built for sm_100a (B200) only", device, pr.major, pr.minor);
+    CUDA_CHECK(cudaSetDevice(device));
+}
+
+std::shared_ptr<Engine> finish_open(unsigned char *d_arena, size_t bytes, int device, const std::string &path) {
+    auto e = std::make_shared<Engine>();
+    e->device = device; e->path = path;
+    bind_model(e->model, d_arena, bytes, device);
+    gemm_init();
+    return e;
+}
+
+}  // namespace
+
+std::shared_ptr<Engine> engine_open(const std::string &path, int device) {
+    check_device(device);
+    std::vector<unsigned char> img = build_arena_image(path);
+    unsigned char *d = dmalloc<unsigned char>(img.size());
+    CUDA_CHECK(cudaMemcpy(d, img.data(), img.size(), cudaMemcpyHostToDevice));
+    return finish_open(d, img.size(), device, path);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL weight broadcast: the only collective of the path, at init.
+// libnccl is dlopen'ed so that the library loads on hosts without NCCL / without a GPU.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, unsigned char[128] /* by value in the real ABI */, int) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char internal[128]; };
+typedef int (*CommInitRankFn)(void **, int, NcclId, int);
+
+NcclApi &nccl() {
+    static NcclApi api;
+    if (api.h) return api;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.h) break; }
+    if (!api.h) SS_THROW(-8, "cannot dlopen libnccl.so.2: %s", dlerror());
+    api.GetUniqueId = reinterpret_cast<int (*)(void *)>(dlsym(api.h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.h, "ncclCommInitRank"));
+    api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.h, "ncclBroadcast"));
+    api.CommDestroy = reinterpret_cast<int (*)(void *)>(dlsym(api.h, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<const char *(*)(int)>(dlsym(api.h, "ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.CommDestroy) SS_THROW(-8, "libnccl lacks expected symbols");
+    return api;
+}
+#define NCCL_CHECK(expr)                                                                                   \
+    do {                                                                                                   \
+        int _r = (expr);                                                                                   \
+        if (_r != 0) SS_THROW(-8, "NCCL error %d (%s) at %s:%d", _r, nccl().GetErrorString ? nccl().GetErrorString(_r) : "?", __FILE__, __LINE__); \
+    } while (0)
+}  // namespace
+
+void nccl_unique_id(unsigned char out[128]) {
+    NcclId id;
+    NCCL_CHECK(nccl().GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+}
+
+std::shared_ptr<Engine> engine_open_dist(const char *path, int device, int rank, int world, const unsigned char *nccl_id) {
+    check_device(device);
+    if (world <= 1) { if (!path) SS_THROW(-1, "model path required"); return engine_open(path, device); }
+    NcclApi &api = nccl();
+    NcclId id; memcpy(id.internal, nccl_id, 128);
+    void *comm = nullptr;
+    NCCL_CHECK(reinterpret_cast<CommInitRankFn>(api.CommInitRank)(&comm, world, id, rank));
+    cudaStream_t st; CUDA_CHECK(cudaStreamCreate(&st));
+    unsigned long long *d_sz = dmalloc<unsigned long long>(1);
+    std::vector<unsigned char> img;
+    unsigned long long sz = 0;
+    if (rank == 0) {
+        if (!path) SS_THROW(-1, "rank 0 needs the model path");
+        img = build_arena_image(path); sz = img.size();
+        CUDA_CHECK(cudaMemcpy(d_sz, &sz, 8, cudaMemcpyHostToDevice));
+    }
+    NCCL_CHECK(api.Broadcast(d_sz, d_sz, 8, /*ncclUint8*/ 1, 0, comm, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(cudaMemcpy(&sz, d_sz, 8, cudaMemcpyDeviceToHost));
+    unsigned char *d = dmalloc<unsigned char>(sz);
+    if (rank == 0) CUDA_CHECK(cudaMemcpy(d, img.data(), sz, cudaMemcpyHostToDevice));
+    NCCL_CHECK(api.Broadcast(d, d, sz, 1, 0, comm, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    api.CommDestroy(comm);
+    cudaFree(d_sz); cudaStreamDestroy(st);
+    return finish_open(d, sz, device, path ? path : "<nccl broadcast>");
+}
+
+// ------------------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------------------
+static Decoder *new_decoder(State &s, bool with_keep) {
+    const Model &m = s.engine->model; const HParams &hp = m.hp;
+    auto d = std::make_unique<Decoder>();
+    const size_t dd = hp.n_text_state, kv = (size_t)hp.n_text_layer * hp.n_text_ctx * dd;
+    DecodeBuffers &b = d->b;
+    b.ctl = dmalloc<DecCtl>(1);
+    b.x = dmalloc<float>(dd); b.q = dmalloc<float>(dd); b.h = dmalloc<float>(4 * dd);
+    b.part = dmalloc<float>((size_t)hp.n_text_head * std::max(kSelfSplit, kCrossSplit) * 66);
+    b.logits = dmalloc<float>(hp.n_vocab);
+    b.tok_out = dmalloc<TokData>(hp.n_text_ctx);
+    b.self_k = dmalloc<__half>(kv); b.self_v = dmalloc<__half>(kv);
+    CUDA_CHECK(cudaMemset(b.self_k, 0, kv * 2)); CUDA_CHECK(cudaMemset(b.self_v, 0, kv * 2));
+    b.cross_k = s.cross_k; b.cross_v = s.cross_v;
+    b.keep = with_keep ? s.keep : nullptr; b.keep_cap = with_keep ? s.keep_cap : 0;
+    d->h_ctl = hmalloc<DecCtl>(1); d->h_tok = hmalloc<TokData>(hp.n_text_ctx);
+    memset(d->h_ctl, 0, sizeof(DecCtl));
+    Decoder *raw = d.get();
+    s.dec.push_back(std::move(d));
+    return raw;
+}
+
+State *state_new(const std::shared_ptr<Engine> &e) {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    auto s = std::make_unique<State>();
+    s->engine = e;
+    const HParams &hp = e->model.hp;
+    const size_t T = hp.n_audio_ctx, d = hp.n_audio_state, H = hp.n_audio_head, dd = hp.n_text_state;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto &ev : s->ev) CUDA_CHECK(cudaEventCreate(&ev));
+    s->d_max = dmalloc<int>(1);
+    s->win = dmalloc<__half>((2 * T + 2) * hp.n_mels);
+    s->x1 = dmalloc<__half>((2 * T + 2) * d);
+    CUDA_CHECK(cudaMemset(s->x1, 0, (2 * T + 2) * d * 2));
+    s->x = dmalloc<float>(T * d); s->xn = dmalloc<__half>(T * d); s->qkv = dmalloc<__half>(T * 3 * d);
+    s->S = dmalloc<float>(H * T * (T + 4)); s->P = dmalloc<__half>(H * T * (T + 36));
+    s->att = dmalloc<__half>(T * d); s->ff = dmalloc<__half>(T * 4 * d);
+    s->enc_out = dmalloc<float>(T * d); s->enc16 = dmalloc<__half>(T * d);
+    s->cross_k = dmalloc<__half>((size_t)hp.n_text_layer * T * dd); s->cross_v = dmalloc<__half>((size_t)hp.n_text_layer * T * dd);
+    s->h_logits = hmalloc<float>(hp.n_vocab);
+    new_decoder(*s, true);
+    return s.release();
+}
+
+State::~State() {
+    if (!engine) return;
+    cudaSetDevice(engine->device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto &d : dec) {
+        if (d->graph) cudaGraphExecDestroy(d->graph);
+        DecodeBuffers &b = d->b;
+        cudaFree(b.ctl); cudaFree(b.x); cudaFree(b.q); cudaFree(b.h); cudaFree(b.part); cudaFree(b.logits); cudaFree(b.tok_out);
+        cudaFree(b.self_k); cudaFree(b.self_v);
+        cudaFreeHost(d->h_ctl); cudaFreeHost(d->h_tok);
+    }
+    void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, P, att, ff, enc16, x, S, enc_out, cross_k, cross_v, keep};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h_pcm) cudaFreeHost(h_pcm);
+    if (h_logits) cudaFreeHost(h_logits);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stages
+// ------------------------------------------------------------------------------------------------
+void run_log_mel(State &s, const float *pcm, size_t n) {
+    const Model &m = s.engine->model;
+    CUDA_CHECK(cudaSetDevice(s.engine->device));
+    if (n + 1 > s.pcm_cap) {
+        if (s.d_pcm) cudaFree(s.d_pcm);
+        s.pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.d_pcm = dmalloc<float>(s.pcm_cap);
+    }
+    if (n + 1 > s.h_pcm_cap) {
+        if (s.h_pcm) cudaFreeHost(s.h_pcm);
+        s.h_pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.h_pcm = hmalloc<float>(s.h_pcm_cap);
+    }
+    s.n_len = mel_n_len(n); s.n_len_org = mel_n_len_org(n);
+    const size_t need = (size_t)m.hp.n_mels * s.n_len;
+    if (need > s.mel_cap) { if (s.d_mel) cudaFree(s.d_mel); s.mel_cap = need; s.d_mel = dmalloc<float>(need); }
+    if (n) memcpy(s.h_pcm, pcm, n * sizeof(float));      // caller memory is pageable: stage through pinned
+    if (n) CUDA_CHECK(cudaMemcpyAsync(s.d_pcm, s.h_pcm, n * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    mel_enqueue(m, s.d_pcm, n, s.d_mel, s.n_len, s.d_max, s.stream, &s.n_launches);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void run_encode(State &s, int seek) {
+    const Model &m = s.engine->model; const HParams &hp = m.hp;
+    CUDA_CHECK(cudaSetDevice(s.engine->device));
+    cudaStream_t st = s.stream; int *nl = &s.n_launches;
+    const int T = hp.n_audio_ctx, d = hp.n_audio_state, H = hp.n_audio_head, C = hp.n_mels;
+    mel_window_enqueue(m, s.d_mel, s.n_len, seek, s.win, st, nl);
+    {   // conv1 (k3,s1,p1) + bias + GELU as implicit GEMM over overlapping rows of the padded window
+        GemmOperand A; A.ptr = s.win; A.rows = 2 * T; A.ld = C;
+        GemmOperand B; B.ptr = m.conv1.w; B.rows = d; B.ld = 3 * C;
+        GemmEpilogue ep; ep.bias = m.conv1.b; ep.gelu = 1; ep.out = s.x1; ep.out_type = GEMM_OUT_F16; ep.out_ld = d; ep.out_row_offset = 1;
+        gemm_enqueue(A, B, 2 * T, d, 3 * C, false, ep, st, nl);
+    }
+    {   // conv2 (k3,s2,p1) + bias + GELU + positional embedding -> residual stream (f32)
+        GemmOperand A; A.ptr = s.x1; A.rows = T; A.ld = 2 * d;
+        GemmOperand B; B.ptr = m.conv2.w; B.rows = d; B.ld = 3 * d;
+        GemmEpilogue ep; ep.bias = m.conv2.b; ep.gelu = 1; ep.pos = m.e_pos; ep.pos_rows = T; ep.out = s.x; ep.out_type = GEMM_OUT_F32; ep.out_ld = d;
+        gemm_enqueue(A, B, T, d, 3 * d, false, ep, st, nl);
+    }
+    const long ldS = T + 4, ldP = T + 36;
+    for (int il = 0; il < hp.n_audio_layer; il++) {
+        const EncLayer &L = m.enc[il];
+        layernorm_f16_enqueue(s.x, s.xn, T, d, L.attn_ln, st, nl);
+        {
+            GemmOperand A; A.ptr = s.xn; A.rows = T; A.ld = d;
+            GemmOperand B; B.ptr = L.qkv.w; B.rows = 3 * d; B.ld = d;
+            GemmEpilogue ep; ep.bias = L.qkv.b; ep.out = s.qkv; ep.out_ld = 3 * d;
+            gemm_enqueue(A, B, T, 3 * d, d, false, ep, st, nl);
+        }
+        {   // S = Q K^T / sqrt(64), all heads batched
+            GemmOperand A; A.ptr = s.qkv; A.rows = T; A.ld = 3 * d; A.batch0 = H; A.stride0 = 64;
+            GemmOperand B; B.ptr = s.qkv + d; B.rows = T; B.ld = 3 * d; B.batch0 = H; B.stride0 = 64;
+            GemmEpilogue ep; ep.alpha = 1.0f / sqrtf(64.0f); ep.alpha_cols = T; ep.out = s.S; ep.out_type = GEMM_OUT_F32; ep.out_ld = ldS; ep.out_stride0 = (long)T * ldS;
+            gemm_enqueue(A, B, T, T, 64, false, ep, st, nl);
+        }
+        softmax_rows_enqueue(s.S, ldS, s.P, ldP, (long)H * T, T, st, nl);
+        {   // O = P V  (V consumed MN-major straight from the QKV buffer)
+            GemmOperand A; A.ptr = s.P; A.rows = T; A.ld = ldP; A.batch0 = H; A.stride0 = (long)T * ldP;
+            GemmOperand B; B.ptr = s.qkv + 2 * d; B.rows = T; B.ld = 3 * d; B.batch0 = H; B.stride0 = 64;
+            GemmEpilogue ep; ep.out = s.att; ep.out_ld = d; ep.out_stride0 = 64;
+            gemm_enqueue(A, B, T, 64, (int)ldP, true, ep, st, nl);
+        }
+        {
+            GemmOperand A; A.ptr = s.att; A.rows = T; A.ld = d;
+            GemmOperand B; B.ptr = L.o.w; B.rows = d; B.ld = d;
+            GemmEpilogue ep; ep.bias = L.o.b; ep.residual = 1; ep.out = s.x; ep.out_type = GEMM_OUT_F32; ep.out_ld = d;
+            gemm_enqueue(A, B, T, d, d, false, ep, st, nl);
+        }
+        layernorm_f16_enqueue(s.x, s.xn, T, d, L.mlp_ln, st, nl);
+        {
+            GemmOperand A; A.ptr = s.xn; A.rows = T; A.ld = d;
+            GemmOperand B; B.ptr = L.fc1.w; B.rows = 4 * d; B.ld = d;
+            GemmEpilogue ep; ep.bias = L.fc1.b; ep.gelu = 1; ep.out = s.ff; ep.out_ld = 4 * d;
+            gemm_enqueue(A, B, T, 4 * d, d, false, ep, st, nl);
+        }
+        {
+            GemmOperand A; A.ptr = s.ff; A.rows = T; A.ld = 4 * d;
+            GemmOperand B; B.ptr = L.fc2.w; B.rows = d; B.ld = 4 * d;
+            GemmEpilogue ep; ep.bias = L.fc2.b; ep.residual = 1; ep.out = s.x; ep.out_type = GEMM_OUT_F32; ep.out_ld = d;
+            gemm_enqueue(A, B, T, d, 4 * d, false, ep, st, nl);
+        }
+    }
+    layernorm_f32_enqueue(s.x, s.enc_out, T, d, m.ln_post, st, nl);
+    f32_to_f16_enqueue(s.enc_out, s.enc16, (size_t)T * d, st, nl);
+    // cross-attention K/V for every decoder layer, written head-major into the persistent cache
+    const int dd = hp.n_text_state;
+    const float s4 = powf((float)(dd / hp.n_text_head), -0.25f);
+    for (int il = 0; il < hp.n_text_layer; il++) {
+        const DecLayer &L = m.dec[il];
+        GemmOperand A; A.ptr = s.enc16; A.rows = T; A.ld = d;
+        GemmOperand Bk; Bk.ptr = L.ckv.w; Bk.rows = dd; Bk.ld = d;
+        GemmEpilogue ek; ek.alpha = s4; ek.alpha_cols = dd; ek.out = s.cross_k + (size_t)il * T * dd; ek.head_major = 1; ek.head_rows = T;
+        gemm_enqueue(A, Bk, T, dd, d, false, ek, st, nl);
+        GemmOperand Bv; Bv.ptr = L.ckv.w + (size_t)dd * d; Bv.rows = dd; Bv.ld = d;
+        GemmEpilogue evv; evv.bias = L.ckv.b + dd; evv.out = s.cross_v + (size_t)il * T * dd; evv.head_major = 1; evv.head_rows = T;
+        gemm_enqueue(A, Bv, T, dd, d, false, evv, st, nl);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder driving
+// ------------------------------------------------------------------------------------------------
+static void ensure_graph(State &s, Decoder &d) {
+    if (d.graph) return;
+    const Model &m = s.engine->model;
+    d.b.cross_k = s.cross_k; d.b.cross_v = s.cross_v;
+    cudaGraph_t g;
+    int dummy = 0;
+    CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+    decode_step_enqueue(m, d.b, s.stream, &dummy);
+    CUDA_CHECK(cudaStreamEndCapture(s.stream, &g));
+    CUDA_CHECK(cudaGraphInstantiate(&d.graph, g, 0));
+    CUDA_CHECK(cudaGraphDestroy(g));
+}
+
+// run the step graph until the device says done (or max_steps); returns steps launched
+static int run_steps(State &s, Decoder &d, int max_steps, int chunk) {
+    const Model &m = s.engine->model;
+    int launched = 0;
+    while (launched < max_steps) {
+        const int k = std::min(chunk, max_steps - launched);
+        for (int i = 0; i < k; i++) CUDA_CHECK(cudaGraphLaunch(d.graph, s.stream));
+        launched += k;
+        CUDA_CHECK(cudaMemcpyAsync(d.h_ctl, d.b.ctl, offsetof(DecCtl, prompt), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        if (d.h_ctl->done) break;
+    }
+    s.n_launches += launched * decode_step_num_launches(m);
+    return launched;
+}
+
+static void upload_ctl(State &s, Decoder &d) {
+    CUDA_CHECK(cudaMemcpyAsync(d.b.ctl, d.h_ctl, sizeof(DecCtl), cudaMemcpyHostToDevice, s.stream));
+}
+
+void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *logits_out) {
+    const Model &m = s.engine->model; const HParams &hp = m.hp;
+    CUDA_CHECK(cudaSetDevice(s.engine->device));
+    if (n <= 0 || n > kMaxPrompt || n_past < 0 || n_past + n > hp.n_text_ctx) SS_THROW(-1, "decode: bad token count / position");
+    Decoder &d = *s.dec[0];
+    ensure_graph(s, d);
+    DecCtl &c = *d.h_ctl;
+    memset(&c, 0, sizeof c);
+    c.pos = n_past; c.pos0 = n_past; c.token = tokens[0]; c.n_prompt = n; c.sample = 0; c.last_id = -1; c.penult_id = -1;
+    c.n_max = hp.n_text_ctx / 2 - 4;
+    for (int i = 0; i < n; i++) {
+        if (tokens[i] < 0 || tokens[i] >= hp.n_vocab) SS_THROW(-1, "decode: token id out of range");
+        c.prompt[i] = tokens[i];
+    }
+    upload_ctl(s, d);
+    run_steps(s, d, n, n);
+    s.n_decoded += n;
+    CUDA_CHECK(cudaMemcpyAsync(s.h_logits, d.b.logits, (size_t)hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    if (logits_out) memcpy(logits_out, s.h_logits, (size_t)hp.n_vocab * sizeof(float));
+}
+
+// ---- host restatement of whisper_process_logits / whisper_sample_token for the t>0 fallback path
+static void process_logits_host(const Model &m, const FullParams &P, Decoder &dc, const float *raw, float temperature) {
+    const Vocab &v = m.vocab; const int nv = m.hp.n_vocab;
+    dc.logits.assign(raw, raw + nv); dc.logprobs.resize(nv); dc.probs.resize(nv);
+    float *logits = dc.logits.data(), *logprobs = dc.logprobs.data(), *probs = dc.probs.data();
+    const auto &tk = dc.seq.tokens;
+    const bool is_initial = tk.empty();
+    if (temperature > 0.0f) for (int i = 0; i < nv; i++) logits[i] /= temperature;
+    if (P.suppress_blank && is_initial) { logits[v.eot] = -INFINITY; if (v.blank >= 0) logits[v.blank] = -INFINITY; }
+    logits[v.not_] = -INFINITY; logits[v.sot] = -INFINITY; logits[v.nosp] = -INFINITY;
+    if (!P.tdrz_enable) logits[v.solm] = -INFINITY;
+    logits[v.translate] = -INFINITY; logits[v.transcribe] = -INFINITY; logits[v.prev] = -INFINITY;
+    for (int i = 0; i < kNumLangSuppress; i++) { const int t = v.sot + 1 + i; if (t < nv) logits[t] = -INFINITY; }
+    {
+        const bool last_ts = !tk.empty() && tk.back().id >= v.beg;
+        const bool penult_ts = tk.size() < 2 || tk[tk.size() - 2].id >= v.beg;
+        if (last_ts) {
+            if (penult_ts) for (int i = v.beg; i < nv; i++) logits[i] = -INFINITY;
+            else for (int i = 0; i < v.eot; i++) logits[i] = -INFINITY;
+        }
+    }
+    if (is_initial && P.max_initial_ts > 0.0f) {
+        const float precision = (float)kChunkSec / m.hp.n_audio_ctx;
+        const int tid0 = (int)std::round(P.max_initial_ts / precision);
+        for (int i = v.beg + tid0 + 1; i < nv; i++) logits[i] = -INFINITY;
+    }
+    if (dc.has_ts) { const int tid0 = dc.seek_delta / 2; for (int i = v.beg; i < v.beg + tid0 && i < nv; i++) logits[i] = -INFINITY; }
+    {
+        const float mx = *std::max_element(logits, logits + nv);
+        float lse = 0.0f;
+        for (int i = 0; i < nv; i++) if (logits[i] > -INFINITY) lse += expf(logits[i] - mx);
+        lse = logf(lse) + mx;
+        for (int i = 0; i < nv; i++) logprobs[i] = logits[i] > -INFINITY ? logits[i] - lse : -INFINITY;
+    }
+    {
+        float ts_lp = -INFINITY;
+        {
+            float lse = 0.0f;
+            const float mx = *std::max_element(logprobs + v.beg, logprobs + nv);
+            for (int i = v.beg; i < nv; i++) if (logprobs[i] > -INFINITY) lse += expf(logprobs[i] - mx);
+            if (lse > 0.0f) ts_lp = logf(lse) + mx;
+        }
+        const float mt = *std::max_element(logprobs, logprobs + v.beg);
+        if (ts_lp > mt) for (int i = 0; i < v.beg; i++) { logits[i] = -INFINITY; logprobs[i] = -INFINITY; }
+    }
+    for (int i = 0; i < nv; i++) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
+}
+
+static TokData sample_token_host(const Model &m, Decoder &dc, bool best) {
+    const Vocab &v = m.vocab; const int nv = m.hp.n_vocab;
+    TokData r{0, 0, 0.f, 0.f, 0.f, 0.f};
+    {
+        double sum_ts = 0.0, max_ts = 0.0;
+        for (int i = v.beg; i < nv; i++) { sum_ts += dc.probs[i]; if (max_ts < dc.probs[i]) { max_ts = dc.probs[i]; r.tid = i; } }
+        r.pt = (float)(max_ts / (sum_ts + 1e-10)); r.ptsum = (float)sum_ts;
+    }
+    if (best) {
+        for (int i = 0; i < nv; i++) if (r.p < dc.probs[i]) { r.id = i; r.p = dc.probs[i]; r.plog = dc.logprobs[i]; }
+    } else {
+        std::discrete_distribution<> dist(dc.probs.begin(), dc.probs.end());
+        r.id = dist(dc.rng); r.p = dc.probs[r.id]; r.plog = dc.logprobs[r.id];
+    }
+    if (r.id >= v.beg) { r.tid = r.id; r.pt = r.p; }
+    return r;
+}
+
+static void sequence_score(const FullParams &P, Sequence &q) {
+    if (q.result_len == 0) return;
+    double result = 0.0;
+    for (int i = 0; i < q.result_len; i++) result += q.tokens[i].plog;
+    q.sum_logprobs = result; q.avg_logprobs = result / q.result_len;
+    double penalty = q.result_len;
+    if (P.length_penalty > 0.0f) penalty = pow((5.0 + penalty) / 6.0, P.length_penalty);
+    q.score = result / penalty;
+    int cnt = 0; double entropy = 0.0;
+    std::map<int, int> counts;
+    for (int i = std::max(0, q.result_len - 32); i < q.result_len; i++) { counts[q.tokens[i].id]++; cnt++; }
+    for (const auto &kv : counts) { const double p = kv.second / (double)cnt; entropy -= p * log(p); }
+    q.entropy = entropy;
+}
+
+// one forward step of decoder `d` feeding `token` at position n_past; raw logits land in s.h_logits
+static void step_host_sampled(State &s, Decoder &d, const int *tokens, int n, int n_past) {
+    ensure_graph(s, d);
+    DecCtl &c = *d.h_ctl;
+    memset(&c, 0, offsetof(DecCtl, prompt));
+    c.pos = n_past; c.pos0 = n_past; c.token = tokens[0]; c.n_prompt = n; c.sample = 0; c.last_id = -1; c.penult_id = -1;
+    for (int i = 0; i < n; i++) c.prompt[i] = tokens[i];
+    upload_ctl(s, d);
+    run_steps(s, d, n, n);
+    s.n_decoded += 1;
+    CUDA_CHECK(cudaMemcpyAsync(s.h_logits, d.b.logits, (size_t)s.engine->model.hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+static void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos) {
+    const HParams &hp = s.engine->model.hp;
+    const size_t pitch = (size_t)hp.n_text_ctx * 64 * 2, width = (size_t)n_pos * 64 * 2, height = (size_t)hp.n_text_layer * hp.n_text_head;
+    CUDA_CHECK(cudaMemcpy2DAsync(to.b.self_k, pitch, from.b.self_k, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(to.b.self_v, pitch, from.b.self_v, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// whisper_full
+// ------------------------------------------------------------------------------------------------
+int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P, bool stream_mode) {
+    const Model &m = s.engine->model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
+    CUDA_CHECK(cudaSetDevice(s.engine->device));
+    s.raw.clear(); s.out.clear(); s.full_text.clear(); s.result_tokens.clear();
+    s.n_fallbacks = 0; s.n_decoded = 0; s.n_windows = 0; s.n_launches = 0; s.n_keep = 0; s.h_keep.clear();
+    s.ms_mel = s.ms_enc = s.ms_dec = 0;
+    if (P.beam_size > 1) SS_THROW(-1, "beam search is not implemented in this build (beam_size=%d)", P.beam_size);
+
+    int lang = 0;
+    if (v.multilingual) { lang = lang_id(P.language.c_str()); if (lang < 0) SS_THROW(-6, "unknown language '%s'", P.language.c_str()); }
+
+    if (P.keep_logits && !s.keep) {
+        s.keep_cap = hp.n_text_ctx / 2; s.keep = dmalloc<float>((size_t)s.keep_cap * hp.n_vocab);
+        s.dec[0]->b.keep = s.keep; s.dec[0]->b.keep_cap = s.keep_cap;
+        if (s.dec[0]->graph) { cudaGraphExecDestroy(s.dec[0]->graph); s.dec[0]->graph = nullptr; }
+    }
+
+    CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
+    run_log_mel(s, pcm, n_samples);
+    CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    { float ms; cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.ms_mel += ms; }
+
+    const int seek_start = 0, seek_end = s.n_len_org;
+    if (seek_end < seek_start + 100) return postprocess(s, stream_mode);
+
+    std::vector<float> temps;
+    if (P.temperature_inc > 0.0f) { for (float t = P.temperature; t < 1.0f + 1e-6f; t += P.temperature_inc) temps.push_back(t); }
+    else temps.push_back(P.temperature);
+
+    int n_decoders = std::max(1, P.best_of);
+    if (P.no_context) s.prompt_past.clear();
+
+    std::vector<int> prompt_init = {v.sot};
+    if (v.multilingual) { prompt_init.push_back(v.sot + 1 + lang); prompt_init.push_back(v.transcribe); }
+
+    const int n_max = hp.n_text_ctx / 2 - 4;
+    const float precision = (float)kChunkSec / hp.n_audio_ctx;
+    const int tid0_init = P.max_initial_ts > 0.0f ? (int)std::round(P.max_initial_ts / precision) : -1;
+    int seek = seek_start;
+    std::vector<int> prompt;
+
+    while (true) {
+        if (seek + 100 >= seek_end) break;
+        CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
+        run_encode(s, seek);
+        CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
+        s.n_windows++;
+        if (seek > seek_start && seek + 500 >= seek_end) s.prompt_past.clear();
+
+        int best_decoder_id = 0;
+        for (size_t it = 0; it < temps.size(); it++) {
+            const float t_cur = temps[it];
+            const int n_cur = t_cur > 0.0f ? n_decoders : 1;
+            if (it > 0) s.n_fallbacks++;
+            while ((int)s.dec.size() < n_cur) new_decoder(s, false);
+            for (int j = 0; j < n_cur; j++) {
+                Decoder &dc = *s.dec[j];
+                dc.seq = Sequence{}; dc.seq.sum_logprobs = -INFINITY; dc.seq.avg_logprobs = -INFINITY; dc.seq.score = -INFINITY;
+                dc.seek_delta = 100 * kChunkSec; dc.failed = false; dc.completed = false; dc.has_ts = false;
+            }
+            prompt.clear();
+            if (!s.prompt_past.empty() && t_cur < 0.5f && P.n_max_text_ctx > 0) {
+                const int n_take = std::min({P.n_max_text_ctx, hp.n_text_ctx / 2, (int)s.prompt_past.size()});
+                prompt.push_back(v.prev);
+                prompt.insert(prompt.end(), s.prompt_past.end() - n_take, s.prompt_past.end());
+            }
+            prompt.insert(prompt.end(), prompt_init.begin(), prompt_init.end());
+            const int n_prompt = (int)prompt.size();
+
+            CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
+            if (t_cur < 1e-6f) {
+                // ---------------- greedy at temperature 0: whole loop on the device ----------------
+                Decoder &dc = *s.dec[0];
+                dc.b.suppress_blank = P.suppress_blank; dc.b.tdrz = P.tdrz_enable; dc.b.tid0_init = tid0_init;
+                ensure_graph(s, dc);
+                DecCtl &c = *dc.h_ctl;
+                memset(&c, 0, sizeof c);
+                c.pos = 0; c.pos0 = 0; c.token = prompt[0]; c.n_prompt = n_prompt; c.sample = 1; c.last_id = -1; c.penult_id = -1;
+                c.seek = seek; c.seek_end = seek_end; c.n_max = n_max; c.seek_delta = 100 * kChunkSec;
+                c.keep_logits = (P.keep_logits && it == 0) ? 1 : 0; c.n_kept = 0;
+                for (int i = 0; i < n_prompt; i++) c.prompt[i] = prompt[i];
+                upload_ctl(s, dc);
+                const int steps = run_steps(s, dc, n_prompt + n_max - 1, 16);
+                (void)steps;
+                const int ns = dc.h_ctl->n_sampled;
+                s.n_decoded += n_prompt - 1 + ns;
+                if (ns > 0) {
+                    CUDA_CHECK(cudaMemcpyAsync(dc.h_tok, dc.b.tok_out, (size_t)ns * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
+                    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+                }
+                dc.seq.tokens.assign(dc.h_tok, dc.h_tok + ns);
+                for (int i = 0; i < ns; i++) dc.seq.sum_logprobs_all += dc.h_tok[i].plog;
+                dc.seq.result_len = dc.h_ctl->result_len; dc.seek_delta = dc.h_ctl->seek_delta;
+                dc.failed = dc.h_ctl->failed; dc.completed = dc.h_ctl->completed; dc.has_ts = dc.h_ctl->has_ts;
+                if (c.keep_logits) {
+                    const int nk = std::min(dc.h_ctl->n_kept, s.keep_cap);
+                    const size_t old = s.h_keep.size();
+                    s.h_keep.resize(old + (size_t)nk * hp.n_vocab);
+                    CUDA_CHECK(cudaMemcpy(s.h_keep.data() + old, s.keep, (size_t)nk * hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost));
+                    s.n_keep += nk;
+                }
+            } else {
+                // ---------------- t > 0: best_of sampled decoders, host-side sampling ----------------
+                for (int j = 0; j < n_cur; j++) { s.dec[j]->b.suppress_blank = P.suppress_blank; s.dec[j]->b.tdrz = P.tdrz_enable; s.dec[j]->b.tid0_init = tid0_init; }
+                step_host_sampled(s, *s.dec[0], prompt.data(), n_prompt, 0);
+                s.n_decoded += n_prompt - 1;
+                process_logits_host(m, P, *s.dec[0], s.h_logits, t_cur);
+                for (int j = 1; j < n_cur; j++) {
+                    kv_copy(s, *s.dec[0], *s.dec[j], n_prompt);
+                    s.dec[j]->probs = s.dec[0]->probs; s.dec[j]->logits = s.dec[0]->logits; s.dec[j]->logprobs = s.dec[0]->logprobs;
+                }
+                for (int i = 0; i < n_max; i++) {
+                    for (int j = 0; j < n_cur; j++) {
+                        Decoder &dc = *s.dec[j];
+                        if (dc.completed || dc.failed) continue;
+                        dc.seq.tokens.push_back(sample_token_host(m, dc, false));
+                        dc.seq.sum_logprobs_all += dc.seq.tokens.back().plog;
+                    }
+                    for (int j = 0; j < n_cur; j++) {
+                        Decoder &dc = *s.dec[j];
+                        if (dc.completed || dc.failed) continue;
+                        const TokData &tk = dc.seq.tokens.back();
+                        if (tk.id > v.beg) {
+                            const int sd_new = 2 * (tk.id - v.beg);
+                            if (dc.has_ts && dc.seek_delta > sd_new && dc.seq.result_len < i) { dc.failed = true; continue; }
+                            dc.seek_delta = sd_new; dc.seq.result_len = i + 1; dc.has_ts = true;
+                        }
+                        if (tk.id == v.eot || (P.max_tokens > 0 && i >= P.max_tokens) || (dc.has_ts && seek + dc.seek_delta + 100 >= seek_end)) {
+                            if (dc.seq.result_len == 0) {
+                                if (seek + dc.seek_delta + 100 >= seek_end) dc.seq.result_len = i + 1;
+                                else { dc.failed = true; continue; }
+                            }
+                            if (P.single_segment) { dc.seq.result_len = i + 1; dc.seek_delta = 100 * kChunkSec; }
+                            dc.completed = true; continue;
+                        }
+                        if (i == n_max - 1 && (dc.seq.result_len == 0 || dc.seek_delta < 100 * kChunkSec / 2)) { dc.failed = true; continue; }
+                    }
+                    bool all = true;
+                    for (int j = 0; j < n_cur; j++) if (!(s.dec[j]->completed || s.dec[j]->failed)) all = false;
+                    if (all) break;
+                    const int n_past = n_prompt + i;
+                    for (int j = 0; j < n_cur; j++) {
+                        Decoder &dc = *s.dec[j];
+                        if (dc.failed || dc.completed) continue;
+                        const int tok = dc.seq.tokens.back().id;
+                        step_host_sampled(s, dc, &tok, 1, n_past);
+                        process_logits_host(m, P, dc, s.h_logits, t_cur);
+                    }
+                }
+            }
+            CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
+            CUDA_CHECK(cudaStreamSynchronize(s.stream));
+            { float ms; cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.ms_dec += ms; }
+            if (it == 0) { float ms; cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.ms_enc += ms; }
+
+            {
+                double best_score = -INFINITY;
+                for (int j = 0; j < n_cur; j++) {
+                    Decoder &dc = *s.dec[j];
+                    if (dc.failed) continue;
+                    dc.seq.tokens.resize(std::min<size_t>(dc.seq.tokens.size(), (size_t)dc.seq.result_len));
+                    sequence_score(P, dc.seq);
+                    if (dc.seq.entropy < P.entropy_thold) { dc.failed = true; continue; }
+                    if (best_score < dc.seq.score) { best_score = dc.seq.score; best_decoder_id = j; }
+                }
+            }
+            bool success = true;
+            if (it != temps.size() - 1) {
+                const Decoder &dc = *s.dec[best_decoder_id];
+                if (dc.failed || dc.seq.avg_logprobs < P.logprob_thold) success = false;
+            }
+            if (success) break;
+        }
+        {
+            const Decoder &bd = *s.dec[best_decoder_id];
+            const int seek_delta = bd.seek_delta, result_len = bd.seq.result_len;
+            const auto &tc = bd.seq.tokens;
+            std::vector<int> keep;
+            if (prompt.front() == v.prev) keep.assign(prompt.begin() + 1, prompt.end() - prompt_init.size());
+            s.prompt_past = keep;
+            for (int i = 0; i < result_len && i < (int)tc.size(); i++) s.prompt_past.push_back(tc[i].id);
+            if (!tc.empty()) {
+                s.result_tokens.insert(s.result_tokens.end(), tc.begin(), tc.end());
+                int64_t t0 = seek + 2 * (tc.front().tid - v.beg);
+                std::string text; bool turn = false;
+                for (int i = 0; i < (int)tc.size(); i++) {
+                    if (tc[i].id < v.eot) text += v.id_to_token[tc[i].id];
+                    if (P.tdrz_enable && tc[i].id == v.solm) turn = true;
+                    if (tc[i].id > v.beg && !P.single_segment) {
+                        const int64_t t1 = seek + 2 * (tc[i].tid - v.beg);
+                        if (!text.empty()) s.raw.push_back({t0, t1, text, turn});
+                        text.clear();
+                        while (i < (int)tc.size() && tc[i].id > v.beg) i++;
+                        i--;
+                        t0 = t1; turn = false;
+                    }
+                }
+                if (!text.empty()) s.raw.push_back({t0, (int64_t)seek + seek_delta, text, turn});
+            }
+            seek += seek_delta;
+        }
+    }
+    return postprocess(s, stream_mode);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rust-side post-processing (whisper.rs:9-14, 41-43, 84-128, 175-201)
+// ------------------------------------------------------------------------------------------------
+bool is_valid_utf8(const std::string &t) {
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(t.data());
+    size_t n = t.size(), i = 0;
+    while (i < n) {
+        unsigned char c = p[i];
+        if (c < 0x80) { i++; continue; }
+        int len; uint32_t cp;
+        if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; }
+        else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; }
+        else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; }
+        else return false;
+        if (i + len > n) return false;
+        for (int k = 1; k < len; k++) { if ((p[i + k] & 0xC0) != 0x80) return false; cp = (cp << 6) | (p[i + k] & 0x3F); }
+        if ((len == 2 && cp < 0x80) || (len == 3 && cp < 0x800) || (len == 4 && cp < 0x10000)) return false;
+        if (cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+        i += len;
+    }
+    return true;
+}
+
+static const char *kPromo[14] = {
+    "请不吝点赞", "請不吝點贊", "點贊", "訂閱", "订阅", "打赏", "打賞", "打賞支持明鏡與點點欄目", "打赏支持明镜与点点栏目",
+    "並且按下小鈴鐺才能收到最新消息哦!", "請按讚、訂閱、分享!", "明镜需要您的支持 欢迎收看订阅明镜",
+    "請按讚,訂閱,分享,打開小鈴鐺,並且按下小鈴鐺才能收到最新消息謝謝觀看",
+    "請按讚,訂閱,分享,打開小鈴鐺,並且按下小鈴鐺才能收到最新消息哦!"};
+
+static bool contains(const std::string &t, const char *needle) { return t.find(needle) != std::string::npos; }
+static bool ends_with(const std::string &t, const char *suffix) {
+    const size_t n = strlen(suffix);
+    return t.size() >= n && memcmp(t.data() + t.size() - n, suffix, n) == 0;
+}
+static std::string add_punctuation(const std::string &text) {
+    if (ends_with(text, "。") || ends_with(text, "！") || ends_with(text, "？") || ends_with(text, "，")) return text;
+    const bool q = contains(text, "吗") || contains(text, "呢") || contains(text, "什么") || contains(text, "为何") || contains(text, "怎么");
+    const bool e = contains(text, "啊") || contains(text, "哇") || contains(text, "太") || contains(text, "真") || contains(text, "好") || contains(text, "真是");
+    std::string r = text;
+    if (q) r += "？"; else if (e) r += "！"; else r += " ";
+    return r;
+}
+
+int postprocess(State &s, bool stream_mode) {
+    s.out.clear(); s.full_text.clear();
+    const int n = (int)s.raw.size();
+    int speaker = 0;
+    for (int i = 0; i < n; i++) {
+        const std::string &text = s.raw[i].text;
+        if (!is_valid_utf8(text) || text.find('\0') != std::string::npos) {   // full_get_segment_text -> Err -> `?` (whisper.rs:85)
+            s.out.clear(); s.full_text.clear();
+            SS_THROW(-7, "segment %d text is not valid UTF-8", i);
+        }
+        bool promo = false;
+        for (const char *p : kPromo) if (contains(text, p)) { promo = true; break; }
+        if (promo) continue;
+        if (i > 0 && s.raw[i - 1].speaker_turn_next) speaker++;
+        const std::string processed = add_punctuation(text);
+        if (stream_mode) {
+            if (i == n - 1) { s.out.push_back({processed, speaker, (double)s.raw[i].t0, (double)s.raw[i].t1}); s.full_text = processed; }
+        } else {
+            s.out.push_back({processed, speaker, (double)s.raw[i].t0, (double)s.raw[i].t1});
+            s.full_text += processed;
+        }
+    }
+    return 0;
+}
+
+}  // namespace ss

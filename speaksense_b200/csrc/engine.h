@@ -1,0 +1,92 @@
+// engine.h - host side of the engine: sessions (ss_state), KV caches, the whisper_full decode loop,
+// segment assembly and the reference's Rust-side post-processing.
+#pragma once
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace ss {
+
+struct Engine {
+    Model model;
+    int device = 0;
+    std::string path;
+};
+
+struct FullParams {   // == build_params (whisper.rs:131-173) + overrides (:60-71)
+    std::string language = "en";
+    bool tdrz_enable = false, no_context = false, single_segment = false;
+    int best_of = 5, beam_size = 0;
+    float temperature = 0.0f, temperature_inc = 0.2f, entropy_thold = 2.4f, logprob_thold = -1.0f;
+    float max_initial_ts = 1.0f, length_penalty = -1.0f;
+    bool suppress_blank = true;
+    int n_max_text_ctx = 16384, max_tokens = 0;
+    bool keep_logits = false;
+};
+
+struct Sequence {
+    std::vector<TokData> tokens;
+    int result_len = 0;
+    double sum_logprobs_all = 0, sum_logprobs = 0, avg_logprobs = 0, entropy = 0, score = 0;
+};
+
+struct Decoder {
+    DecodeBuffers b{};
+    cudaGraphExec_t graph = nullptr;
+    DecCtl *h_ctl = nullptr;          // pinned mirror
+    TokData *h_tok = nullptr;         // pinned
+    Sequence seq;
+    int seek_delta = 0;
+    bool failed = false, completed = false, has_ts = false;
+    std::vector<float> probs, logits, logprobs;   // host-sampled fallback path
+    std::mt19937 rng{0};
+};
+
+struct RawSegment { int64_t t0, t1; std::string text; bool speaker_turn_next; };
+struct OutSegment { std::string text; int speaker_id; double start, end; };
+
+struct State {
+    std::shared_ptr<Engine> engine;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // audio / mel
+    float *d_pcm = nullptr; size_t pcm_cap = 0; float *h_pcm = nullptr; size_t h_pcm_cap = 0;
+    float *d_mel = nullptr; size_t mel_cap = 0; int n_len = 0, n_len_org = 0; int *d_max = nullptr;
+    // encoder scratch (one window)
+    __half *win = nullptr, *x1 = nullptr, *xn = nullptr, *qkv = nullptr, *P = nullptr, *att = nullptr, *ff = nullptr, *enc16 = nullptr;
+    float *x = nullptr, *S = nullptr, *enc_out = nullptr;
+    __half *cross_k = nullptr, *cross_v = nullptr;
+    // decoders
+    std::vector<std::unique_ptr<Decoder>> dec;
+    float *keep = nullptr; int keep_cap = 0; std::vector<float> h_keep; int n_keep = 0;
+    float *h_logits = nullptr;   // pinned [n_vocab]
+    // results
+    std::vector<int> prompt_past;
+    std::vector<RawSegment> raw;
+    std::vector<OutSegment> out;
+    std::string full_text;
+    std::vector<TokData> result_tokens;
+    int n_fallbacks = 0, n_decoded = 0, n_windows = 0, n_launches = 0;
+    float ms_mel = 0, ms_enc = 0, ms_dec = 0;
+
+    ~State();
+};
+
+std::shared_ptr<Engine> engine_open(const std::string &path, int device);
+std::shared_ptr<Engine> engine_open_dist(const char *path, int device, int rank, int world, const unsigned char *nccl_id);
+void nccl_unique_id(unsigned char out[128]);
+State *state_new(const std::shared_ptr<Engine> &e);
+
+void run_log_mel(State &s, const float *pcm, size_t n);
+void run_encode(State &s, int seek);
+void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *logits_out);
+int transcribe(State &s, const float *pcm, size_t n, const FullParams &fp, bool stream_mode);
+
+// Rust-side post-processing of whisper.rs:84-128 on s.raw -> s.out / s.full_text
+int postprocess(State &s, bool stream_mode);
+bool is_valid_utf8(const std::string &t);
+
+}  // namespace ss

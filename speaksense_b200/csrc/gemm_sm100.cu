@@ -1,0 +1,310 @@
+// gemm_sm100.cu - TMA-fed tcgen05 GEMM for sm_100a: D = A . B^T with f16 operands, f32 accumulation in
+// TMEM and a fused epilogue (bias / scale / GELU / positional add / residual / f16 or f32 store, row- or
+// head-major).  This is the encoder's workhorse (BASELINE.json north_star stage 2; SURVEY.md §2.4 rows
+// mul_mm / im2col / add / gelu / cpy): conv stem as implicit GEMM over an overlapping-row TMA view,
+// QKV / out / MLP projections, QK^T, PV and the cross-KV projection all go through this kernel.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  128 x BN output tile, BLOCK_K = 64 (one
+// 128-byte swizzle atom), kStages-deep mbarrier ring; two CTAs are co-resident per SM so one tile's
+// epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace ss {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+// K-major tile: rows of 128 B, 8-row atoms 1024 B apart (SBO), LBO unused (=1).
+// MN-major tile (B = V[k][n], n contiguous 64 elements = 128 B): 8 k-rows per atom, atoms 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct GemmDev {
+    int M, N, K;
+    int nb0;                    // inner batch count (blockIdx.z = b1 * nb0 + b0)
+    const float *bias; float alpha; int alpha_cols; int gelu;
+    const float *pos; int pos_rows; int residual; int out_f16;
+    void *out; long out_ld, out_stride0, out_stride1; int head_major; long head_rows; int out_row_offset;
+};
+
+__device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ float gelu_ggml(float x) {
+    const float xh = r16(x);
+    return r16(0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh))));
+}
+
+template <int BN, int kStages, bool B_MN>
+__global__ void __launch_bounds__(kThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t kABytes = BM * BK * 2;            // 16 KB
+    constexpr uint32_t kBBytes = BN * BK * 2;
+    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;    // power of two >= 32
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + kStages * kABytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + kStages * kBBytes);
+    uint64_t *empty = full + kStages;
+    uint64_t *tmem_full = empty + kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int b0 = blockIdx.z % p.nb0, b1 = blockIdx.z / p.nb0;
+    const int nkb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], kABytes + kBBytes);
+                tma_load_4d(&tmA, &full[s], sA + s * kABytes, kb * BK, m0, b0, b1);
+                if (B_MN) tma_load_4d(&tmB, &full[s], sB + s * kBBytes, n0, kb * BK, b0, b1);
+                else      tma_load_4d(&tmB, &full[s], sB + s * kBBytes, kb * BK, n0, b0, b1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b F16 (0),
+            // a K-major, b major bit 16, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * kABytes));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * kBBytes));
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) {
+                    // K-major: +32 B per UMMA_K inside the swizzle atom; MN-major: +16 k-rows = 2048 B
+                    const uint64_t ad = adesc + (uint64_t)((k * 32) >> 4);
+                    const uint64_t bd = bdesc + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4);
+                    tcgen05_mma_f16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                }
+                tcgen05_commit(&empty[s]);
+            }
+            tcgen05_commit(tmem_full);
+        }
+    } else {
+        // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) ----------------
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+        const long zoff = (long)b0 * p.out_stride0 + (long)b1 * p.out_stride1;
+        const bool row_ok = m < p.M;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            const int nb = n0 + c;
+            if (!row_ok || nb >= p.N) continue;
+            const int nvalid = min(32, p.N - nb);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float x = __uint_as_float(r[j]);
+                const int n = nb + j;
+                if (j < nvalid) {
+                    if (p.bias) x += __ldg(p.bias + n);
+                    if (n < p.alpha_cols) x *= p.alpha;
+                    if (p.gelu) x = gelu_ggml(x);
+                    if (p.pos) x += __ldg(p.pos + (size_t)(m % p.pos_rows) * p.N + n);
+                }
+                v[j] = x;
+            }
+            long idx;
+            if (p.head_major) idx = ((long)(nb >> 6) * p.head_rows + m) * 64 + (nb & 63) + zoff;
+            else idx = (long)(m + p.out_row_offset) * p.out_ld + nb + zoff;
+            if (p.out_f16) {
+                __half *o = reinterpret_cast<__half *>(p.out) + idx;
+                if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                        uint4 u;
+                        u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
+                        u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
+                        *reinterpret_cast<uint4 *>(o + j) = u;
+                    }
+                } else {
+                    for (int j = 0; j < nvalid; j++) o[j] = __float2half_rn(v[j]);
+                }
+            } else {
+                float *o = reinterpret_cast<float *>(p.out) + idx;
+                if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (p.residual) { const float4 g = *reinterpret_cast<const float4 *>(o + j); f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w; }
+                        *reinterpret_cast<float4 *>(o + j) = f;
+                    }
+                } else {
+                    for (int j = 0; j < nvalid; j++) o[j] = p.residual ? o[j] + v[j] : v[j];
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+template <int BN, int kStages>
+constexpr size_t smem_bytes() { return 1024 + (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + (2 * kStages + 1) * 8 + 16; }
+
+void make_map(CUtensorMap *map, const GemmOperand &op, long inner, long rows, int box_inner, int box_rows) {
+    cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)op.batch0, (cuuint64_t)op.batch1};
+    auto fix = [&](long s, long fallback) { long v = s > 0 ? s : fallback; return (cuuint64_t)v * 2; };
+    const long natural = op.ld * rows;
+    cuuint64_t strides[3] = {(cuuint64_t)op.ld * 2, fix(op.stride0, natural), fix(op.stride1, natural * op.batch0)};
+    cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 3; i++)
+        if (strides[i] % 16) SS_THROW(-9, "GEMM operand stride %llu B is not a multiple of 16", (unsigned long long)strides[i]);
+    if (reinterpret_cast<uintptr_t>(op.ptr) % 16) SS_THROW(-9, "GEMM operand pointer is not 16-byte aligned");
+    CUresult rc = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(op.ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) SS_THROW(-4, "cuTensorMapEncodeTiled failed with %d (inner %ld rows %ld ld %ld)", (int)rc, inner, rows, op.ld);
+}
+
+template <int BN, int kStages, bool B_MN>
+void launch(const GemmOperand &A, const GemmOperand &B, const GemmDev &p, int nbatch, cudaStream_t st) {
+    CUtensorMap ta, tb;
+    make_map(&ta, A, p.K, A.rows, BK, BM);
+    if (B_MN) make_map(&tb, B, p.N, B.rows, 64, BK);   // [K rows][N contiguous]
+    else make_map(&tb, B, p.K, B.rows, BK, BN);
+    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), nbatch);
+    gemm_tcgen05_kernel<BN, kStages, B_MN><<<grid, kThreads, smem_bytes<BN, kStages>(), st>>>(ta, tb, p);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void gemm_init() {
+    if (!g_encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) SS_THROW(-4, "cuTensorMapEncodeTiled is not available in this driver");
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128, 3>()));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<64, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64, 4>()));
+}
+
+void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int K, bool b_mn_major, const GemmEpilogue &ep,
+                  cudaStream_t st, int *launches) {
+    GemmDev p{};
+    p.M = M; p.N = N; p.K = K; p.nb0 = (int)A.batch0;
+    p.bias = ep.bias; p.alpha = ep.alpha; p.alpha_cols = ep.alpha_cols; p.gelu = ep.gelu; p.pos = ep.pos; p.pos_rows = ep.pos_rows > 0 ? ep.pos_rows : 1;
+    p.residual = ep.residual; p.out_f16 = ep.out_type == GEMM_OUT_F16; p.out = ep.out; p.out_ld = ep.out_ld;
+    p.out_stride0 = ep.out_stride0; p.out_stride1 = ep.out_stride1; p.head_major = ep.head_major; p.head_rows = ep.head_rows;
+    p.out_row_offset = ep.out_row_offset;
+    if (p.residual && p.out_f16) SS_THROW(-9, "residual epilogue needs an f32 output");
+    if (A.batch0 != B.batch0 || A.batch1 != B.batch1) SS_THROW(-9, "GEMM batch mismatch");
+    const int nbatch = (int)(A.batch0 * A.batch1);
+    if (b_mn_major) {
+        if (N > 64) SS_THROW(-9, "MN-major B supports N <= 64");
+        launch<64, 4, true>(A, B, p, nbatch, st);
+    } else {
+        launch<128, 3, false>(A, B, p, nbatch, st);
+    }
+    (*launches)++;
+}
+
+}  // namespace ss

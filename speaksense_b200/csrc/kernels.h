@@ -1,0 +1,101 @@
+// kernels.h - device-side argument blocks and host launchers of the sm_100a kernels.
+#pragma once
+#include "common.h"
+#include "model.h"
+
+namespace ss {
+
+// ---------------------------------------------------------------- log-mel (mel.cu)
+// Raw log10-mel for frames [0, n_len) of one clip into mel[n_mels][n_len] plus the clip's running
+// maximum (float bits, ordered-int atomicMax), then in-place clamp/scale, then window extraction.
+void mel_enqueue(const Model &m, const float *d_pcm, size_t n_samples, float *d_mel, int n_len,
+                 int *d_max_bits, cudaStream_t st, int *launches);
+// frames [seek, seek+2*n_audio_ctx) -> f16 [2*n_audio_ctx + 2][n_mels] (zero rows at both ends,
+// zero past n_len) = the conv1 implicit-GEMM operand.
+void mel_window_enqueue(const Model &m, const float *d_mel, int n_len, int seek, __half *d_win,
+                        cudaStream_t st, int *launches);
+inline int mel_n_len(size_t n_samples) { return (int)((n_samples + (size_t)kSampleRate * kChunkSec) / kHop); }
+inline int mel_n_len_org(size_t n_samples) { return 1 + (int)(((long)n_samples + kNFft / 2 - kNFft) / kHop); }
+
+// ---------------------------------------------------------------- tcgen05 GEMM (gemm_sm100.cu)
+struct GemmOperand {        // a K-major (or, for B, MN-major) f16 operand described as up to 4-D strided view
+    const __half *ptr = nullptr;
+    long rows = 0;          // extent of the row (M or N) dimension per batch
+    long ld = 0;            // elements between rows
+    long batch0 = 1, stride0 = 0;   // inner batch (e.g. head)
+    long batch1 = 1, stride1 = 0;   // outer batch (e.g. clip)
+};
+enum : int { GEMM_OUT_F32 = 0, GEMM_OUT_F16 = 1 };
+struct GemmEpilogue {
+    const float *bias = nullptr;     // [N]
+    float alpha = 1.0f;              // applied to columns < alpha_cols after bias
+    int alpha_cols = 0;
+    int gelu = 0;                    // ggml f16-LUT GELU semantics
+    const float *pos = nullptr;      // + pos[(m % pos_rows)][n], ld = N
+    int pos_rows = 1;
+    int residual = 0;                // out (f32) += value
+    int out_type = GEMM_OUT_F16;
+    void *out = nullptr;
+    long out_ld = 0, out_stride0 = 0, out_stride1 = 0;   // elements
+    int head_major = 0;              // out index = ((n/64) * head_rows + m) * 64 + n%64 (+ batch strides)
+    long head_rows = 0;
+    int out_row_offset = 0;          // rows shift (padded conv layouts)
+};
+// D[b][M][N] = A[b][M][K] . B[b][N][K]^T  (B K-major) or A . B[b][K][N] (b_mn_major)
+void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int K, bool b_mn_major,
+                  const GemmEpilogue &ep, cudaStream_t st, int *launches);
+void gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
+
+// ---------------------------------------------------------------- encoder helpers (encoder.cu)
+void layernorm_f16_enqueue(const float *x, __half *y, int rows, int d, const LNp &ln, cudaStream_t st, int *launches);
+void layernorm_f32_enqueue(const float *x, float *y, int rows, int d, const LNp &ln, cudaStream_t st, int *launches);
+// rows of `n` f32 scores (ld_in) -> f16 probabilities, zero padded to ld_out
+void softmax_rows_enqueue(const float *s, long ld_in, __half *p, long ld_out, long rows, int n, cudaStream_t st, int *launches);
+void f32_to_f16_enqueue(const float *x, __half *y, size_t n, cudaStream_t st, int *launches);
+
+// ---------------------------------------------------------------- decoder (decoder.cu)
+constexpr int kSelfSplit = 4;
+constexpr int kCrossSplit = 8;
+constexpr int kNumLangSuppress = 100;
+constexpr int kMaxPrompt = 448;
+
+struct TokData { int id, tid; float p, plog, pt, ptsum; };
+
+struct DecCtl {   // device resident; written by dec_sample_kernel, read by every kernel of the step
+    int pos, token, done, n_sampled;
+    int has_ts, seek_delta, result_len, failed, completed;
+    int last_id, penult_id;
+    int n_prompt, pos0;
+    int seek, seek_end, n_max;
+    int sample, keep_logits, n_kept;
+    int pad;
+    int prompt[kMaxPrompt];
+};
+
+enum : int { PRO_PLAIN = 0, PRO_LN = 1, PRO_ATTN = 2 };
+enum : int { EPI_STORE = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_QSCALE = 3, EPI_QKV = 4 };
+
+struct GemvArgs {
+    const __half *W; const float *bias; int N, K;
+    int pro; const float *xin; const float *lnw; const float *lnb; const float *part; int n_split;
+    int epi; float *out; float s4; __half *kcache; __half *vcache; int ctx;
+    const DecCtl *ctl; int logits_gate;
+};
+struct AttnArgs {
+    const float *q; const __half *K; const __half *V; int ctx; int n_keys; float *part; const DecCtl *ctl;
+};
+struct SampleArgs {
+    DecCtl *ctl; const float *logits; int n_vocab; TokData *out; float *keep; int keep_cap;
+    int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
+    int suppress_blank, tdrz, tid0_init; float inv_temperature;
+};
+struct DecodeBuffers {   // one decoder sequence
+    DecCtl *ctl; float *x, *q, *h, *part, *logits; TokData *tok_out; float *keep; int keep_cap;
+    __half *self_k, *self_v;              // [layer][head][n_text_ctx][64]
+    const __half *cross_k, *cross_v;      // [layer][head][n_audio_ctx][64]
+    int suppress_blank, tdrz, tid0_init;
+};
+void decode_step_enqueue(const Model &m, const DecodeBuffers &b, cudaStream_t st, int *launches);
+int decode_step_num_launches(const Model &m);
+
+}  // namespace ss
