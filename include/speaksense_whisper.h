@@ -85,6 +85,14 @@ int  ss_transcribe(ss_engine *e, ss_state *s, const float *pcm, size_t n_samples
 int  ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *const *pcm,
                          const size_t *n_samples, int batch, const ss_params *p);
 
+/* Device-resident form used for kernel-side throughput measurement: ss_upload_pcm stages the clip in
+ * HBM once, ss_transcribe_resident runs the same path without the host->device copy. */
+int  ss_upload_pcm(ss_engine *e, ss_state *s, const float *pcm, size_t n_samples);
+int  ss_transcribe_resident(ss_engine *e, ss_state *s, const ss_params *p);
+/* Replays the decode-step CUDA graph n_steps times at positions n_past0.. (dummy tokens) and returns
+ * the device time per step (CUDA events on the state's stream): the roofline probe of stage 3. */
+int  ss_bench_decode_steps(ss_engine *e, ss_state *s, int n_steps, int n_past0, float *ms_per_step);
+
 /* results of the last transcribe on this state; pointers valid until the next call on it.
  * "raw" == what whisper-rs returns (full_n_segments / full_get_segment_*; whisper.rs:77-95);
  * the un-prefixed accessors == TranscribeResult after the Rust post-processing (whisper.rs:84-128). */

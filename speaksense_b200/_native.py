@@ -37,6 +37,9 @@ SYMBOLS = [
     ("ss_state_new", C.c_int, [_P, C.POINTER(_P)]),
     ("ss_state_free", None, [_P]),
     ("ss_transcribe", C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(SsParams)]),
+    ("ss_upload_pcm", C.c_int, [_P, _P, _P, C.c_size_t]),
+    ("ss_transcribe_resident", C.c_int, [_P, _P, C.POINTER(SsParams)]),
+    ("ss_bench_decode_steps", C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("ss_transcribe_batch", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_int, C.POINTER(SsParams)]),
     ("ss_n_segments_raw", C.c_int, [_P]),
     ("ss_segment_text_raw", C.c_char_p, [_P, C.c_int]),

@@ -202,6 +202,21 @@ class WhisperAsr(AsrEngine):          # whisper.rs:16-129
             _native.check(_native.lib().ss_transcribe(self._h, state._h, pcm.ctypes.data, pcm.size, C.byref(p)))
             return self._read_result(state)
 
+    def upload_pcm(self, state: WhisperState, audio):
+        pcm = np.ascontiguousarray(audio, dtype=np.float32)
+        _native.check(_native.lib().ss_upload_pcm(self._h, state._h, pcm.ctypes.data, pcm.size))
+
+    def transcribe_resident(self, state: WhisperState, params: AsrParams) -> TranscribeResult:
+        p = params._native()
+        with state._lock:
+            _native.check(_native.lib().ss_transcribe_resident(self._h, state._h, C.byref(p)))
+            return self._read_result(state)
+
+    def bench_decode_steps(self, state: WhisperState, n_steps: int, n_past0: int = 0) -> float:
+        ms = C.c_float()
+        _native.check(_native.lib().ss_bench_decode_steps(self._h, state._h, n_steps, n_past0, C.byref(ms)))
+        return ms.value
+
     def transcribe_batch(self, states: Sequence[WhisperState], audios: Sequence[np.ndarray], params: AsrParams):
         """Data-parallel batch inside one GPU (BASELINE configs 3/4): result i belongs to audios[i]."""
         n = len(states)

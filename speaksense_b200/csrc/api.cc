@@ -96,6 +96,28 @@ int ss_transcribe(ss_engine *e, ss_state *s, const float *pcm, size_t n, const s
         return transcribe(*s->s, pcm, n, make_params(p), p && p->stream_mode);
     });
 }
+int ss_upload_pcm(ss_engine *e, ss_state *s, const float *pcm, size_t n) {
+    return guard([&]() -> int {
+        if (!e || !s || (!pcm && n)) SS_THROW(SS_ERR_INVALID, "null argument");
+        upload_pcm(*s->s, pcm, n);
+        CUDA_CHECK(cudaStreamSynchronize(s->s->stream));
+        return 0;
+    });
+}
+int ss_transcribe_resident(ss_engine *e, ss_state *s, const ss_params *p) {
+    return guard([&]() -> int {
+        if (!e || !s) SS_THROW(SS_ERR_INVALID, "null argument");
+        if (!s->s->d_pcm) SS_THROW(SS_ERR_INVALID, "no resident PCM: call ss_upload_pcm first");
+        return transcribe(*s->s, nullptr, s->s->n_resident, make_params(p), p && p->stream_mode);
+    });
+}
+int ss_bench_decode_steps(ss_engine *e, ss_state *s, int n_steps, int n_past0, float *ms_per_step) {
+    return guard([&]() -> int {
+        if (!e || !s || !ms_per_step) SS_THROW(SS_ERR_INVALID, "null argument");
+        *ms_per_step = bench_decode_steps(*s->s, n_steps, n_past0);
+        return 0;
+    });
+}
 int ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *const *pcm, const size_t *n, int batch, const ss_params *p) {
     return guard([&]() -> int {
         if (!e || !states || !pcm || !n || batch < 0) SS_THROW(SS_ERR_INVALID, "null argument");

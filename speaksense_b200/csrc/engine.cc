@@ -198,9 +198,34 @@ State::~State() {
 // ------------------------------------------------------------------------------------------------
 // stages
 // ------------------------------------------------------------------------------------------------
+void upload_pcm(State &s, const float *pcm, size_t n) {
+    CUDA_CHECK(cudaSetDevice(s.engine->device));
+    if (n + 1 > s.pcm_cap) {
+        if (s.d_pcm) cudaFree(s.d_pcm);
+        s.pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.d_pcm = dmalloc<float>(s.pcm_cap);
+    }
+    if (n + 1 > s.h_pcm_cap) {
+        if (s.h_pcm) cudaFreeHost(s.h_pcm);
+        s.h_pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.h_pcm = hmalloc<float>(s.h_pcm_cap);
+    }
+    if (n) memcpy(s.h_pcm, pcm, n * sizeof(float));      // caller memory is pageable: stage through pinned
+    if (n) CUDA_CHECK(cudaMemcpyAsync(s.d_pcm, s.h_pcm, n * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    s.n_resident = n;
+}
+
 void run_log_mel(State &s, const float *pcm, size_t n) {
     const Model &m = s.engine->model;
     CUDA_CHECK(cudaSetDevice(s.engine->device));
+    if (pcm == nullptr && n == s.n_resident && s.d_pcm) {   // PCM already resident in HBM (ss_upload_pcm)
+        s.n_len = mel_n_len(n); s.n_len_org = mel_n_len_org(n);
+        const size_t need0 = (size_t)m.hp.n_mels * s.n_len;
+        if (need0 > s.mel_cap) { if (s.d_mel) cudaFree(s.d_mel); s.mel_cap = need0; s.d_mel = dmalloc<float>(need0); }
+        mel_enqueue(m, s.d_pcm, n, s.d_mel, s.n_len, s.d_max, s.stream, &s.n_launches);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     if (n + 1 > s.pcm_cap) {
         if (s.d_pcm) cudaFree(s.d_pcm);
         s.pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
@@ -216,6 +241,7 @@ void run_log_mel(State &s, const float *pcm, size_t n) {
     if (need > s.mel_cap) { if (s.d_mel) cudaFree(s.d_mel); s.mel_cap = need; s.d_mel = dmalloc<float>(need); }
     if (n) memcpy(s.h_pcm, pcm, n * sizeof(float));      // caller memory is pageable: stage through pinned
     if (n) CUDA_CHECK(cudaMemcpyAsync(s.d_pcm, s.h_pcm, n * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+    s.n_resident = n;
     mel_enqueue(m, s.d_pcm, n, s.d_mel, s.n_len, s.d_max, s.stream, &s.n_launches);
     CUDA_CHECK(cudaGetLastError());
 }
@@ -333,6 +359,29 @@ static int run_steps(State &s, Decoder &d, int max_steps, int chunk) {
 
 static void upload_ctl(State &s, Decoder &d) {
     CUDA_CHECK(cudaMemcpyAsync(d.b.ctl, d.h_ctl, sizeof(DecCtl), cudaMemcpyHostToDevice, s.stream));
+}
+
+// replay the decode-step graph `n_steps` times back to back (teacher-forced dummy tokens, positions
+// n_past0..) and return the device time per step measured with CUDA events on the state's stream.
+float bench_decode_steps(State &s, int n_steps, int n_past0) {
+    const Model &m = s.engine->model; const HParams &hp = m.hp;
+    CUDA_CHECK(cudaSetDevice(s.engine->device));
+    if (n_steps <= 0 || n_past0 < 0 || n_past0 + n_steps > hp.n_text_ctx) SS_THROW(-1, "bench_decode_steps: bad range");
+    Decoder &d = *s.dec[0];
+    ensure_graph(s, d);
+    DecCtl &c = *d.h_ctl;
+    memset(&c, 0, sizeof c);
+    c.pos = n_past0; c.pos0 = n_past0; c.n_prompt = n_steps; c.sample = 0; c.last_id = -1; c.penult_id = -1; c.n_max = hp.n_text_ctx;
+    for (int i = 0; i < n_steps; i++) c.prompt[i] = 1000 + 7 * i;
+    c.token = c.prompt[0];
+    upload_ctl(s, d);
+    CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
+    for (int i = 0; i < n_steps; i++) CUDA_CHECK(cudaGraphLaunch(d.graph, s.stream));
+    CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
+    s.n_launches += n_steps * decode_step_num_launches(m);
+    return ms / n_steps;
 }
 
 void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *logits_out) {

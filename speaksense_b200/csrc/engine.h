@@ -53,7 +53,7 @@ struct State {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // audio / mel
-    float *d_pcm = nullptr; size_t pcm_cap = 0; float *h_pcm = nullptr; size_t h_pcm_cap = 0;
+    float *d_pcm = nullptr; size_t pcm_cap = 0; size_t n_resident = 0; float *h_pcm = nullptr; size_t h_pcm_cap = 0;
     float *d_mel = nullptr; size_t mel_cap = 0; int n_len = 0, n_len_org = 0; int *d_max = nullptr;
     // encoder scratch (one window)
     __half *win = nullptr, *x1 = nullptr, *xn = nullptr, *qkv = nullptr, *P = nullptr, *att = nullptr, *ff = nullptr, *enc16 = nullptr;
@@ -80,7 +80,9 @@ std::shared_ptr<Engine> engine_open_dist(const char *path, int device, int rank,
 void nccl_unique_id(unsigned char out[128]);
 State *state_new(const std::shared_ptr<Engine> &e);
 
-void run_log_mel(State &s, const float *pcm, size_t n);
+void upload_pcm(State &s, const float *pcm, size_t n);
+void run_log_mel(State &s, const float *pcm, size_t n);   // pcm == nullptr: use the resident PCM
+float bench_decode_steps(State &s, int n_steps, int n_past0);
 void run_encode(State &s, int seek);
 void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *logits_out);
 int transcribe(State &s, const float *pcm, size_t n, const FullParams &fp, bool stream_mode);
