@@ -134,19 +134,38 @@ std::shared_ptr<Engine> engine_open_dist(const char *path, int device, int rank,
 // state
 // ------------------------------------------------------------------------------------------------
 static Decoder *new_decoder(State &s, bool with_keep) {
-    const Model &m = s.engine->model; const HParams &hp = m.hp;
+    const Model &m = s.engine->model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
+    if (hp.n_text_layer > kMaxLayers || hp.n_text_state > 1280) SS_THROW(-2, "decoder larger than large-v3 is not supported");
     auto d = std::make_unique<Decoder>();
     const size_t dd = hp.n_text_state, kv = (size_t)hp.n_text_layer * hp.n_text_ctx * dd;
-    DecodeBuffers &b = d->b;
+    MegaParams &b = d->mp;
+    b.d = hp.n_text_state; b.H = hp.n_text_head; b.L = hp.n_text_layer; b.T = hp.n_audio_ctx; b.ctx = hp.n_text_ctx; b.n_vocab = hp.n_vocab;
+    b.xsplit = std::max(1, std::min(32, s.mega_grid / b.H)); b.ssplit = std::max(1, std::min(8, s.mega_grid / b.H));
+    b.s4 = powf((float)(b.d / b.H), -0.25f);
+    if (ceil_div(hp.n_vocab, s.mega_grid) > 500 || ceil_div(b.T, b.xsplit) > 500 || ceil_div(b.ctx, b.ssplit) > 500)
+        SS_THROW(-3, "device has too few SMs (%d) for the decode kernel's per-CTA work buffers", s.mega_grid);
+    b.tok_emb = m.tok_emb; b.d_pos = m.d_pos; b.lnf_w = m.d_ln.w; b.lnf_b = m.d_ln.b;
+    for (int i = 0; i < hp.n_text_layer; i++) {
+        const DecLayer &L = m.dec[i]; MegaLayer &o = b.layer[i];
+        o.qkv_w = L.qkv.w; o.o_w = L.o.w; o.cq_w = L.cq.w; o.co_w = L.co.w; o.fc1_w = L.fc1.w; o.fc2_w = L.fc2.w;
+        o.qkv_b = L.qkv.b; o.o_b = L.o.b; o.cq_b = L.cq.b; o.co_b = L.co.b; o.fc1_b = L.fc1.b; o.fc2_b = L.fc2.b;
+        o.ln1_w = L.attn_ln.w; o.ln1_b = L.attn_ln.b; o.ln2_w = L.cross_ln.w; o.ln2_b = L.cross_ln.b; o.ln3_w = L.mlp_ln.w; o.ln3_b = L.mlp_ln.b;
+    }
     b.ctl = dmalloc<DecCtl>(1);
     b.x = dmalloc<float>(dd); b.q = dmalloc<float>(dd); b.h = dmalloc<float>(4 * dd);
-    b.part = dmalloc<float>((size_t)hp.n_text_head * std::max(kSelfSplit, kCrossSplit) * 66);
+    b.part = dmalloc<float>((size_t)hp.n_text_head * 32 * 66);
     b.logits = dmalloc<float>(hp.n_vocab);
+    b.stats = dmalloc<float>((size_t)s.mega_grid * 8);
     b.tok_out = dmalloc<TokData>(hp.n_text_ctx);
     b.self_k = dmalloc<__half>(kv); b.self_v = dmalloc<__half>(kv);
     CUDA_CHECK(cudaMemset(b.self_k, 0, kv * 2)); CUDA_CHECK(cudaMemset(b.self_v, 0, kv * 2));
     b.cross_k = s.cross_k; b.cross_v = s.cross_v;
     b.keep = with_keep ? s.keep : nullptr; b.keep_cap = with_keep ? s.keep_cap : 0;
+    b.bar = dmalloc<unsigned int>(1);
+    b.eot = v.eot; b.sot = v.sot; b.translate = v.translate; b.transcribe = v.transcribe; b.solm = v.solm; b.prev = v.prev;
+    b.nosp = v.nosp; b.not_ = v.not_; b.beg = v.beg; b.blank = v.blank;
+    b.suppress_blank = 1; b.tdrz = 0; b.tid0_init = -1;
+    d->d_mp = dmalloc<MegaParams>(1); d->mp_dirty = true;
     d->h_ctl = hmalloc<DecCtl>(1); d->h_tok = hmalloc<TokData>(hp.n_text_ctx);
     memset(d->h_ctl, 0, sizeof(DecCtl));
     Decoder *raw = d.get();
@@ -172,6 +191,8 @@ State *state_new(const std::shared_ptr<Engine> &e) {
     s->enc_out = dmalloc<float>(T * d); s->enc16 = dmalloc<__half>(T * d);
     s->cross_k = dmalloc<__half>((size_t)hp.n_text_layer * T * dd); s->cross_v = dmalloc<__half>((size_t)hp.n_text_layer * T * dd);
     s->h_logits = hmalloc<float>(hp.n_vocab);
+    decode_mega_configure();
+    s->mega_grid = decode_mega_grid(e->device);
     new_decoder(*s, true);
     return s.release();
 }
@@ -181,10 +202,9 @@ State::~State() {
     cudaSetDevice(engine->device);
     if (stream) cudaStreamSynchronize(stream);
     for (auto &d : dec) {
-        if (d->graph) cudaGraphExecDestroy(d->graph);
-        DecodeBuffers &b = d->b;
-        cudaFree(b.ctl); cudaFree(b.x); cudaFree(b.q); cudaFree(b.h); cudaFree(b.part); cudaFree(b.logits); cudaFree(b.tok_out);
-        cudaFree(b.self_k); cudaFree(b.self_v);
+        MegaParams &b = d->mp;
+        cudaFree(b.ctl); cudaFree(b.x); cudaFree(b.q); cudaFree(b.h); cudaFree(b.part); cudaFree(b.logits); cudaFree(b.stats); cudaFree(b.tok_out);
+        cudaFree(b.self_k); cudaFree(b.self_v); cudaFree(b.bar); cudaFree(d->d_mp);
         cudaFreeHost(d->h_ctl); cudaFreeHost(d->h_tok);
     }
     void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, P, att, ff, enc16, x, S, enc_out, cross_k, cross_v, keep};
@@ -328,37 +348,25 @@ void run_encode(State &s, int seek) {
 // ------------------------------------------------------------------------------------------------
 // decoder driving
 // ------------------------------------------------------------------------------------------------
-static void ensure_graph(State &s, Decoder &d) {
-    if (d.graph) return;
-    const Model &m = s.engine->model;
-    d.b.cross_k = s.cross_k; d.b.cross_v = s.cross_v;
-    cudaGraph_t g;
-    int dummy = 0;
-    CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
-    decode_step_enqueue(m, d.b, s.stream, &dummy);
-    CUDA_CHECK(cudaStreamEndCapture(s.stream, &g));
-    CUDA_CHECK(cudaGraphInstantiate(&d.graph, g, 0));
-    CUDA_CHECK(cudaGraphDestroy(g));
+static void ensure_params(State &s, Decoder &d) {
+    if (!d.mp_dirty) return;
+    d.mp.cross_k = s.cross_k; d.mp.cross_v = s.cross_v;
+    CUDA_CHECK(cudaMemcpyAsync(d.d_mp, &d.mp, sizeof(MegaParams), cudaMemcpyHostToDevice, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));   // d.mp is pageable host memory
+    d.mp_dirty = false;
 }
 
-// run the step graph until the device says done (or max_steps); returns steps launched
-static int run_steps(State &s, Decoder &d, int max_steps, int chunk) {
-    const Model &m = s.engine->model;
-    int launched = 0;
-    while (launched < max_steps) {
-        const int k = std::min(chunk, max_steps - launched);
-        for (int i = 0; i < k; i++) CUDA_CHECK(cudaGraphLaunch(d.graph, s.stream));
-        launched += k;
-        CUDA_CHECK(cudaMemcpyAsync(d.h_ctl, d.b.ctl, offsetof(DecCtl, prompt), cudaMemcpyDeviceToHost, s.stream));
-        CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        if (d.h_ctl->done) break;
-    }
-    s.n_launches += launched * decode_step_num_launches(m);
-    return launched;
+// one launch of the persistent decode kernel: runs until the device says done or `max_steps` tokens
+static void run_steps(State &s, Decoder &d, int max_steps) {
+    ensure_params(s, d);
+    decode_mega_launch(d.d_mp, d.mp.bar, max_steps, s.mega_grid, s.stream);
+    s.n_launches += 1;
+    CUDA_CHECK(cudaMemcpyAsync(d.h_ctl, d.mp.ctl, offsetof(DecCtl, prompt), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
 }
 
 static void upload_ctl(State &s, Decoder &d) {
-    CUDA_CHECK(cudaMemcpyAsync(d.b.ctl, d.h_ctl, sizeof(DecCtl), cudaMemcpyHostToDevice, s.stream));
+    CUDA_CHECK(cudaMemcpyAsync(d.mp.ctl, d.h_ctl, sizeof(DecCtl), cudaMemcpyHostToDevice, s.stream));
 }
 
 // replay the decode-step graph `n_steps` times back to back (teacher-forced dummy tokens, positions
@@ -368,20 +376,22 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     if (n_steps <= 0 || n_past0 < 0 || n_past0 + n_steps > hp.n_text_ctx) SS_THROW(-1, "bench_decode_steps: bad range");
     Decoder &d = *s.dec[0];
-    ensure_graph(s, d);
+    ensure_params(s, d);
     DecCtl &c = *d.h_ctl;
     memset(&c, 0, sizeof c);
-    c.pos = n_past0; c.pos0 = n_past0; c.n_prompt = n_steps; c.sample = 0; c.last_id = -1; c.penult_id = -1; c.n_max = hp.n_text_ctx;
+    // teacher-forced dummy tokens with the LM head forced on for every step: n_steps whole steps, one launch
+    c.pos = n_past0; c.pos0 = n_past0; c.n_prompt = n_steps; c.sample = 0; c.all_logits = 1; c.last_id = -1; c.penult_id = -1; c.n_max = hp.n_text_ctx;
     for (int i = 0; i < n_steps; i++) c.prompt[i] = 1000 + 7 * i;
     c.token = c.prompt[0];
+    (void)m;
     upload_ctl(s, d);
     CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
-    for (int i = 0; i < n_steps; i++) CUDA_CHECK(cudaGraphLaunch(d.graph, s.stream));
+    decode_mega_launch(d.d_mp, d.mp.bar, n_steps, s.mega_grid, s.stream);
     CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
-    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]));
-    s.n_launches += n_steps * decode_step_num_launches(m);
-    return ms / n_steps;
+    float total = 0.f; CUDA_CHECK(cudaEventElapsedTime(&total, s.ev[2], s.ev[3]));
+    s.n_launches += 1;
+    return total / n_steps;
 }
 
 void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *logits_out) {
@@ -389,7 +399,7 @@ void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *lo
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     if (n <= 0 || n > kMaxPrompt || n_past < 0 || n_past + n > hp.n_text_ctx) SS_THROW(-1, "decode: bad token count / position");
     Decoder &d = *s.dec[0];
-    ensure_graph(s, d);
+    ensure_params(s, d);
     DecCtl &c = *d.h_ctl;
     memset(&c, 0, sizeof c);
     c.pos = n_past; c.pos0 = n_past; c.token = tokens[0]; c.n_prompt = n; c.sample = 0; c.last_id = -1; c.penult_id = -1;
@@ -399,11 +409,17 @@ void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *lo
         c.prompt[i] = tokens[i];
     }
     upload_ctl(s, d);
-    run_steps(s, d, n, n);
+    run_steps(s, d, n);
     s.n_decoded += n;
-    CUDA_CHECK(cudaMemcpyAsync(s.h_logits, d.b.logits, (size_t)hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaMemcpyAsync(s.h_logits, d.mp.logits, (size_t)hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     if (logits_out) memcpy(logits_out, s.h_logits, (size_t)hp.n_vocab * sizeof(float));
+}
+
+static void set_sampling(Decoder &d, const FullParams &P, int tid0_init) {
+    if (d.mp.suppress_blank != (int)P.suppress_blank || d.mp.tdrz != (int)P.tdrz_enable || d.mp.tid0_init != tid0_init) {
+        d.mp.suppress_blank = P.suppress_blank; d.mp.tdrz = P.tdrz_enable; d.mp.tid0_init = tid0_init; d.mp_dirty = true;
+    }
 }
 
 // ---- host restatement of whisper_process_logits / whisper_sample_token for the t>0 fallback path
@@ -489,23 +505,23 @@ static void sequence_score(const FullParams &P, Sequence &q) {
 
 // one forward step of decoder `d` feeding `token` at position n_past; raw logits land in s.h_logits
 static void step_host_sampled(State &s, Decoder &d, const int *tokens, int n, int n_past) {
-    ensure_graph(s, d);
+    ensure_params(s, d);
     DecCtl &c = *d.h_ctl;
     memset(&c, 0, offsetof(DecCtl, prompt));
     c.pos = n_past; c.pos0 = n_past; c.token = tokens[0]; c.n_prompt = n; c.sample = 0; c.last_id = -1; c.penult_id = -1;
     for (int i = 0; i < n; i++) c.prompt[i] = tokens[i];
     upload_ctl(s, d);
-    run_steps(s, d, n, n);
+    run_steps(s, d, n);
     s.n_decoded += 1;
-    CUDA_CHECK(cudaMemcpyAsync(s.h_logits, d.b.logits, (size_t)s.engine->model.hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaMemcpyAsync(s.h_logits, d.mp.logits, (size_t)s.engine->model.hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
 }
 
 static void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos) {
     const HParams &hp = s.engine->model.hp;
     const size_t pitch = (size_t)hp.n_text_ctx * 64 * 2, width = (size_t)n_pos * 64 * 2, height = (size_t)hp.n_text_layer * hp.n_text_head;
-    CUDA_CHECK(cudaMemcpy2DAsync(to.b.self_k, pitch, from.b.self_k, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
-    CUDA_CHECK(cudaMemcpy2DAsync(to.b.self_v, pitch, from.b.self_v, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(to.mp.self_k, pitch, from.mp.self_k, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(to.mp.self_v, pitch, from.mp.self_v, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -524,8 +540,7 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
 
     if (P.keep_logits && !s.keep) {
         s.keep_cap = hp.n_text_ctx / 2; s.keep = dmalloc<float>((size_t)s.keep_cap * hp.n_vocab);
-        s.dec[0]->b.keep = s.keep; s.dec[0]->b.keep_cap = s.keep_cap;
-        if (s.dec[0]->graph) { cudaGraphExecDestroy(s.dec[0]->graph); s.dec[0]->graph = nullptr; }
+        s.dec[0]->mp.keep = s.keep; s.dec[0]->mp.keep_cap = s.keep_cap; s.dec[0]->mp_dirty = true;
     }
 
     CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
@@ -585,8 +600,8 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
             if (t_cur < 1e-6f) {
                 // ---------------- greedy at temperature 0: whole loop on the device ----------------
                 Decoder &dc = *s.dec[0];
-                dc.b.suppress_blank = P.suppress_blank; dc.b.tdrz = P.tdrz_enable; dc.b.tid0_init = tid0_init;
-                ensure_graph(s, dc);
+                set_sampling(dc, P, tid0_init);
+                ensure_params(s, dc);
                 DecCtl &c = *dc.h_ctl;
                 memset(&c, 0, sizeof c);
                 c.pos = 0; c.pos0 = 0; c.token = prompt[0]; c.n_prompt = n_prompt; c.sample = 1; c.last_id = -1; c.penult_id = -1;
@@ -594,12 +609,11 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
                 c.keep_logits = (P.keep_logits && it == 0) ? 1 : 0; c.n_kept = 0;
                 for (int i = 0; i < n_prompt; i++) c.prompt[i] = prompt[i];
                 upload_ctl(s, dc);
-                const int steps = run_steps(s, dc, n_prompt + n_max - 1, 16);
-                (void)steps;
+                run_steps(s, dc, n_prompt + n_max - 1);
                 const int ns = dc.h_ctl->n_sampled;
                 s.n_decoded += n_prompt - 1 + ns;
                 if (ns > 0) {
-                    CUDA_CHECK(cudaMemcpyAsync(dc.h_tok, dc.b.tok_out, (size_t)ns * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
+                    CUDA_CHECK(cudaMemcpyAsync(dc.h_tok, dc.mp.tok_out, (size_t)ns * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
                     CUDA_CHECK(cudaStreamSynchronize(s.stream));
                 }
                 dc.seq.tokens.assign(dc.h_tok, dc.h_tok + ns);
@@ -615,7 +629,7 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
                 }
             } else {
                 // ---------------- t > 0: best_of sampled decoders, host-side sampling ----------------
-                for (int j = 0; j < n_cur; j++) { s.dec[j]->b.suppress_blank = P.suppress_blank; s.dec[j]->b.tdrz = P.tdrz_enable; s.dec[j]->b.tid0_init = tid0_init; }
+                for (int j = 0; j < n_cur; j++) set_sampling(*s.dec[j], P, tid0_init);
                 step_host_sampled(s, *s.dec[0], prompt.data(), n_prompt, 0);
                 s.n_decoded += n_prompt - 1;
                 process_logits_host(m, P, *s.dec[0], s.h_logits, t_cur);

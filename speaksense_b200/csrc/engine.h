@@ -34,8 +34,9 @@ struct Sequence {
 };
 
 struct Decoder {
-    DecodeBuffers b{};
-    cudaGraphExec_t graph = nullptr;
+    MegaParams mp{};                  // host copy of the device-resident descriptor
+    MegaParams *d_mp = nullptr;
+    bool mp_dirty = true;
     DecCtl *h_ctl = nullptr;          // pinned mirror
     TokData *h_tok = nullptr;         // pinned
     Sequence seq;
@@ -63,6 +64,7 @@ struct State {
     std::vector<std::unique_ptr<Decoder>> dec;
     float *keep = nullptr; int keep_cap = 0; std::vector<float> h_keep; int n_keep = 0;
     float *h_logits = nullptr;   // pinned [n_vocab]
+    int mega_grid = 0;
     // results
     std::vector<int> prompt_past;
     std::vector<RawSegment> raw;

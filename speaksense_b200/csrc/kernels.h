@@ -54,8 +54,6 @@ void softmax_rows_enqueue(const float *s, long ld_in, __half *p, long ld_out, lo
 void f32_to_f16_enqueue(const float *x, __half *y, size_t n, cudaStream_t st, int *launches);
 
 // ---------------------------------------------------------------- decoder (decoder.cu)
-constexpr int kSelfSplit = 4;
-constexpr int kCrossSplit = 8;
 constexpr int kNumLangSuppress = 100;
 constexpr int kMaxPrompt = 448;
 
@@ -68,34 +66,32 @@ struct DecCtl {   // device resident; written by dec_sample_kernel, read by ever
     int n_prompt, pos0;
     int seek, seek_end, n_max;
     int sample, keep_logits, n_kept;
-    int pad;
+    int all_logits;   // compute the LM head for every token, not only from the last prompt token on
     int prompt[kMaxPrompt];
 };
 
-enum : int { PRO_PLAIN = 0, PRO_LN = 1, PRO_ATTN = 2 };
-enum : int { EPI_STORE = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_QSCALE = 3, EPI_QKV = 4 };
-
-struct GemvArgs {
-    const __half *W; const float *bias; int N, K;
-    int pro; const float *xin; const float *lnw; const float *lnb; const float *part; int n_split;
-    int epi; float *out; float s4; __half *kcache; __half *vcache; int ctx;
-    const DecCtl *ctl; int logits_gate;
+struct MegaLayer {
+    const __half *qkv_w, *o_w, *cq_w, *co_w, *fc1_w, *fc2_w;
+    const float *qkv_b, *o_b, *cq_b, *co_b, *fc1_b, *fc2_b;
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
 };
-struct AttnArgs {
-    const float *q; const __half *K; const __half *V; int ctx; int n_keys; float *part; const DecCtl *ctl;
-};
-struct SampleArgs {
-    DecCtl *ctl; const float *logits; int n_vocab; TokData *out; float *keep; int keep_cap;
-    int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
-    int suppress_blank, tdrz, tid0_init; float inv_temperature;
-};
-struct DecodeBuffers {   // one decoder sequence
-    DecCtl *ctl; float *x, *q, *h, *part, *logits; TokData *tok_out; float *keep; int keep_cap;
+constexpr int kMaxLayers = 32;
+struct MegaParams {   // device-resident descriptor of one decoder sequence (decoder_mega.cu)
+    int d, H, L, T, ctx, n_vocab;
+    int xsplit, ssplit;          // (head, split) units of the cross / self attention phases
+    float s4;                    // head_dim^-1/4
+    const __half *tok_emb; const float *d_pos; const float *lnf_w, *lnf_b;
+    MegaLayer layer[kMaxLayers];
+    DecCtl *ctl; float *x, *q, *h, *part, *logits, *stats; TokData *tok_out; float *keep; int keep_cap;
     __half *self_k, *self_v;              // [layer][head][n_text_ctx][64]
     const __half *cross_k, *cross_v;      // [layer][head][n_audio_ctx][64]
+    unsigned int *bar;
+    int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
     int suppress_blank, tdrz, tid0_init;
 };
-void decode_step_enqueue(const Model &m, const DecodeBuffers &b, cudaStream_t st, int *launches);
-int decode_step_num_launches(const Model &m);
+size_t decode_mega_smem_bytes();
+void decode_mega_configure();
+int decode_mega_grid(int device);
+void decode_mega_launch(const MegaParams *d_params, unsigned int *d_bar, int max_steps, int grid, cudaStream_t st);
 
 }  // namespace ss
