@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -140,9 +141,9 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     const size_t dd = hp.n_text_state, kv = (size_t)hp.n_text_layer * hp.n_text_ctx * dd;
     MegaParams &b = d->mp;
     b.d = hp.n_text_state; b.H = hp.n_text_head; b.L = hp.n_text_layer; b.T = hp.n_audio_ctx; b.ctx = hp.n_text_ctx; b.n_vocab = hp.n_vocab;
-    b.xsplit = std::max(1, std::min(32, s.mega_grid / b.H)); b.ssplit = std::max(1, std::min(8, s.mega_grid / b.H));
+    b.xsplit = std::max(1, std::min(8, s.mega_grid / b.H)); b.ssplit = std::max(1, std::min(8, s.mega_grid / b.H));
     b.s4 = powf((float)(b.d / b.H), -0.25f);
-    if (ceil_div(hp.n_vocab, s.mega_grid) > 500 || ceil_div(b.T, b.xsplit) > 500 || ceil_div(b.ctx, b.ssplit) > 500)
+    if (ceil_div(hp.n_vocab, s.mega_grid) > 500 || ceil_div(b.T, b.xsplit) > 500 || b.ctx > 512 || ceil_div(4 * b.d, s.mega_grid) > 250 || b.H > s.mega_grid || b.H + 1 > kMegaBarWords)
         SS_THROW(-3, "device has too few SMs (%d) for the decode kernel's per-CTA work buffers", s.mega_grid);
     b.tok_emb = m.tok_emb; b.d_pos = m.d_pos; b.lnf_w = m.d_ln.w; b.lnf_b = m.d_ln.b;
     for (int i = 0; i < hp.n_text_layer; i++) {
@@ -152,7 +153,7 @@ static Decoder *new_decoder(State &s, bool with_keep) {
         o.ln1_w = L.attn_ln.w; o.ln1_b = L.attn_ln.b; o.ln2_w = L.cross_ln.w; o.ln2_b = L.cross_ln.b; o.ln3_w = L.mlp_ln.w; o.ln3_b = L.mlp_ln.b;
     }
     b.ctl = dmalloc<DecCtl>(1);
-    b.x = dmalloc<float>(dd); b.q = dmalloc<float>(dd); b.h = dmalloc<float>(4 * dd);
+    b.x = dmalloc<float>(dd); b.q = dmalloc<float>(dd); b.h = dmalloc<float>(4 * dd); b.att = dmalloc<float>(dd);
     b.part = dmalloc<float>((size_t)hp.n_text_head * 32 * 66);
     b.logits = dmalloc<float>(hp.n_vocab);
     b.stats = dmalloc<float>((size_t)s.mega_grid * 8);
@@ -161,7 +162,8 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     CUDA_CHECK(cudaMemset(b.self_k, 0, kv * 2)); CUDA_CHECK(cudaMemset(b.self_v, 0, kv * 2));
     b.cross_k = s.cross_k; b.cross_v = s.cross_v;
     b.keep = with_keep ? s.keep : nullptr; b.keep_cap = with_keep ? s.keep_cap : 0;
-    b.bar = dmalloc<unsigned int>(1);
+    b.bar = dmalloc<unsigned int>(kMegaBarWords);
+    b.prof = getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 8) : nullptr;
     b.eot = v.eot; b.sot = v.sot; b.translate = v.translate; b.transcribe = v.transcribe; b.solm = v.solm; b.prev = v.prev;
     b.nosp = v.nosp; b.not_ = v.not_; b.beg = v.beg; b.blank = v.blank;
     b.suppress_blank = 1; b.tdrz = 0; b.tid0_init = -1;
@@ -203,7 +205,7 @@ State::~State() {
     if (stream) cudaStreamSynchronize(stream);
     for (auto &d : dec) {
         MegaParams &b = d->mp;
-        cudaFree(b.ctl); cudaFree(b.x); cudaFree(b.q); cudaFree(b.h); cudaFree(b.part); cudaFree(b.logits); cudaFree(b.stats); cudaFree(b.tok_out);
+        cudaFree(b.ctl); cudaFree(b.x); cudaFree(b.q); cudaFree(b.h); cudaFree(b.att); cudaFree(b.part); cudaFree(b.logits); cudaFree(b.stats); cudaFree(b.tok_out);
         cudaFree(b.self_k); cudaFree(b.self_v); cudaFree(b.bar); cudaFree(d->d_mp);
         cudaFreeHost(d->h_ctl); cudaFreeHost(d->h_tok);
     }
@@ -391,6 +393,16 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     float total = 0.f; CUDA_CHECK(cudaEventElapsedTime(&total, s.ev[2], s.ev[3]));
     s.n_launches += 1;
+    if (d.mp.prof) {
+        std::vector<long long> h((size_t)s.mega_grid * 8);
+        CUDA_CHECK(cudaMemcpy(h.data(), d.mp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
+        const char *names[8] = {"arrive(membar+red)", "spin", "gemv_rows", "total", "barriers", "gemv full-wait", "gemv row compute", "gemv rows(warp0)"};
+        for (int k = 0; k < 8; k++) {
+            long long mn = h[k], mx = h[k]; double sum = 0;
+            for (int c = 0; c < s.mega_grid; c++) { long long v = h[(size_t)c * 8 + k]; mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)v; }
+            fprintf(stderr, "[mega prof] %-20s cycles/step: min %.0f mean %.0f max %.0f\n", names[k], (double)mn / n_steps, sum / s.mega_grid / n_steps, (double)mx / n_steps);
+        }
+    }
     return total / n_steps;
 }
 

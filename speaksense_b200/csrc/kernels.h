@@ -78,17 +78,19 @@ struct MegaLayer {
 constexpr int kMaxLayers = 32;
 struct MegaParams {   // device-resident descriptor of one decoder sequence (decoder_mega.cu)
     int d, H, L, T, ctx, n_vocab;
-    int xsplit, ssplit;          // (head, split) units of the cross / self attention phases
+    int xsplit, ssplit;          // (head, split) units of the cross-attention phase (ssplit unused: one CTA per head)
     float s4;                    // head_dim^-1/4
     const __half *tok_emb; const float *d_pos; const float *lnf_w, *lnf_b;
     MegaLayer layer[kMaxLayers];
-    DecCtl *ctl; float *x, *q, *h, *part, *logits, *stats; TokData *tok_out; float *keep; int keep_cap;
+    DecCtl *ctl; float *x, *q, *h, *att, *part, *logits, *stats; TokData *tok_out; float *keep; int keep_cap;
     __half *self_k, *self_v;              // [layer][head][n_text_ctx][64]
     const __half *cross_k, *cross_v;      // [layer][head][n_audio_ctx][64]
-    unsigned int *bar;
+    unsigned int *bar;           // [0] grid barrier counter, [1 + h] per-head cross-attention arrival counters
+    long long *prof;             // optional [grid][8] cycle counters (SS_MEGA_PROF=1), else null
     int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
     int suppress_blank, tdrz, tid0_init;
 };
+constexpr int kMegaBarWords = 64;
 size_t decode_mega_smem_bytes();
 void decode_mega_configure();
 int decode_mega_grid(int device);
