@@ -3,24 +3,28 @@
 // KV-cache"; SURVEY.md §8a rows a8/a9, §7.2 "batch-1 decode latency").
 //
 // Why one kernel: a decoder step is ~260 dependent mat-vec phases of 0.5-2 us of HBM traffic each.
-// As separate launches the dependency latency of each launch (6.8 us measured in round-1 v0, 16 % of
-// the HBM roofline) dominates.  Here one CTA per SM stays resident for the whole decode loop:
+// As separate launches the dependency latency of every launch dominates (6.8 us per launch measured
+// in round-1 v0 = 16 % of the HBM roofline).  Here one CTA per SM stays resident for the whole
+// decode loop:
 //   * warp 8 (producer) streams this CTA's static slice of the weights and of the cross-attention K/V
 //     cache through an 8 x 20 KB shared-memory ring with cp.async.bulk + mbarriers.  Its schedule does
 //     not depend on activations, so it runs ahead across phase, layer and token boundaries and keeps
-//     the HBM pipe busy while the consumers wait at grid barriers.
+//     the HBM pipe busy while the consumers wait for each other's activations.
 //   * warps 0..7 (consumers) compute dot products straight out of the ring against an activation
-//     vector held in registers, publish the phase's outputs (a few KB) to L2 and meet at a grid-wide
-//     barrier (one monotonic counter, release/acquire).
+//     vector held in registers.
+//   * CTAs exchange activations (a few KB per phase) through L2 with a flag-in-data protocol: every
+//     float travels as one 64-bit word {epoch, bits}, written with a single 8-byte store and polled
+//     by the readers until the epoch matches.  There are no grid barriers, fences or atomics on the
+//     critical path: a phase boundary costs one L2 store-to-load latency instead of
+//     fence + atomic + poll (measured 3.2 k cycles per barrier before this change).
 //   * logits filter, greedy sampling and the decoder-state update (whisper_process_logits /
 //     whisper_sample_token / whisper_full bookkeeping) are folded in: every CTA
 //     reduces its slice of the vocabulary, all CTAs combine the per-CTA records redundantly, so the
-//     next token is known everywhere without another barrier and the loop never returns to the host.
+//     next token is known everywhere and the loop never returns to the host.
 //
 // Arithmetic is the oracle's (oracle/whisper_oracle.c wo_decode / process_logits): f16 weights,
-// activations rounded to f16 in front of every mat-vec, f32 accumulation.
-#include <cooperative_groups.h>
-
+// activations rounded to f16 in front of every mat-vec, f32 accumulation (LayerNorm statistics in one
+// pass, E[x^2] - mean^2, instead of ggml's two passes: within the logits tolerance).
 #include "kernels.h"
 
 namespace ss {
@@ -36,35 +40,38 @@ constexpr int kMaxXs = 5120;          // largest mat-vec input (4 * d, d <= 1280
 constexpr int kMaxRowsPerCta = 512;   // per phase, x KQ partials
 constexpr int kMaxScores = 512;
 constexpr int kMaxJ = 5;              // d / 8 / 32 uint4 chunks per lane, d <= 1280
+typedef unsigned long long u64;
+
+enum SegKind : int { SEG_QKV = 0, SEG_O, SEG_CQ, SEG_XK, SEG_XV, SEG_CO, SEG_FC1, SEG_FC2, SEG_LM, SEG_COUNT };
 
 struct DecState {   // replicated per CTA (thread-uniform, lives in shared memory)
     int pos, token, n_sampled, has_ts, seek_delta, result_len, last_id, penult_id, n_kept, failed, completed, done;
 };
+struct SegTab { int row0, rows, row_bytes, rows_per_chunk, n_chunks; };
 
 struct __align__(128) MegaSmem {
     uint8_t ring[kSlots][kChunkBytes];
-    float xs[kMaxXs];
-    float lnw[1280], lnb[1280];     // LayerNorm affine of the coming phase (cp.async prefetched across the barrier)
-    float bias[kMaxRowsPerCta];     // bias slice of this CTA's rows for the coming phase
-    MegaParams P;                   // descriptor copy: no pointer chasing through L2 on the critical path
-    float acc[kMaxRowsPerCta];
-    float sc[kMaxScores];
-    float red[kConsumerWarps][64];
-    float red1[32];
+    float xs[kMaxXs];               // raw input vector of the current phase
+    float lnw[1280], lnb[1280];     // LayerNorm affine of the current phase (cp.async, overlapped with the poll)
+    float bias[kMaxRowsPerCta];     // bias slice of this CTA's rows for the current phase
+    float xown[256];                // this CTA's rows of the residual stream (stashed when the stream is polled)
+    alignas(16) MegaParams P;       // descriptor copy: no pointer chasing through L2 on the critical path
+    alignas(16) float acc[kMaxRowsPerCta];
+    alignas(16) float sc[kMaxScores];
+    alignas(16) float red[kConsumerWarps][64];
+    alignas(16) float red1[32];
+    alignas(16) float qkv[192];                 // q / current k / current v of this CTA's head
     int redi[32];
-    uint64_t full[kSlots];
+    alignas(16) uint64_t full[kSlots];
     uint64_t empty[kSlots];
+    SegTab seg[SEG_COUNT];
     DecState st;
-    unsigned int bar_target, xuse;
     volatile int stop_req;      // consumers -> producer: stop issuing
     volatile int prod_done;     // producer -> consumers: `issued` is final
     volatile uint32_t issued;
-    long long prof[8];          // thread-0 cycle counters: arrive, spin, gemv, total, barriers
+    long long prof[8];          // thread-0 cycle counters: poll, gemv, total
 };
 
-// The kernel's code is deliberately small: every phase of every layer runs through the SAME few
-// non-inlined routines.  (A fully inlined first version was 183 KB of SASS and ran at instruction-fetch
-// speed: each phase's private copy of the mat-vec loop missed the instruction caches every time.)
 extern __shared__ __align__(128) uint8_t mega_smem_raw[];
 #define SM (*reinterpret_cast<MegaSmem *>(mega_smem_raw))
 
@@ -132,155 +139,59 @@ __device__ __forceinline__ void axpy8(const uint4 &v, float p, float (&acc)[8]) 
     f = h2f(v.w); acc[6] = fmaf(p, f.x, acc[6]); acc[7] = fmaf(p, f.y, acc[7]);
 }
 
-// ------------------------------------------------------------------------------------------------
-// static work schedule: which bytes CTA `c` streams for segment kind `k` of layer `l`
-// ------------------------------------------------------------------------------------------------
-enum SegKind : int { SEG_QKV = 0, SEG_O, SEG_CQ, SEG_XK, SEG_XV, SEG_CO, SEG_FC1, SEG_FC2, SEG_LM, SEG_COUNT };
-enum Phase : int { PH_QKV = 0, PH_SELF, PH_O, PH_CQ, PH_CROSS, PH_CO, PH_FC1, PH_FC2, PH_LM, PH_NONE };
-
-struct Seg {
-    const uint8_t *base;   // first byte of this CTA's slice
-    int rows;              // rows (or keys) in the slice
-    int row0;              // first row index (global)
-    int row_bytes;
-    int rows_per_chunk;
-    int n_chunks;
-};
-
-__device__ __noinline__ Seg make_seg(int kind, int layer) {
-    const MegaParams &P = SM.P;
-    const int cta = blockIdx.x, ncta = gridDim.x;
-    Seg s;
-    const int d = P.d;
-    const __half *w = nullptr;
-    int N = 0, K = d;
-    if (kind == SEG_XK || kind == SEG_XV) {
-        if (cta >= P.H * P.xsplit) { s.base = nullptr; s.rows = 0; s.row0 = 0; s.row_bytes = 128; s.rows_per_chunk = kChunkBytes / 128; s.n_chunks = 0; return s; }
-        const int h = cta / P.xsplit, sp = cta % P.xsplit;
-        const int per = (P.T + P.xsplit - 1) / P.xsplit;
-        const int j0 = sp * per, j1 = min(P.T, j0 + per);
-        const __half *b = (kind == SEG_XK ? P.cross_k : P.cross_v) + (size_t)layer * P.T * d + ((size_t)h * P.T + j0) * 64;
-        s.base = reinterpret_cast<const uint8_t *>(b);
-        s.rows = max(0, j1 - j0); s.row0 = j0; s.row_bytes = 128;
-    } else {
-        const MegaLayer &L = P.layer[layer];
-        switch (kind) {
-            case SEG_QKV: w = L.qkv_w; N = 3 * d; break;
-            case SEG_O: w = L.o_w; N = d; break;
-            case SEG_CQ: w = L.cq_w; N = d; break;
-            case SEG_CO: w = L.co_w; N = d; break;
-            case SEG_FC1: w = L.fc1_w; N = 4 * d; break;
-            case SEG_FC2: w = L.fc2_w; N = d; K = 4 * d; break;
-            default: w = P.tok_emb; N = P.n_vocab; break;
-        }
-        const int r0 = (int)((long)cta * N / ncta), r1 = (int)((long)(cta + 1) * N / ncta);
-        s.base = reinterpret_cast<const uint8_t *>(w + (size_t)r0 * K);
-        s.rows = r1 - r0; s.row0 = r0; s.row_bytes = K * 2;
-    }
-    s.rows_per_chunk = max(1, kChunkBytes / s.row_bytes);
-    s.n_chunks = (s.rows + s.rows_per_chunk - 1) / s.rows_per_chunk;
-    return s;
+// ---- flag-in-data exchange through L2: one 64-bit word {epoch << 32 | float bits} per value -------
+__device__ __forceinline__ void ll_store(u64 *p, float v, uint32_t epoch) {
+    const u64 w = ((u64)epoch << 32) | (u64)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-
-// static (weight-side) small operands of phase `ph`: issued before a grid barrier, landed after it
-__device__ __noinline__ void prefetch_static(int ph, int il) {
-    MegaSmem &sm = SM;
-    const MegaParams &P = sm.P;
-    const int d = P.d, tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
-    const float *lw = nullptr, *lb = nullptr, *bias = nullptr;
-    int N = 0;
-    if (ph < PH_LM) {
-        const MegaLayer &ly = P.layer[il];
-        switch (ph) {
-            case PH_QKV: lw = ly.ln1_w; lb = ly.ln1_b; bias = ly.qkv_b; N = 3 * d; break;
-            case PH_O: bias = ly.o_b; N = d; break;
-            case PH_CQ: lw = ly.ln2_w; lb = ly.ln2_b; bias = ly.cq_b; N = d; break;
-            case PH_CO: bias = ly.co_b; N = d; break;
-            case PH_FC1: lw = ly.ln3_w; lb = ly.ln3_b; bias = ly.fc1_b; N = 4 * d; break;
-            case PH_FC2: bias = ly.fc2_b; N = d; break;
-            default: break;
-        }
-    } else if (ph == PH_LM) { lw = P.lnf_w; lb = P.lnf_b; }
-    if (lw) for (int i = tid; i < (d >> 2); i += kConsumerThreads) { cp_async16(&sm.lnw[4 * i], lw + 4 * i); cp_async16(&sm.lnb[4 * i], lb + 4 * i); }
-    if (bias) {
-        const int r0 = (int)((long)cta * N / ncta), r1 = (int)((long)(cta + 1) * N / ncta);
-        for (int R = tid; R < r1 - r0; R += kConsumerThreads) cp_async4(&sm.bias[R], bias + r0 + R);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+__device__ __forceinline__ ulonglong2 ll_load2(const u64 *p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
 }
-
-// grid barrier: one monotonic counter (reset by the host before launch).  Arrive = release-atomic after
-// the CTA barrier (cumulative over the CTA's stores, which are therefore in L2 before the count moves);
-// wait = relaxed gpu-scope poll.  Everything another CTA produced is read with ld.global.cg (L2, the
-// point of coherence) after the poll exits, so no acquire fence / L1 invalidation (CCTL.IVALL) is
-// needed.  The next phase's static operands are prefetched with cp.async while thread 0 polls.
-__device__ __noinline__ void grid_sync(int next_ph, int next_il) {
-    MegaSmem &sm = SM;
-    consumer_sync();
-    if (next_ph != PH_NONE) prefetch_static(next_ph, next_il);
-    if (threadIdx.x == 0) {
-        unsigned int *bar = sm.P.bar;
-        const unsigned int target = sm.bar_target + gridDim.x;
-        sm.bar_target = target;
-        const long long c0 = clock64();
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-        const long long c1 = clock64();
-        unsigned int v;
-        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
-        sm.prof[0] += c1 - c0; sm.prof[1] += clock64() - c1; sm.prof[4] += 1;
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    consumer_sync();
-}
-
-// consumer: rows of the current segment against the x vector staged in sm.xs; kq (1 or 4) warps share a
-// row (K split in kq slices of d) so the slice of x a lane needs lives in registers.
-__device__ __noinline__ uint32_t gemv_rows(uint32_t cons, int rows, int row_bytes, int rows_per_chunk, int n_chunks, int d, int kq) {
-    MegaSmem &sm = SM;
-    const long long tg0 = clock64();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int quarter = warp & (kq - 1);
-    const int group = kq == 1 ? warp : (warp >> 2);
-    const int gmask = kConsumerWarps / kq - 1;   // groups are a power of two
-    const int nchunk = d >> 3;                   // uint4 chunks per row slice
-    float4 xa[kMaxJ], xb[kMaxJ];
-    {
-        const float4 *x4 = reinterpret_cast<const float4 *>(sm.xs + quarter * d);
+// poll n (even) flagged floats into dst (shared); every thread spins only on its own words.
+// Returns this thread's {sum, sum of squares} of what it fetched (LayerNorm statistics for free).
+__device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, float *dst) {
+    const int n2 = n >> 1, tid = threadIdx.x;
+    float s = 0.f, s2 = 0.f;
+    const long long t0 = clock64();
+    for (int base = 0; base < n2; base += kConsumerThreads * kMaxJ) {
+        ulonglong2 v[kMaxJ];
+        bool all;
+        do {
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) { const int i = base + tid + j * kConsumerThreads; if (i < n2) v[j] = ll_load2(buf + 2 * i); }
+            all = true;
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) {
+                const int i = base + tid + j * kConsumerThreads;
+                if (i < n2 && ((uint32_t)(v[j].x >> 32) != epoch || (uint32_t)(v[j].y >> 32) != epoch)) all = false;
+            }
+        } while (!all);
 #pragma unroll
         for (int j = 0; j < kMaxJ; j++) {
-            const int c = lane + 32 * j;
-            if (c < nchunk) { xa[j] = x4[2 * c]; xb[j] = x4[2 * c + 1]; }
-            else { xa[j] = make_float4(0, 0, 0, 0); xb[j] = xa[j]; }
+            const int i = base + tid + j * kConsumerThreads;
+            if (i < n2) {
+                const float a = __uint_as_float((uint32_t)v[j].x), b = __uint_as_float((uint32_t)v[j].y);
+                reinterpret_cast<float2 *>(dst)[i] = make_float2(a, b);
+                s += a + b; s2 += a * a + b * b;
+            }
         }
     }
-    for (int ch = 0; ch < n_chunks; ch++) {
-        const int slot = cons % kSlots;
-        const long long tw0 = clock64();
-        mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
-        if (threadIdx.x == 0) sm.prof[5] += clock64() - tw0;
-        const int rbase = ch * rows_per_chunk;
-        const int nrows = min(rows_per_chunk, rows - rbase);
-        for (int r = 0; r < nrows; r++) {
-            const int R = rbase + r;
-            if ((R & gmask) != group) continue;
-            const long long tr0 = clock64();
-            const uint4 *w = reinterpret_cast<const uint4 *>(sm.ring[slot] + (size_t)r * row_bytes + (size_t)quarter * d * 2);
-            uint4 u[kMaxJ];
-#pragma unroll
-            for (int j = 0; j < kMaxJ; j++) { const int c = lane + 32 * j; u[j] = c < nchunk ? w[c] : make_uint4(0, 0, 0, 0); }
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < kMaxJ; j++) { if (j & 1) a1 = dot8(u[j], xa[j], xb[j], a1); else a0 = dot8(u[j], xa[j], xb[j], a0); }
-            const float a = warp_sum(a0 + a1);
-            if (lane == 0) sm.acc[R * kq + quarter] = a;
-            if (threadIdx.x == 0) { sm.prof[6] += clock64() - tr0; sm.prof[7] += 1; }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[slot]);
-        cons++;
-    }
-    if (threadIdx.x == 0) sm.prof[2] += clock64() - tg0;
-    return cons;
+    if (tid == 0) SM.prof[0] += clock64() - t0;
+    return make_float2(s, s2);
+}
+
+// static (weight-side) small operands of a mat-vec phase, fetched with cp.async while the input is polled
+__device__ __forceinline__ void prefetch_ln(const float *lw, const float *lb, int d) {
+    MegaSmem &sm = SM;
+    if (lw) for (int i = threadIdx.x; i < (d >> 2); i += kConsumerThreads) { cp_async16(&sm.lnw[4 * i], lw + 4 * i); cp_async16(&sm.lnb[4 * i], lb + 4 * i); }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_bias(const float *bias, int row0, int rows) {
+    MegaSmem &sm = SM;
+    if (bias) for (int R = threadIdx.x; R < rows; R += kConsumerThreads) cp_async4(&sm.bias[R], bias + row0 + R);
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // block-wide (256 consumer threads) reductions; result broadcast
@@ -295,6 +206,17 @@ __device__ __forceinline__ float consumer_sum(float v) {
     for (int i = 0; i < kConsumerWarps; i++) t += sm.red1[i];
     return t;
 }
+__device__ __forceinline__ float2 consumer_sum2(float2 v) {
+    MegaSmem &sm = SM;
+    v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+    consumer_sync();
+    if ((threadIdx.x & 31) == 0) { sm.red1[threadIdx.x >> 5] = v.x; sm.red1[8 + (threadIdx.x >> 5)] = v.y; }
+    consumer_sync();
+    float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kConsumerWarps; i++) { t.x += sm.red1[i]; t.y += sm.red1[8 + i]; }
+    return t;
+}
 __device__ __forceinline__ float consumer_max(float v) {
     MegaSmem &sm = SM;
     v = warp_max(v);
@@ -307,35 +229,8 @@ __device__ __forceinline__ float consumer_max(float v) {
     return t;
 }
 
-// LayerNorm of the K-vector already in sm.xs (ggml_norm + affine, eps 1e-5), rounded to f16
-__device__ __noinline__ void ln_inplace(int K) {
-    MegaSmem &sm = SM;
-    const int tid = threadIdx.x;
-    float s = 0.f;
-    for (int i = tid; i < K; i += kConsumerThreads) s += sm.xs[i];
-    const float mean = consumer_sum(s) / K;
-    float s2 = 0.f;
-    for (int i = tid; i < K; i += kConsumerThreads) { const float v = sm.xs[i] - mean; sm.xs[i] = v; s2 += v * v; }
-    const float var = consumer_sum(s2) / K;
-    const float scale = rsqrtf(var + 1e-5f);
-    for (int i = tid; i < K; i += kConsumerThreads) sm.xs[i] = r16(sm.xs[i] * scale * sm.lnw[i] + sm.lnb[i]);
-    consumer_sync();
-}
-
-// n floats (multiple of 4) from L2 (ld.global.cg: produced by other CTAs) into sm.xs with all loads of a
-// thread in flight at once: one L2 round trip on the critical path.
-__device__ __noinline__ void load_xs(const float *g, int n) {
-    MegaSmem &sm = SM;
-    float4 v[kMaxJ];
-    const int n4 = n >> 2;
-#pragma unroll
-    for (int j = 0; j < kMaxJ; j++) { const int i = threadIdx.x + j * kConsumerThreads; v[j] = i < n4 ? __ldcg(reinterpret_cast<const float4 *>(g) + i) : make_float4(0, 0, 0, 0); }
-#pragma unroll
-    for (int j = 0; j < kMaxJ; j++) { const int i = threadIdx.x + j * kConsumerThreads; if (i < n4) reinterpret_cast<float4 *>(sm.xs)[i] = v[j]; }
-}
-
-// token embedding + positional embedding -> sm.xs (every CTA) and the residual stream in L2 (CTA 0)
-__device__ __noinline__ void embed_xs() {
+// token embedding + positional embedding -> sm.xs; returns the thread's {sum, sumsq}
+__device__ __noinline__ float2 embed_xs() {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
     const int d = P.d, tid = threadIdx.x;
@@ -344,8 +239,123 @@ __device__ __noinline__ void embed_xs() {
     float v[kMaxJ];
 #pragma unroll
     for (int j = 0; j < kMaxJ; j++) { const int i = tid + j * kConsumerThreads; v[j] = i < d ? __half2float(__ldg(e + i)) + __ldg(pe + i) : 0.f; }
+    float s = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxJ; j++) { const int i = tid + j * kConsumerThreads; if (i < d) { sm.xs[i] = v[j]; if (blockIdx.x == 0) P.x[i] = v[j]; } }
+    for (int j = 0; j < kMaxJ; j++) { const int i = tid + j * kConsumerThreads; if (i < d) { sm.xs[i] = v[j]; s += v[j]; s2 += v[j] * v[j]; } }
+    return make_float2(s, s2);
+}
+
+// One mat-vec phase, start to finish: prefetch static operands, poll the input vector, (LayerNorm), rows
+// of this CTA's slice straight out of the ring, epilogue, flagged stores of the outputs.
+//   kind  : SEG_QKV / SEG_O / SEG_CQ / SEG_CO / SEG_FC1 / SEG_FC2 / SEG_LM
+//   ep_in : epoch the input carries; outputs are published with ep_out
+__device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uint32_t ep_in, uint32_t ep_out) {
+    MegaSmem &sm = SM;
+    const MegaParams &P = sm.P;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = P.d;
+    const SegTab seg = sm.seg[kind];
+    const bool has_ln = kind == SEG_QKV || kind == SEG_CQ || kind == SEG_FC1 || kind == SEG_LM;
+    const int kq = kind == SEG_FC2 ? 4 : 1;
+    const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : kind == SEG_FC1 ? 4 : 5;
+    const int lidx = kind == SEG_QKV ? 0 : kind == SEG_CQ ? 1 : 2;
+    const SegTab own = sm.seg[SEG_O];          // partition of the d residual rows
+    // ---- static operands: LayerNorm affine now (lands while the input is polled); the bias slice after the
+    //      first CTA barrier of this phase (the previous phase's epilogue may still be reading sm.bias)
+    if (kind == SEG_LM) prefetch_ln(P.lnf_w, P.lnf_b, d);
+    else prefetch_ln(has_ln ? P.layer[il].lnw[lidx] : nullptr, has_ln ? P.layer[il].lnb[lidx] : nullptr, d);
+    // ---- input vector
+    float2 ss;
+    if (kind == SEG_QKV && il == 0) ss = embed_xs();
+    else {
+        const u64 *src = kind == SEG_QKV || kind == SEG_LM ? P.xA : kind == SEG_O ? P.att1 : kind == SEG_CQ ? P.xB : kind == SEG_CO ? P.att2
+                         : kind == SEG_FC1 ? P.xC : P.hbuf;
+        ss = poll_vec(src, kind == SEG_FC2 ? 4 * d : d, ep_in, sm.xs);
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (has_ln) {
+        const float2 t = consumer_sum2(ss);     // also publishes sm.xs to every consumer thread
+        mean = t.x / d;
+        rstd = rsqrtf(fmaxf(t.y / d - mean * mean, 0.f) + 1e-5f);
+        if (kind != SEG_LM && tid < own.rows) sm.xown[tid] = sm.xs[own.row0 + tid];
+    } else consumer_sync();
+    prefetch_bias(kind == SEG_LM ? nullptr : P.layer[il].b[widx], seg.row0, seg.rows);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");     // LayerNorm affine landed (bias may still be in flight)
+    consumer_sync();
+    // ---- the slice of x this lane multiplies with, in registers (LayerNorm applied on the way)
+    const long long tg0 = clock64();
+    const int quarter = warp & (kq - 1);
+    const int group = kq == 1 ? warp : (warp >> 2);
+    const int ngroups = kConsumerWarps / kq;
+    const int nchunk = d >> 3;
+    float4 xa[kMaxJ], xb[kMaxJ];
+    {
+        const float4 *x4 = reinterpret_cast<const float4 *>(sm.xs + quarter * d);
+        const float4 *w4 = reinterpret_cast<const float4 *>(sm.lnw), *b4 = reinterpret_cast<const float4 *>(sm.lnb);
+#pragma unroll
+        for (int j = 0; j < kMaxJ; j++) {
+            const int c = lane + 32 * j;
+            if (c < nchunk) {
+                xa[j] = x4[2 * c]; xb[j] = x4[2 * c + 1];
+                if (has_ln) {
+                    const float4 wa = w4[2 * c], wb = w4[2 * c + 1], ba = b4[2 * c], bb = b4[2 * c + 1];
+                    xa[j].x = r16((xa[j].x - mean) * rstd * wa.x + ba.x); xa[j].y = r16((xa[j].y - mean) * rstd * wa.y + ba.y);
+                    xa[j].z = r16((xa[j].z - mean) * rstd * wa.z + ba.z); xa[j].w = r16((xa[j].w - mean) * rstd * wa.w + ba.w);
+                    xb[j].x = r16((xb[j].x - mean) * rstd * wb.x + bb.x); xb[j].y = r16((xb[j].y - mean) * rstd * wb.y + bb.y);
+                    xb[j].z = r16((xb[j].z - mean) * rstd * wb.z + bb.z); xb[j].w = r16((xb[j].w - mean) * rstd * wb.w + bb.w);
+                }
+            } else { xa[j] = make_float4(0, 0, 0, 0); xb[j] = xa[j]; }
+        }
+    }
+    // ---- rows out of the ring
+    for (int ch = 0; ch < seg.n_chunks; ch++) {
+        const int slot = cons & (kSlots - 1);
+        mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
+        const int rbase = ch * seg.rows_per_chunk;
+        const int rend = min(rbase + seg.rows_per_chunk, seg.rows);
+        for (int R = rbase + ((group - rbase) & (ngroups - 1)); R < rend; R += ngroups) {
+            const uint4 *w = reinterpret_cast<const uint4 *>(sm.ring[slot] + (size_t)(R - rbase) * seg.row_bytes + (size_t)quarter * d * 2);
+            uint4 u[kMaxJ];
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) { const int c = lane + 32 * j; u[j] = c < nchunk ? w[c] : make_uint4(0, 0, 0, 0); }
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) { if (j & 1) a1 = dot8(u[j], xa[j], xb[j], a1); else a0 = dot8(u[j], xa[j], xb[j], a0); }
+            const float a = warp_sum(a0 + a1);
+            if (lane == 0) sm.acc[R * kq + quarter] = a;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[slot]);
+        cons++;
+    }
+    if (tid == 0) sm.prof[1] += clock64() - tg0;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    consumer_sync();
+    // ---- epilogue
+    if (kind == SEG_QKV) {
+        const int pos = sm.st.pos;
+        __half *sk = P.self_k + (size_t)il * P.ctx * d, *sv = P.self_v + (size_t)il * P.ctx * d;
+        for (int R = tid; R < seg.rows; R += kConsumerThreads) {
+            const int row = seg.row0 + R;
+            const float v = sm.acc[R] + sm.bias[R];
+            if (row < d) ll_store(P.q1 + row, r16(v * P.s4), ep_out);
+            else if (row < 2 * d) {
+                const int n = row - d; const __half hk = __float2half_rn(v * P.s4);
+                sk[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
+            } else {
+                const int n = row - 2 * d; const __half hv = __float2half_rn(v);
+                sv[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
+            }
+        }
+    } else if (kind != SEG_LM && tid < seg.rows) {
+        const int row = seg.row0 + tid;
+        if (kind == SEG_FC2) ll_store(P.xA + row, sm.xown[tid] + (sm.acc[4 * tid] + sm.acc[4 * tid + 1] + sm.acc[4 * tid + 2] + sm.acc[4 * tid + 3]) + sm.bias[tid], ep_out);
+        else if (kind == SEG_O) ll_store(P.xB + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
+        else if (kind == SEG_CO) ll_store(P.xC + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
+        else if (kind == SEG_CQ) ll_store(P.q2 + row, r16((sm.acc[tid] + sm.bias[tid]) * P.s4), ep_out);
+        else ll_store(P.hbuf + row, gelu16(sm.acc[tid] + sm.bias[tid]), ep_out);
+    }
+    return cons;
 }
 
 // scores of one query against n key rows (128 B each) at `K`: 8 lanes per row, 4 rows per warp per step.
@@ -409,42 +419,62 @@ __device__ __forceinline__ float attn_fold(float (&acc)[8]) {
     return o;
 }
 
-// P1: self-attention, one CTA per head, K/V straight from L2 (written by this kernel: ld.global.cg)
-__device__ __noinline__ void self_attn(int il) {
+// self-attention, one CTA per head: past keys/values from the KV cache in L2, the current token's q/k/v
+// from the flagged exchange buffers
+__device__ __noinline__ void self_attn(int il, uint32_t ep) {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
-    const int h = blockIdx.x;
+    const int h = blockIdx.x, tid = threadIdx.x;
     if (h >= P.H) return;
-    const int n = sm.st.pos + 1, d = P.d, l8 = threadIdx.x & 7;
+    const int n_past = sm.st.pos, d = P.d, l8 = tid & 7;
+    if (tid < 96) {   // 3 x 64 flagged floats: q, k, v of this head
+        const int which = tid >> 5, i2 = tid & 31;
+        const u64 *src = (which == 0 ? P.q1 : which == 1 ? P.kcur : P.vcur) + h * 64 + 2 * i2;
+        ulonglong2 v;
+        do { v = ll_load2(src); } while ((uint32_t)(v.x >> 32) != ep || (uint32_t)(v.y >> 32) != ep);
+        sm.qkv[which * 64 + 2 * i2] = __uint_as_float((uint32_t)v.x); sm.qkv[which * 64 + 2 * i2 + 1] = __uint_as_float((uint32_t)v.y);
+    }
+    consumer_sync();
     const uint8_t *Kh = reinterpret_cast<const uint8_t *>(P.self_k + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
     const uint8_t *Vh = reinterpret_cast<const uint8_t *>(P.self_v + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
-    const float4 qa = __ldcg(reinterpret_cast<const float4 *>(P.q + h * 64 + l8 * 8));
-    const float4 qb = __ldcg(reinterpret_cast<const float4 *>(P.q + h * 64 + l8 * 8 + 4));
-    const float lmax = attn_scores<false>(Kh, n, 0, qa, qb, -INFINITY);
+    const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
+    float lmax = attn_scores<false>(Kh, n_past, 0, qa, qb, -INFINITY);
+    if (tid < 32) {   // the current token's own key
+        float ds = sm.qkv[tid] * sm.qkv[64 + tid] + sm.qkv[32 + tid] * sm.qkv[96 + tid];
+        ds = warp_sum(ds);
+        if (tid == 0) sm.sc[n_past] = ds;
+        lmax = fmaxf(lmax, ds);
+    }
     const float m = consumer_max(lmax);
     float lsum = 0.f;
-    for (int j = threadIdx.x; j < n; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; lsum += e; }
+    for (int j = tid; j <= n_past; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; lsum += e; }
     const float l = consumer_sum(lsum);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    attn_pv<false>(Vh, n, 0, acc);
-    const float o = attn_fold(acc);
-    if (threadIdx.x < 64) P.att[h * 64 + threadIdx.x] = r16(o / l);
+    attn_pv<false>(Vh, n_past, 0, acc);
+    float o = attn_fold(acc);
+    if (tid < 64) { o += sm.sc[n_past] * sm.qkv[128 + tid]; ll_store(P.att1 + h * 64 + tid, r16(o / l), ep); }
 }
 
-// P4: cross-attention; K then V streamed through the ring; the last split of a head to finish combines the
-// head's partials into the attention vector
-__device__ __noinline__ uint32_t cross_attn(int il, uint32_t cons) {
+// cross-attention; K then V of this CTA's (head, key split) streamed through the ring; split 0 of every head
+// folds the head's partials into the attention vector
+__device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
-    const Seg sk = make_seg(SEG_XK, il);
+    const SegTab sk = sm.seg[SEG_XK];
     if (sk.n_chunks == 0) return cons;
     const int tid = threadIdx.x, lane = tid & 31, l8 = tid & 7;
     const int ns = P.xsplit, h = blockIdx.x / ns, sp = blockIdx.x % ns, n = sk.rows;
-    const float4 qa = __ldcg(reinterpret_cast<const float4 *>(P.q + h * 64 + l8 * 8));
-    const float4 qb = __ldcg(reinterpret_cast<const float4 *>(P.q + h * 64 + l8 * 8 + 4));
+    if (tid < 32) {
+        const u64 *src = P.q2 + h * 64 + 2 * tid;
+        ulonglong2 v;
+        do { v = ll_load2(src); } while ((uint32_t)(v.x >> 32) != ep || (uint32_t)(v.y >> 32) != ep);
+        sm.qkv[2 * tid] = __uint_as_float((uint32_t)v.x); sm.qkv[2 * tid + 1] = __uint_as_float((uint32_t)v.y);
+    }
+    consumer_sync();
+    const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
     float lmax = -INFINITY;
     for (int ch = 0; ch < sk.n_chunks; ch++) {
-        const int slot = cons % kSlots;
+        const int slot = cons & (kSlots - 1);
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
         lmax = attn_scores<true>(sm.ring[slot], nk, kbase, qa, qb, lmax);
@@ -458,7 +488,7 @@ __device__ __noinline__ uint32_t cross_attn(int il, uint32_t cons) {
     const float l = consumer_sum(lsum);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int ch = 0; ch < sk.n_chunks; ch++) {     // the V slice has the same chunking as the K slice
-        const int slot = cons % kSlots;
+        const int slot = cons & (kSlots - 1);
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
         attn_pv<true>(sm.ring[slot], nk, kbase, acc);
@@ -467,32 +497,24 @@ __device__ __noinline__ uint32_t cross_attn(int il, uint32_t cons) {
         cons++;
     }
     const float o = attn_fold(acc);
-    float *out = P.part + ((size_t)h * ns + sp) * 66;
-    if (tid < 64) out[2 + tid] = o;
-    if (tid == 0) { out[0] = m; out[1] = l; }
+    u64 *out = P.part + ((size_t)h * ns + sp) * 66;
+    if (tid < 64) ll_store(out + 2 + tid, o, ep);
+    if (tid == 0) { ll_store(out, m, ep); ll_store(out + 1, l, ep); }
+    if (sp != 0) return cons;
+    // ---- split 0 folds all ns (<= 8) partial records of head h
+    poll_vec(P.part + (size_t)h * ns * 66, ns * 66, ep, sm.xs);
     consumer_sync();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int old = atomicAdd(P.bar + 1 + h, 1u);
-        sm.redi[24] = (old == sm.xuse * (unsigned int)ns + (unsigned int)ns - 1u) ? 1 : 0;
-    }
-    consumer_sync();
-    if (sm.redi[24] && tid < 64) {   // last split of head h: fold all ns partials (<= 8)
-        const float *p = P.part + (size_t)h * ns * 66;
-        float pm[8], pl[8], po[8];
-#pragma unroll
-        for (int s2 = 0; s2 < 8; s2++) {
-            if (s2 < ns) { pm[s2] = __ldcg(p + s2 * 66); pl[s2] = __ldcg(p + s2 * 66 + 1); po[s2] = __ldcg(p + s2 * 66 + 2 + tid); }
-            else { pm[s2] = -INFINITY; pl[s2] = 0.f; po[s2] = 0.f; }
-        }
+    if (tid < 64) {
         float M = -INFINITY;
-#pragma unroll
-        for (int s2 = 0; s2 < 8; s2++) M = fmaxf(M, pm[s2]);
+        for (int s2 = 0; s2 < ns; s2++) M = fmaxf(M, sm.xs[s2 * 66]);
         float Lsum = 0.f, oo = 0.f;
-#pragma unroll
-        for (int s2 = 0; s2 < 8; s2++) if (pm[s2] > -INFINITY) { const float e = __expf(pm[s2] - M); Lsum += pl[s2] * e; oo += po[s2] * e; }
-        P.att[h * 64 + tid] = r16(oo / Lsum);
+        for (int s2 = 0; s2 < ns; s2++) {
+            const float pm = sm.xs[s2 * 66];
+            if (pm > -INFINITY) { const float e = __expf(pm - M); Lsum += sm.xs[s2 * 66 + 1] * e; oo += sm.xs[s2 * 66 + 2 + tid] * e; }
+        }
+        ll_store(P.att2 + h * 64 + tid, r16(oo / Lsum), ep);
     }
+    consumer_sync();
     return cons;
 }
 
@@ -515,10 +537,11 @@ __device__ __forceinline__ bool token_masked(const MegaParams &P, const DecState
 
 // LM-head epilogue: publish raw logits; when sampling, the logits filter (whisper_process_logits) and this
 // CTA's softmax statistics {max text, argmax, max timestamp, argmax, sum exp, sum exp over timestamps}
-__device__ __noinline__ void lm_epilogue(int rows, int row0, bool keep, bool sampling) {
+__device__ __noinline__ void lm_epilogue(bool keep, bool sampling, uint32_t ep) {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rows = sm.seg[SEG_LM].rows, row0 = sm.seg[SEG_LM].row0;
     const DecState st = sm.st;
     MaxIdx mt{-INFINITY, 0x7fffffff}, ms{-INFINITY, 0x7fffffff};
     for (int R = tid; R < rows; R += kConsumerThreads) {
@@ -550,32 +573,27 @@ __device__ __noinline__ void lm_epilogue(int rows, int row0, bool keep, bool sam
     }
     sa = consumer_sum(sa);
     sb = consumer_sum(sb);
-    if (tid == 0) {
-        float *rec = P.stats + (size_t)blockIdx.x * 8;
-        rec[0] = mt.v; rec[1] = __int_as_float(mt.i); rec[2] = ms.v; rec[3] = __int_as_float(ms.i); rec[4] = sa; rec[5] = sb;
+    if (tid < 8) {
+        u64 *rec = P.stats + (size_t)blockIdx.x * 8;
+        const float vals[8] = {mt.v, __int_as_float(mt.i), ms.v, __int_as_float(ms.i), sa, sb, 0.f, 0.f};
+        ll_store(rec + tid, vals[tid], ep);
     }
 }
 
 // combine the per-CTA records (every CTA, identically), greedy sample (whisper_sample_token best=true) and
 // the per-token decoder bookkeeping of whisper_full; updates sm.st
-__device__ __noinline__ void sample_and_update(int seek, int seek_end, int n_max) {
+__device__ __noinline__ void sample_and_update(int seek, int seek_end, int n_max, uint32_t ep) {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
     const int tid = threadIdx.x, lane = tid & 31, ncta = gridDim.x;
+    poll_vec(P.stats, ncta * 8, ep, sm.xs);
+    consumer_sync();
     if (tid < 32) {
-        float r0[5], r1[5], r2[5], r3[5], r4[5], r5[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const int c = lane + 32 * k;
-            if (c < ncta) {
-                const float4 a = __ldcg(reinterpret_cast<const float4 *>(P.stats + (size_t)c * 8));
-                const float2 b = __ldcg(reinterpret_cast<const float2 *>(P.stats + (size_t)c * 8 + 4));
-                r0[k] = a.x; r1[k] = a.y; r2[k] = a.z; r3[k] = a.w; r4[k] = b.x; r5[k] = b.y;
-            } else { r0[k] = -INFINITY; r1[k] = __int_as_float(0x7fffffff); r2[k] = -INFINITY; r3[k] = __int_as_float(0x7fffffff); r4[k] = 0.f; r5[k] = 0.f; }
-        }
         MaxIdx mt{-INFINITY, 0x7fffffff}, ms{-INFINITY, 0x7fffffff};
-#pragma unroll
-        for (int k = 0; k < 5; k++) { mt = better(mt, MaxIdx{r0[k], __float_as_int(r1[k])}); ms = better(ms, MaxIdx{r2[k], __float_as_int(r3[k])}); }
+        for (int c = lane; c < ncta; c += 32) {
+            const float *r = sm.xs + c * 8;
+            mt = better(mt, MaxIdx{r[0], __float_as_int(r[1])}); ms = better(ms, MaxIdx{r[2], __float_as_int(r[3])});
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             MaxIdx a{__shfl_xor_sync(0xffffffffu, mt.v, o), __shfl_xor_sync(0xffffffffu, mt.i, o)}; mt = better(mt, a);
@@ -583,11 +601,11 @@ __device__ __noinline__ void sample_and_update(int seek, int seek_end, int n_max
         }
         const float m_all = fmaxf(mt.v, ms.v);
         float sa = 0.f, sb = 0.f;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const float cm = fmaxf(r0[k], r2[k]), cs = r2[k];
-            if (cm > -INFINITY) sa += r4[k] * expf(cm - m_all);
-            if (cs > -INFINITY) sb += r5[k] * expf(cs - ms.v);
+        for (int c = lane; c < ncta; c += 32) {
+            const float *r = sm.xs + c * 8;
+            const float cm = fmaxf(r[0], r[2]), cs = r[2];
+            if (cm > -INFINITY) sa += r[4] * expf(cm - m_all);
+            if (cs > -INFINITY) sb += r[5] * expf(cs - ms.v);
         }
         sa = warp_sum(sa); sb = warp_sum(sb);
         if (lane == 0) {
@@ -632,13 +650,47 @@ __device__ __noinline__ void sample_and_update(int seek, int seek_end, int n_max
     consumer_sync();
 }
 
+// per-CTA slice of every segment kind (computed once: the 64-bit divisions stay off the critical path)
+__device__ void build_segtab() {
+    MegaSmem &sm = SM;
+    const MegaParams &P = sm.P;
+    const int cta = blockIdx.x, ncta = gridDim.x, d = P.d;
+    for (int kind = threadIdx.x; kind < SEG_COUNT; kind += blockDim.x) {
+        SegTab s;
+        if (kind == SEG_XK || kind == SEG_XV) {
+            s.row_bytes = 128;
+            if (cta >= P.H * P.xsplit) { s.row0 = 0; s.rows = 0; }
+            else {
+                const int sp = cta % P.xsplit, per = (P.T + P.xsplit - 1) / P.xsplit;
+                s.row0 = sp * per; s.rows = max(0, min(P.T, s.row0 + per) - s.row0);
+            }
+        } else {
+            const int N = kind == SEG_QKV ? 3 * d : kind == SEG_FC1 ? 4 * d : kind == SEG_LM ? P.n_vocab : d;
+            const int K = kind == SEG_FC2 ? 4 * d : d;
+            s.row0 = (int)((long)cta * N / ncta); s.rows = (int)((long)(cta + 1) * N / ncta) - s.row0; s.row_bytes = K * 2;
+        }
+        s.rows_per_chunk = max(1, kChunkBytes / s.row_bytes);
+        s.n_chunks = (s.rows + s.rows_per_chunk - 1) / s.rows_per_chunk;
+        sm.seg[kind] = s;
+    }
+}
+__device__ __forceinline__ const uint8_t *seg_base(const MegaParams &P, const SegTab &s, int kind, int il) {
+    if (kind == SEG_XK || kind == SEG_XV) {
+        const int h = blockIdx.x / P.xsplit;
+        return reinterpret_cast<const uint8_t *>((kind == SEG_XK ? P.cross_k : P.cross_v) + (size_t)il * P.T * P.d + ((size_t)h * P.T + s.row0) * 64);
+    }
+    const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : kind == SEG_FC1 ? 4 : 5;
+    const __half *w = kind == SEG_LM ? P.tok_emb : P.layer[il].w[widx];
+    return reinterpret_cast<const uint8_t *>(w) + (size_t)s.row0 * s.row_bytes;
+}
+
 }  // namespace
 
 // ================================================================================================
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const MegaParams *__restrict__ Pp, int max_steps) {
     MegaSmem &sm = SM;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cta = blockIdx.x, ncta = gridDim.x;
+    const int cta = blockIdx.x;
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(Pp);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.P);
@@ -646,7 +698,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     }
     __syncthreads();
     const MegaParams &P = sm.P;
-    const int d = P.d, L = P.L;
+    const int L = P.L;
+    build_segtab();
 
     DecCtl *ctl = P.ctl;
     // snapshot of the control block (identical in every CTA)
@@ -657,7 +710,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 
     if (tid == 0) {
         for (int s = 0; s < kSlots; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
-        sm.stop_req = 0; sm.prod_done = 0; sm.issued = 0; sm.bar_target = 0; sm.xuse = 0;
+        sm.stop_req = 0; sm.prod_done = 0; sm.issued = 0;
         for (int i = 0; i < 8; i++) sm.prof[i] = 0;
         DecState st;
         st.pos = pos_start; st.token = ctl->token; st.n_sampled = ctl->n_sampled; st.has_ts = ctl->has_ts; st.seek_delta = ctl->seek_delta;
@@ -682,16 +735,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
                 const int nseg = L * (SEG_LM) + (need_logits ? 1 : 0);
                 for (int si = 0; si < nseg && !stopped; si++) {
                     const int layer = si / SEG_LM, kind = si < L * SEG_LM ? si % SEG_LM : SEG_LM;
-                    const Seg seg = make_seg(kind, layer < L ? layer : 0);
+                    const SegTab seg = sm.seg[kind];
+                    const uint8_t *base = seg_base(P, seg, kind, layer < L ? layer : 0);
                     for (int ch = 0; ch < seg.n_chunks; ch++) {
-                        const int slot = issued % kSlots;
+                        const int slot = issued & (kSlots - 1);
                         const uint32_t par = ((issued / kSlots) & 1) ^ 1;
                         while (!mbar_try_wait(&sm.empty[slot], par)) { if (sm.stop_req) { stopped = true; break; } }
                         if (stopped || sm.stop_req) { stopped = true; break; }
                         const int rbase = ch * seg.rows_per_chunk;
                         const uint32_t bytes = (uint32_t)min(seg.rows_per_chunk, seg.rows - rbase) * seg.row_bytes;
                         mbar_expect_tx(&sm.full[slot], bytes);
-                        bulk_g2s(sm.ring[slot], seg.base + (size_t)rbase * seg.row_bytes, bytes, &sm.full[slot], policy);
+                        bulk_g2s(sm.ring[slot], base + (size_t)rbase * seg.row_bytes, bytes, &sm.full[slot], policy);
                         issued++;
                     }
                 }
@@ -707,72 +761,37 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     // ======================= consumers =======================
     uint32_t cons = 0;
     const long long t_begin = clock64();
-    prefetch_static(PH_QKV, 0);
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    consumer_sync();
+    const uint32_t ep_stride = (uint32_t)L + 1;
 
     for (int t = 0; t < steps_left; t++) {
         if (sm.st.done) break;
         const int jrel = sm.st.pos - pos0;
         const bool need_logits = all_logits || jrel >= n_prompt - 1;
+        const uint32_t ep0 = 1u + (uint32_t)t * ep_stride;      // epoch of layer il: ep0 + il; LM head input: ep0 + L
 
 #pragma unroll 1
         for (int il = 0; il < L; il++) {
-#pragma unroll 1
-            for (int ph = 0; ph < 8; ph++) {
-                if (ph == PH_SELF) {
-                    self_attn(il);
-                } else if (ph == PH_CROSS) {
-                    cons = cross_attn(il, cons);
-                    if (tid == 0) sm.xuse = sm.xuse + 1;
-                } else {
-                    const int kind = ph == PH_QKV ? SEG_QKV : ph == PH_O ? SEG_O : ph == PH_CQ ? SEG_CQ : ph == PH_CO ? SEG_CO : ph == PH_FC1 ? SEG_FC1 : SEG_FC2;
-                    const Seg seg = make_seg(kind, il);
-                    const bool resid = ph == PH_O || ph == PH_CO || ph == PH_FC2;
-                    float xres = 0.f;
-                    if (resid && tid < seg.rows) xres = __ldcg(P.x + seg.row0 + tid);   // residual rows of this CTA, in flight early
-                    if (ph == PH_QKV && il == 0) embed_xs();
-                    else load_xs(resid ? (ph == PH_FC2 ? P.h : P.att) : P.x, ph == PH_FC2 ? 4 * d : d);
-                    consumer_sync();
-                    if (!resid) ln_inplace(d);
-                    cons = gemv_rows(cons, seg.rows, seg.row_bytes, seg.rows_per_chunk, seg.n_chunks, d, ph == PH_FC2 ? 4 : 1);
-                    consumer_sync();
-                    if (ph == PH_QKV) {
-                        const int pos = sm.st.pos;
-                        __half *sk = P.self_k + (size_t)il * P.ctx * d, *sv = P.self_v + (size_t)il * P.ctx * d;
-                        for (int R = tid; R < seg.rows; R += kConsumerThreads) {
-                            const int row = seg.row0 + R;
-                            const float v = sm.acc[R] + sm.bias[R];
-                            if (row < d) P.q[row] = r16(v * P.s4);
-                            else if (row < 2 * d) { const int n = row - d; sk[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = __float2half_rn(v * P.s4); }
-                            else { const int n = row - 2 * d; sv[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = __float2half_rn(v); }
-                        }
-                    } else if (tid < seg.rows) {
-                        const int row = seg.row0 + tid;
-                        if (ph == PH_FC2) P.x[row] = xres + (sm.acc[4 * tid] + sm.acc[4 * tid + 1] + sm.acc[4 * tid + 2] + sm.acc[4 * tid + 3]) + sm.bias[tid];
-                        else if (resid) P.x[row] = xres + sm.acc[tid] + sm.bias[tid];
-                        else if (ph == PH_CQ) P.q[row] = r16((sm.acc[tid] + sm.bias[tid]) * P.s4);
-                        else P.h[row] = gelu16(sm.acc[tid] + sm.bias[tid]);
-                    }
-                }
-                int nph = ph + 1, nil = il;
-                if (ph == PH_FC2) { nil = il + 1 < L ? il + 1 : 0; nph = il + 1 < L ? PH_QKV : (need_logits ? PH_LM : PH_QKV); }
-                grid_sync(nph, nil);
-            }
+            const uint32_t ep = ep0 + (uint32_t)il;
+            cons = gemv_phase(cons, SEG_QKV, il, ep, ep);
+            self_attn(il, ep);
+            cons = gemv_phase(cons, SEG_O, il, ep, ep);
+            cons = gemv_phase(cons, SEG_CQ, il, ep, ep);
+            cons = cross_attn(cons, ep);
+            cons = gemv_phase(cons, SEG_CO, il, ep, ep);
+            cons = gemv_phase(cons, SEG_FC1, il, ep, ep);
+            cons = gemv_phase(cons, SEG_FC2, il, ep, ep + 1);
         }
 
         // ---------------- final LN + LM head + per-CTA softmax statistics ----------------
+        const uint32_t epL = ep0 + (uint32_t)L;
+        const bool sampling = do_sample && jrel >= n_prompt - 1;
         if (need_logits) {
-            load_xs(P.x, d);
-            consumer_sync();
-            ln_inplace(d);
-            const Seg seg = make_seg(SEG_LM, 0);
-            cons = gemv_rows(cons, seg.rows, seg.row_bytes, seg.rows_per_chunk, seg.n_chunks, d, 1);
-            consumer_sync();
+            cons = gemv_phase(cons, SEG_LM, 0, epL, epL);
             const bool keep = keep_logits && sm.st.n_kept < P.keep_cap;
-            lm_epilogue(seg.rows, seg.row0, keep, do_sample && jrel >= n_prompt - 1);
-            grid_sync(PH_QKV, 0);
-            if (keep) { consumer_sync(); if (tid == 0) sm.st.n_kept = sm.st.n_kept + 1; consumer_sync(); }
+            lm_epilogue(keep, sampling, epL);
+            consumer_sync();
+            if (keep && tid == 0) sm.st.n_kept = sm.st.n_kept + 1;
+            consumer_sync();
         }
         if (jrel < n_prompt - 1) {   // prompt token: feed the next one
             consumer_sync();
@@ -781,7 +800,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             continue;
         }
         if (!do_sample) { consumer_sync(); if (tid == 0) sm.st.done = 1; consumer_sync(); break; }
-        sample_and_update(seek, seek_end, n_max);
+        sample_and_update(seek, seek_end, n_max, epL);
     }
 
     // ---------------- shutdown: stop the producer, drain copies still in flight, publish the state ----------------
@@ -820,8 +839,8 @@ int decode_mega_grid(int device) {
     return sms;
 }
 
-void decode_mega_launch(const MegaParams *d_params, unsigned int *d_bar, int max_steps, int grid, cudaStream_t st) {
-    CUDA_CHECK(cudaMemsetAsync(d_bar, 0, kMegaBarWords * sizeof(unsigned int), st));
+void decode_mega_launch(const MegaParams *d_params, void *d_ll, size_t ll_bytes, int max_steps, int grid, cudaStream_t st) {
+    CUDA_CHECK(cudaMemsetAsync(d_ll, 0, ll_bytes, st));     // epochs restart at 1 on every launch
     void *args[] = {(void *)&d_params, (void *)&max_steps};
     CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)decode_mega_kernel, dim3(grid), dim3(kMegaThreads), args, decode_mega_smem_bytes(), st));
 }

@@ -141,28 +141,35 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     const size_t dd = hp.n_text_state, kv = (size_t)hp.n_text_layer * hp.n_text_ctx * dd;
     MegaParams &b = d->mp;
     b.d = hp.n_text_state; b.H = hp.n_text_head; b.L = hp.n_text_layer; b.T = hp.n_audio_ctx; b.ctx = hp.n_text_ctx; b.n_vocab = hp.n_vocab;
-    b.xsplit = std::max(1, std::min(8, s.mega_grid / b.H)); b.ssplit = std::max(1, std::min(8, s.mega_grid / b.H));
+    b.xsplit = std::max(1, std::min(8, s.mega_grid / b.H));
     b.s4 = powf((float)(b.d / b.H), -0.25f);
-    if (ceil_div(hp.n_vocab, s.mega_grid) > 500 || ceil_div(b.T, b.xsplit) > 500 || b.ctx > 512 || ceil_div(4 * b.d, s.mega_grid) > 250 || b.H > s.mega_grid || b.H + 1 > kMegaBarWords)
-        SS_THROW(-3, "device has too few SMs (%d) for the decode kernel's per-CTA work buffers", s.mega_grid);
+    if (ceil_div(hp.n_vocab, s.mega_grid) > 500 || ceil_div(b.T, b.xsplit) > 500 || b.ctx > 500 || ceil_div(4 * b.d, s.mega_grid) > 250 ||
+        b.H > s.mega_grid || s.mega_grid * 8 > 5120 || (b.d & 127))
+        SS_THROW(-3, "device has too few / too many SMs (%d) for the decode kernel's per-CTA work buffers", s.mega_grid);
     b.tok_emb = m.tok_emb; b.d_pos = m.d_pos; b.lnf_w = m.d_ln.w; b.lnf_b = m.d_ln.b;
     for (int i = 0; i < hp.n_text_layer; i++) {
         const DecLayer &L = m.dec[i]; MegaLayer &o = b.layer[i];
-        o.qkv_w = L.qkv.w; o.o_w = L.o.w; o.cq_w = L.cq.w; o.co_w = L.co.w; o.fc1_w = L.fc1.w; o.fc2_w = L.fc2.w;
-        o.qkv_b = L.qkv.b; o.o_b = L.o.b; o.cq_b = L.cq.b; o.co_b = L.co.b; o.fc1_b = L.fc1.b; o.fc2_b = L.fc2.b;
-        o.ln1_w = L.attn_ln.w; o.ln1_b = L.attn_ln.b; o.ln2_w = L.cross_ln.w; o.ln2_b = L.cross_ln.b; o.ln3_w = L.mlp_ln.w; o.ln3_b = L.mlp_ln.b;
+        const Lin *lins[6] = {&L.qkv, &L.o, &L.cq, &L.co, &L.fc1, &L.fc2};
+        for (int k = 0; k < 6; k++) { o.w[k] = lins[k]->w; o.b[k] = lins[k]->b; }
+        const LNp *lns[3] = {&L.attn_ln, &L.cross_ln, &L.mlp_ln};
+        for (int k = 0; k < 3; k++) { o.lnw[k] = lns[k]->w; o.lnb[k] = lns[k]->b; }
     }
     b.ctl = dmalloc<DecCtl>(1);
-    b.x = dmalloc<float>(dd); b.q = dmalloc<float>(dd); b.h = dmalloc<float>(4 * dd); b.att = dmalloc<float>(dd);
-    b.part = dmalloc<float>((size_t)hp.n_text_head * 32 * 66);
+    {   // flagged exchange arena
+        const size_t words = 9 * dd + 4 * dd + (size_t)hp.n_text_head * 8 * 66 + (size_t)s.mega_grid * 8;
+        d->ll_bytes = words * sizeof(ss_u64);
+        ss_u64 *p = dmalloc<ss_u64>(words);
+        d->d_ll = p;
+        b.xA = p; p += dd; b.xB = p; p += dd; b.xC = p; p += dd; b.q1 = p; p += dd; b.kcur = p; p += dd; b.vcur = p; p += dd;
+        b.att1 = p; p += dd; b.q2 = p; p += dd; b.att2 = p; p += dd; b.hbuf = p; p += 4 * dd;
+        b.part = p; p += (size_t)hp.n_text_head * 8 * 66; b.stats = p;
+    }
     b.logits = dmalloc<float>(hp.n_vocab);
-    b.stats = dmalloc<float>((size_t)s.mega_grid * 8);
     b.tok_out = dmalloc<TokData>(hp.n_text_ctx);
     b.self_k = dmalloc<__half>(kv); b.self_v = dmalloc<__half>(kv);
     CUDA_CHECK(cudaMemset(b.self_k, 0, kv * 2)); CUDA_CHECK(cudaMemset(b.self_v, 0, kv * 2));
     b.cross_k = s.cross_k; b.cross_v = s.cross_v;
     b.keep = with_keep ? s.keep : nullptr; b.keep_cap = with_keep ? s.keep_cap : 0;
-    b.bar = dmalloc<unsigned int>(kMegaBarWords);
     b.prof = getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 8) : nullptr;
     b.eot = v.eot; b.sot = v.sot; b.translate = v.translate; b.transcribe = v.transcribe; b.solm = v.solm; b.prev = v.prev;
     b.nosp = v.nosp; b.not_ = v.not_; b.beg = v.beg; b.blank = v.blank;
@@ -205,8 +212,8 @@ State::~State() {
     if (stream) cudaStreamSynchronize(stream);
     for (auto &d : dec) {
         MegaParams &b = d->mp;
-        cudaFree(b.ctl); cudaFree(b.x); cudaFree(b.q); cudaFree(b.h); cudaFree(b.att); cudaFree(b.part); cudaFree(b.logits); cudaFree(b.stats); cudaFree(b.tok_out);
-        cudaFree(b.self_k); cudaFree(b.self_v); cudaFree(b.bar); cudaFree(d->d_mp);
+        cudaFree(b.ctl); cudaFree(d->d_ll); cudaFree(b.logits); cudaFree(b.tok_out); if (b.prof) cudaFree(b.prof);
+        cudaFree(b.self_k); cudaFree(b.self_v); cudaFree(d->d_mp);
         cudaFreeHost(d->h_ctl); cudaFreeHost(d->h_tok);
     }
     void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, P, att, ff, enc16, x, S, enc_out, cross_k, cross_v, keep};
@@ -361,7 +368,7 @@ static void ensure_params(State &s, Decoder &d) {
 // one launch of the persistent decode kernel: runs until the device says done or `max_steps` tokens
 static void run_steps(State &s, Decoder &d, int max_steps) {
     ensure_params(s, d);
-    decode_mega_launch(d.d_mp, d.mp.bar, max_steps, s.mega_grid, s.stream);
+    decode_mega_launch(d.d_mp, d.d_ll, d.ll_bytes, max_steps, s.mega_grid, s.stream);
     s.n_launches += 1;
     CUDA_CHECK(cudaMemcpyAsync(d.h_ctl, d.mp.ctl, offsetof(DecCtl, prompt), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -388,7 +395,7 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     (void)m;
     upload_ctl(s, d);
     CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
-    decode_mega_launch(d.d_mp, d.mp.bar, n_steps, s.mega_grid, s.stream);
+    decode_mega_launch(d.d_mp, d.d_ll, d.ll_bytes, n_steps, s.mega_grid, s.stream);
     CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     float total = 0.f; CUDA_CHECK(cudaEventElapsedTime(&total, s.ev[2], s.ev[3]));
@@ -396,8 +403,9 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     if (d.mp.prof) {
         std::vector<long long> h((size_t)s.mega_grid * 8);
         CUDA_CHECK(cudaMemcpy(h.data(), d.mp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
-        const char *names[8] = {"arrive(membar+red)", "spin", "gemv_rows", "total", "barriers", "gemv full-wait", "gemv row compute", "gemv rows(warp0)"};
-        for (int k = 0; k < 8; k++) {
+        const char *names[4] = {"poll (flag wait)", "gemv (xr + rows)", "-", "total"};
+        for (int k = 0; k < 4; k++) {
+            if (k == 2) continue;
             long long mn = h[k], mx = h[k]; double sum = 0;
             for (int c = 0; c < s.mega_grid; c++) { long long v = h[(size_t)c * 8 + k]; mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)v; }
             fprintf(stderr, "[mega prof] %-20s cycles/step: min %.0f mean %.0f max %.0f\n", names[k], (double)mn / n_steps, sum / s.mega_grid / n_steps, (double)mx / n_steps);

@@ -36,6 +36,7 @@ struct Sequence {
 struct Decoder {
     MegaParams mp{};                  // host copy of the device-resident descriptor
     MegaParams *d_mp = nullptr;
+    void *d_ll = nullptr; size_t ll_bytes = 0;   // flagged exchange arena
     bool mp_dirty = true;
     DecCtl *h_ctl = nullptr;          // pinned mirror
     TokData *h_tok = nullptr;         // pinned

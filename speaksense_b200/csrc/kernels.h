@@ -71,29 +71,31 @@ struct DecCtl {   // device resident; written by dec_sample_kernel, read by ever
 };
 
 struct MegaLayer {
-    const __half *qkv_w, *o_w, *cq_w, *co_w, *fc1_w, *fc2_w;
-    const float *qkv_b, *o_b, *cq_b, *co_b, *fc1_b, *fc2_b;
-    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
+    const __half *w[6];          // qkv, o, cq, co, fc1, fc2
+    const float *b[6];
+    const float *lnw[3], *lnb[3];   // attn_ln, cross_attn_ln, mlp_ln
 };
 constexpr int kMaxLayers = 32;
+typedef unsigned long long ss_u64;
 struct MegaParams {   // device-resident descriptor of one decoder sequence (decoder_mega.cu)
     int d, H, L, T, ctx, n_vocab;
-    int xsplit, ssplit;          // (head, split) units of the cross-attention phase (ssplit unused: one CTA per head)
+    int xsplit;                  // key splits per head of the cross-attention phase
     float s4;                    // head_dim^-1/4
     const __half *tok_emb; const float *d_pos; const float *lnf_w, *lnf_b;
     MegaLayer layer[kMaxLayers];
-    DecCtl *ctl; float *x, *q, *h, *att, *part, *logits, *stats; TokData *tok_out; float *keep; int keep_cap;
+    DecCtl *ctl;
+    // flagged exchange buffers ({epoch, float} words), all inside one arena that is zeroed per launch
+    ss_u64 *xA, *xB, *xC, *q1, *kcur, *vcur, *att1, *q2, *att2, *hbuf, *part, *stats;
+    float *logits; TokData *tok_out; float *keep; int keep_cap;
     __half *self_k, *self_v;              // [layer][head][n_text_ctx][64]
     const __half *cross_k, *cross_v;      // [layer][head][n_audio_ctx][64]
-    unsigned int *bar;           // [0] grid barrier counter, [1 + h] per-head cross-attention arrival counters
     long long *prof;             // optional [grid][8] cycle counters (SS_MEGA_PROF=1), else null
     int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
     int suppress_blank, tdrz, tid0_init;
 };
-constexpr int kMegaBarWords = 64;
 size_t decode_mega_smem_bytes();
 void decode_mega_configure();
 int decode_mega_grid(int device);
-void decode_mega_launch(const MegaParams *d_params, unsigned int *d_bar, int max_steps, int grid, cudaStream_t st);
+void decode_mega_launch(const MegaParams *d_params, void *d_ll, size_t ll_bytes, int max_steps, int grid, cudaStream_t st);
 
 }  // namespace ss
