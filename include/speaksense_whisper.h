@@ -120,6 +120,15 @@ int  ss_n_kernel_launches(const ss_state *s);              /* our kernels launch
 int  ss_stage_ms(const ss_state *s, float *mel_ms, float *encoder_ms, float *decode_ms);
 const float *ss_debug_logits(const ss_state *s, int step, int *n_vocab);  /* parity hook; HOST ptr */
 
+/* ---- host-only helpers (no device needed): the Rust-side text rules of whisper.rs, exposed so that the
+ *      CPU test-suite can pin them, and the ggml loader's view of a model file ---- */
+int  ss_is_promotional_text(const char *utf8);                       /* whisper.rs:41-43 (list at :9-14) */
+int  ss_add_punctuation(const char *utf8, char *out, size_t out_cap);  /* whisper.rs:175-201; returns bytes written or <0 */
+int  ss_is_valid_utf8(const char *bytes, size_t n);                  /* what full_get_segment_text enforces, whisper.rs:85 */
+/* parses a ggml .bin exactly like ss_engine_open (same errors) without touching a GPU */
+int  ss_model_probe(const char *ggml_path, int hparams_out[11], int64_t *arena_bytes, uint64_t *arena_fnv1a,
+                    int *token_eot, int *token_beg, int *n_vocab_strings);
+
 /* ---- stage-level entry points (parity tests and roofline measurement) ---- */
 /* PCM -> log-mel on the device; copies [n_mels][n_len] f32 to host `mel_out` (may be NULL to only
  * time it).  n_len/n_len_org as whisper.cpp defines them. */

@@ -60,6 +60,11 @@ SYMBOLS = [
     ("ss_n_kernel_launches", C.c_int, [_P]),
     ("ss_stage_ms", C.c_int, [_P] + [C.POINTER(C.c_float)] * 3),
     ("ss_debug_logits", C.POINTER(C.c_float), [_P, C.c_int, C.POINTER(C.c_int)]),
+    ("ss_is_promotional_text", C.c_int, [C.c_char_p]),
+    ("ss_add_punctuation", C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
+    ("ss_is_valid_utf8", C.c_int, [C.c_char_p, C.c_size_t]),
+    ("ss_model_probe", C.c_int, [C.c_char_p, C.POINTER(C.c_int * 11), C.POINTER(C.c_int64), C.POINTER(C.c_uint64),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("ss_log_mel", C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("ss_encode", C.c_int, [_P, _P, C.c_int, _P, C.c_size_t]),
     ("ss_decode", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),

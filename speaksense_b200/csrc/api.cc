@@ -170,6 +170,30 @@ const float *ss_debug_logits(const ss_state *s, int step, int *n_vocab) {
     return s->s->h_keep.data() + (size_t)step * nv;
 }
 
+int ss_is_promotional_text(const char *utf8) { return utf8 ? (is_promotional_text(utf8) ? 1 : 0) : 0; }
+int ss_add_punctuation(const char *utf8, char *out, size_t out_cap) {
+    if (!utf8 || !out) { g_err = "null argument"; return SS_ERR_INVALID; }
+    const std::string r = add_punctuation(utf8);
+    if (r.size() + 1 > out_cap) { g_err = "output buffer too small"; return SS_ERR_INVALID; }
+    memcpy(out, r.c_str(), r.size() + 1);
+    return (int)r.size();
+}
+int ss_is_valid_utf8(const char *bytes, size_t n) { return bytes ? (is_valid_utf8(std::string(bytes, n)) ? 1 : 0) : 0; }
+int ss_model_probe(const char *path, int hparams_out[11], int64_t *arena_bytes, uint64_t *arena_fnv1a, int *token_eot, int *token_beg,
+                   int *n_vocab_strings) {
+    return guard([&]() -> int {
+        if (!path) SS_THROW(SS_ERR_INVALID, "null argument");
+        ModelProbe pr = probe_model(path);
+        if (hparams_out) memcpy(hparams_out, &pr.hp, sizeof(int) * 11);
+        if (arena_bytes) *arena_bytes = (int64_t)pr.arena_bytes;
+        if (arena_fnv1a) *arena_fnv1a = pr.fnv1a;
+        if (token_eot) *token_eot = pr.eot;
+        if (token_beg) *token_beg = pr.beg;
+        if (n_vocab_strings) *n_vocab_strings = pr.n_vocab_strings;
+        return 0;
+    });
+}
+
 int ss_log_mel(ss_engine *e, ss_state *s, const float *pcm, size_t n, float *mel_out, size_t mel_cap, int *n_len, int *n_len_org) {
     return guard([&]() -> int {
         if (!e || !s || (!pcm && n)) SS_THROW(SS_ERR_INVALID, "null argument");

@@ -308,6 +308,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uin
         }
     }
     // ---- rows out of the ring
+    if (tid == 0) sm.prof[2] += clock64() - tg0;
     for (int ch = 0; ch < seg.n_chunks; ch++) {
         const int slot = cons & (kSlots - 1);
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);

@@ -403,9 +403,8 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     if (d.mp.prof) {
         std::vector<long long> h((size_t)s.mega_grid * 8);
         CUDA_CHECK(cudaMemcpy(h.data(), d.mp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
-        const char *names[4] = {"poll (flag wait)", "gemv (xr + rows)", "-", "total"};
+        const char *names[4] = {"poll (flag wait)", "gemv (xr + rows)", "gemv xr load", "total"};
         for (int k = 0; k < 4; k++) {
-            if (k == 2) continue;
             long long mn = h[k], mx = h[k]; double sum = 0;
             for (int c = 0; c < s.mega_grid; c++) { long long v = h[(size_t)c * 8 + k]; mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)v; }
             fprintf(stderr, "[mega prof] %-20s cycles/step: min %.0f mean %.0f max %.0f\n", names[k], (double)mn / n_steps, sum / s.mega_grid / n_steps, (double)mx / n_steps);
@@ -785,13 +784,18 @@ static bool ends_with(const std::string &t, const char *suffix) {
     const size_t n = strlen(suffix);
     return t.size() >= n && memcmp(t.data() + t.size() - n, suffix, n) == 0;
 }
-static std::string add_punctuation(const std::string &text) {
+std::string add_punctuation(const std::string &text) {
     if (ends_with(text, "。") || ends_with(text, "！") || ends_with(text, "？") || ends_with(text, "，")) return text;
     const bool q = contains(text, "吗") || contains(text, "呢") || contains(text, "什么") || contains(text, "为何") || contains(text, "怎么");
     const bool e = contains(text, "啊") || contains(text, "哇") || contains(text, "太") || contains(text, "真") || contains(text, "好") || contains(text, "真是");
     std::string r = text;
     if (q) r += "？"; else if (e) r += "！"; else r += " ";
     return r;
+}
+
+bool is_promotional_text(const std::string &t) {
+    for (const char *p : kPromo) if (contains(t, p)) return true;
+    return false;
 }
 
 int postprocess(State &s, bool stream_mode) {
@@ -804,9 +808,7 @@ int postprocess(State &s, bool stream_mode) {
             s.out.clear(); s.full_text.clear();
             SS_THROW(-7, "segment %d text is not valid UTF-8", i);
         }
-        bool promo = false;
-        for (const char *p : kPromo) if (contains(text, p)) { promo = true; break; }
-        if (promo) continue;
+        if (is_promotional_text(text)) continue;
         if (i > 0 && s.raw[i - 1].speaker_turn_next) speaker++;
         const std::string processed = add_punctuation(text);
         if (stream_mode) {

@@ -93,5 +93,7 @@ int transcribe(State &s, const float *pcm, size_t n, const FullParams &fp, bool 
 // Rust-side post-processing of whisper.rs:84-128 on s.raw -> s.out / s.full_text
 int postprocess(State &s, bool stream_mode);
 bool is_valid_utf8(const std::string &t);
+bool is_promotional_text(const std::string &t);
+std::string add_punctuation(const std::string &text);
 
 }  // namespace ss

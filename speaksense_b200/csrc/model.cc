@@ -283,6 +283,23 @@ std::vector<unsigned char> build_arena_image(const std::string &path) {
     return img;
 }
 
+ModelProbe probe_model(const std::string &path) {
+    std::vector<unsigned char> img = build_arena_image(path);
+    ModelProbe pr{};
+    uint64_t ml; memcpy(&ml, img.data() + 8, 8);
+    std::vector<std::string> toks;
+    parse_meta(img.data() + 16, ml, pr.hp, nullptr, &toks);
+    Model tmp; tmp.hp = pr.hp;
+    pr.n_vocab_strings = (int)toks.size();
+    fill_vocab(tmp, std::move(toks));
+    pr.eot = tmp.vocab.eot; pr.beg = tmp.vocab.beg;
+    pr.arena_bytes = img.size();
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : img) { h ^= c; h *= 1099511628211ull; }
+    pr.fnv1a = h;
+    return pr;
+}
+
 void bind_model(Model &m, unsigned char *d_arena, size_t bytes, int device) {
     m.device = device; m.arena = d_arena; m.arena_bytes = bytes;
     unsigned char head[16];

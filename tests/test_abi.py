@@ -1,0 +1,92 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/speaksense_whisper.h
+declares, fails loudly (no CPU fallback) on compute entry points, and its host-only helpers agree with
+the Python restatement of the reference's Rust text rules."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from speaksense_b200 import build, _native
+    build.build()
+    return _native.lib()
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "speaksense_whisper.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(L):
+    from speaksense_b200 import _native
+    names = _declared()
+    assert len(names) >= 40
+    bound = {n for n, _, _ in _native.SYMBOLS}
+    for n in names:
+        assert hasattr(L, n), "library lacks %s" % n
+        assert n in bound, "python binding lacks %s" % n
+    assert L.ss_abi_version() == 1
+    assert b"sm_100a" in L.ss_build_info()
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback(L, tiny_en_peaked):
+    import numpy as np
+    from speaksense_b200 import NativeError, WhisperAsr
+    h = C.c_void_p()
+    assert L.ss_engine_open(tiny_en_peaked.encode(), 0, C.byref(h)) == -3          # SS_ERR_NO_DEVICE
+    assert b"no CPU fallback" in L.ss_last_error()
+    with pytest.raises(NativeError):
+        WhisperAsr(tiny_en_peaked)
+    a = np.zeros((4, 4), np.float16)
+    d = np.zeros((4, 4), np.float32)
+    assert L.ss_debug_gemm(0, a.ctypes.data, a.ctypes.data, d.ctypes.data, 4, 4, 4, 0) == -3
+
+
+def test_text_rules_match_rust_restatement(L):
+    from tests.rust_post import PROMOTIONAL_TEXT, add_punctuation, is_promotional_text
+    buf = C.create_string_buffer(4096)
+    samples = ["你好吗", "这是什么", "啊", "真好", "天气不错", "句号。", "逗号，", "感叹！", "问？", "", "plain ascii", "为何怎么呢",
+               "请订阅", "打赏支持明镜与点点栏目", "x" * 500] + PROMOTIONAL_TEXT
+    for s in samples:
+        n = L.ss_add_punctuation(s.encode(), buf, len(buf))
+        assert n >= 0 and buf.value.decode() == add_punctuation(s)
+        assert bool(L.ss_is_promotional_text(s.encode())) == is_promotional_text(s)
+    assert L.ss_add_punctuation("长".encode() * 2000, buf, 16) < 0               # buffer too small is an error, not a truncation
+    for b, ok in [(b"abc", 1), ("中文".encode(), 1), (b"\xe4\xb8", 0), (b"\xff", 0), (b"\xc0\x80", 0), (b"\xed\xa0\x80", 0), (b"", 1)]:
+        assert L.ss_is_valid_utf8(b, len(b)) == ok
+
+
+def test_model_probe(L, tiny_en_peaked, micro_v3_random, tmp_path):
+    hp = (C.c_int * 11)()
+    ab, h, eot, beg, nv = C.c_int64(), C.c_uint64(), C.c_int(), C.c_int(), C.c_int()
+    assert L.ss_model_probe(tiny_en_peaked.encode(), C.byref(hp), C.byref(ab), C.byref(h), C.byref(eot), C.byref(beg), C.byref(nv)) == 0
+    assert list(hp) == [51864, 1500, 384, 6, 4, 448, 384, 6, 4, 80, 1]
+    assert (eot.value, beg.value, nv.value) == (50256, 50363, 50256)
+    assert ab.value > os.path.getsize(tiny_en_peaked) * 0.99
+    h1 = h.value
+    assert L.ss_model_probe(tiny_en_peaked.encode(), None, None, C.byref(h), None, None, None) == 0 and h.value == h1   # deterministic packing
+    assert L.ss_model_probe(micro_v3_random.encode(), C.byref(hp), None, None, C.byref(eot), C.byref(beg), None) == 0
+    assert (hp[0], eot.value, beg.value) == (51866, 50257, 50365)                  # large-v3 token layout
+    # malformed files fail with SS_ERR_IO, like WhisperContext::new_with_params -> Err (whisper.rs:23-24)
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"nope" + b"\0" * 100)
+    assert L.ss_model_probe(str(bad).encode(), None, None, None, None, None, None) == -2
+    trunc = tmp_path / "trunc.bin"
+    trunc.write_bytes(open(tiny_en_peaked, "rb").read(3_000_000))
+    assert L.ss_model_probe(str(trunc).encode(), None, None, None, None, None, None) == -2
+    assert L.ss_model_probe(b"/nonexistent/model.bin", None, None, None, None, None, None) == -2

@@ -1,0 +1,40 @@
+"""Synthetic ggml writer / reader and audio generator (test + bench tooling)."""
+import numpy as np
+
+from speaksense_b200 import synth
+
+
+def test_roundtrip_and_determinism(tmp_path):
+    hp = synth.HParams(51865, 1500, 128, 2, 1, 448, 128, 2, 1, 80)
+    a, b = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    ma = synth.write_model(a, family="peaked", seed=5, hparams=hp)
+    synth.write_model(b, family="peaked", seed=5, hparams=hp)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    m = synth.read_model(a)
+    assert m["hparams"] == hp and m["filters"].shape == (80, 201) and len(m["vocab"]) == 50257
+    t = m["tensors"]
+    assert t["decoder.token_embedding.weight"].dtype == np.float16 and t["decoder.token_embedding.weight"].shape == (51865, 128)
+    assert t["encoder.conv1.weight"].shape == (128, 80, 3) and t["encoder.conv1.bias"].dtype == np.float32
+    assert "encoder.blocks.0.attn.key.bias" not in t and "decoder.blocks.0.cross_attn.key.bias" not in t
+    assert ma["n_tensors"] == len(t)
+
+
+def test_special_tokens_table():
+    # SURVEY.md Appendix A.5
+    en, v2, v3 = synth.special_tokens(51864), synth.special_tokens(51865), synth.special_tokens(51866)
+    assert (en["eot"], en["sot"], en["transcribe"], en["beg"]) == (50256, 50257, 50358, 50363)
+    assert (v2["eot"], v2["sot"], v2["transcribe"], v2["beg"]) == (50257, 50258, 50359, 50364)
+    assert (v3["eot"], v3["sot"], v3["translate"], v3["transcribe"], v3["beg"]) == (50257, 50258, 50359, 50360, 50365)
+
+
+def test_mel_filters_match_transformers():
+    from transformers.audio_utils import mel_filter_bank
+    for n in (80, 128):
+        ref = mel_filter_bank(201, n, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney").T
+        assert np.abs(synth.mel_filters(n) - ref).max() < 1e-6
+
+
+def test_audio_is_seeded_and_bounded():
+    a, b, c = synth.synth_audio(16000, 1), synth.synth_audio(16000, 1), synth.synth_audio(16000, 2)
+    assert a.dtype == np.float32 and np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.abs(a).max() <= 1.0 and a.std() > 0.05
