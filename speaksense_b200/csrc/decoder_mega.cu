@@ -7,7 +7,7 @@
 // in round-1 v0 = 16 % of the HBM roofline).  Here one CTA per SM stays resident for the whole
 // decode loop:
 //   * warp 8 (producer) streams this CTA's static slice of the weights and of the cross-attention K/V
-//     cache through an 8 x 20 KB shared-memory ring with cp.async.bulk + mbarriers.  Its schedule does
+//     cache through a 7 x 22.5 KB shared-memory ring with cp.async.bulk + mbarriers.  Its schedule does
 //     not depend on activations, so it runs ahead across phase, layer and token boundaries and keeps
 //     the HBM pipe busy while the consumers wait for each other's activations.
 //   * warps 0..7 (consumers) compute dot products straight out of the ring against an activation
@@ -34,8 +34,8 @@ namespace {
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kMegaThreads = kConsumerThreads + 32;
-constexpr int kSlots = 8;
-constexpr int kChunkBytes = 20480;
+constexpr int kSlots = 7;
+constexpr int kChunkBytes = 23040;      // 9 rows of d = 1280: a CTA's whole slice of a d-row matrix is one chunk
 constexpr int kMaxXs = 5120;          // largest mat-vec input (4 * d, d <= 1280)
 constexpr int kMaxRowsPerCta = 512;   // per phase, x KQ partials
 constexpr int kMaxScores = 512;
@@ -282,48 +282,60 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uin
     prefetch_bias(kind == SEG_LM ? nullptr : P.layer[il].b[widx], seg.row0, seg.rows);
     asm volatile("cp.async.wait_group 1;" ::: "memory");     // LayerNorm affine landed (bias may still be in flight)
     consumer_sync();
-    // ---- the slice of x this lane multiplies with, in registers (LayerNorm applied on the way)
     const long long tg0 = clock64();
-    const int quarter = warp & (kq - 1);
-    const int group = kq == 1 ? warp : (warp >> 2);
-    const int ngroups = kConsumerWarps / kq;
+    if (has_ln) {   // normalise once, cooperatively (ggml_norm + affine), rounded to f16 for the mat-vec
+        for (int i = tid; i < d; i += kConsumerThreads) sm.xs[i] = r16((sm.xs[i] - mean) * rstd * sm.lnw[i] + sm.lnb[i]);
+        consumer_sync();
+    }
+    // ---- the slice of x this lane multiplies with, in registers.  Multi-chunk segments are processed by two
+    //      teams of four warps on alternating chunks, every warp keeping two rows in flight.
+    const int nteams = seg.n_chunks >= 2 ? 2 : 1;
+    const int wpt = kConsumerWarps / nteams;
+    const int team = warp / wpt, tw = warp % wpt;
+    const int quarter = tw & (kq - 1);
+    const int group = kq == 1 ? tw : (tw >> 2);
+    const int ngroups = wpt / kq;
     const int nchunk = d >> 3;
     float4 xa[kMaxJ], xb[kMaxJ];
     {
         const float4 *x4 = reinterpret_cast<const float4 *>(sm.xs + quarter * d);
-        const float4 *w4 = reinterpret_cast<const float4 *>(sm.lnw), *b4 = reinterpret_cast<const float4 *>(sm.lnb);
 #pragma unroll
         for (int j = 0; j < kMaxJ; j++) {
             const int c = lane + 32 * j;
-            if (c < nchunk) {
-                xa[j] = x4[2 * c]; xb[j] = x4[2 * c + 1];
-                if (has_ln) {
-                    const float4 wa = w4[2 * c], wb = w4[2 * c + 1], ba = b4[2 * c], bb = b4[2 * c + 1];
-                    xa[j].x = r16((xa[j].x - mean) * rstd * wa.x + ba.x); xa[j].y = r16((xa[j].y - mean) * rstd * wa.y + ba.y);
-                    xa[j].z = r16((xa[j].z - mean) * rstd * wa.z + ba.z); xa[j].w = r16((xa[j].w - mean) * rstd * wa.w + ba.w);
-                    xb[j].x = r16((xb[j].x - mean) * rstd * wb.x + bb.x); xb[j].y = r16((xb[j].y - mean) * rstd * wb.y + bb.y);
-                    xb[j].z = r16((xb[j].z - mean) * rstd * wb.z + bb.z); xb[j].w = r16((xb[j].w - mean) * rstd * wb.w + bb.w);
-                }
-            } else { xa[j] = make_float4(0, 0, 0, 0); xb[j] = xa[j]; }
+            if (c < nchunk) { xa[j] = x4[2 * c]; xb[j] = x4[2 * c + 1]; }
+            else { xa[j] = make_float4(0, 0, 0, 0); xb[j] = xa[j]; }
         }
     }
     // ---- rows out of the ring
     if (tid == 0) sm.prof[2] += clock64() - tg0;
     for (int ch = 0; ch < seg.n_chunks; ch++) {
-        const int slot = cons & (kSlots - 1);
+        const int slot = cons % kSlots;
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
-        const int rbase = ch * seg.rows_per_chunk;
-        const int rend = min(rbase + seg.rows_per_chunk, seg.rows);
-        for (int R = rbase + ((group - rbase) & (ngroups - 1)); R < rend; R += ngroups) {
-            const uint4 *w = reinterpret_cast<const uint4 *>(sm.ring[slot] + (size_t)(R - rbase) * seg.row_bytes + (size_t)quarter * d * 2);
-            uint4 u[kMaxJ];
+        if (nteams == 1 || (ch & 1) == team) {
+            const int rbase = ch * seg.rows_per_chunk;
+            const int nrows = min(seg.rows_per_chunk, seg.rows - rbase);
+            const uint8_t *cbase = sm.ring[slot] + (size_t)quarter * d * 2;
+            for (int r0 = group; r0 < nrows; r0 += 2 * ngroups) {
+                const int r1 = r0 + ngroups;
+                const bool has1 = r1 < nrows;
+                const uint4 *w0 = reinterpret_cast<const uint4 *>(cbase + (size_t)r0 * seg.row_bytes);
+                const uint4 *w1 = reinterpret_cast<const uint4 *>(cbase + (size_t)(has1 ? r1 : r0) * seg.row_bytes);
+                uint4 u0[kMaxJ], u1[kMaxJ];
 #pragma unroll
-            for (int j = 0; j < kMaxJ; j++) { const int c = lane + 32 * j; u[j] = c < nchunk ? w[c] : make_uint4(0, 0, 0, 0); }
-            float a0 = 0.f, a1 = 0.f;
+                for (int j = 0; j < kMaxJ; j++) {
+                    const int c = lane + 32 * j;
+                    if (c < nchunk) { u0[j] = w0[c]; u1[j] = w1[c]; } else { u0[j] = make_uint4(0, 0, 0, 0); u1[j] = u0[j]; }
+                }
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < kMaxJ; j++) { if (j & 1) a1 = dot8(u[j], xa[j], xb[j], a1); else a0 = dot8(u[j], xa[j], xb[j], a0); }
-            const float a = warp_sum(a0 + a1);
-            if (lane == 0) sm.acc[R * kq + quarter] = a;
+                for (int j = 0; j < kMaxJ; j++) { a0 = dot8(u0[j], xa[j], xb[j], a0); a1 = dot8(u1[j], xa[j], xb[j], a1); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+                if (lane == 0) {
+                    sm.acc[(rbase + r0) * kq + quarter] = a0;
+                    if (has1) sm.acc[(rbase + r1) * kq + quarter] = a1;
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
@@ -475,7 +487,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
     float lmax = -INFINITY;
     for (int ch = 0; ch < sk.n_chunks; ch++) {
-        const int slot = cons & (kSlots - 1);
+        const int slot = cons % kSlots;
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
         lmax = attn_scores<true>(sm.ring[slot], nk, kbase, qa, qb, lmax);
@@ -489,7 +501,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     const float l = consumer_sum(lsum);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int ch = 0; ch < sk.n_chunks; ch++) {     // the V slice has the same chunking as the K slice
-        const int slot = cons & (kSlots - 1);
+        const int slot = cons % kSlots;
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
         attn_pv<true>(sm.ring[slot], nk, kbase, acc);
@@ -739,7 +751,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
                     const SegTab seg = sm.seg[kind];
                     const uint8_t *base = seg_base(P, seg, kind, layer < L ? layer : 0);
                     for (int ch = 0; ch < seg.n_chunks; ch++) {
-                        const int slot = issued & (kSlots - 1);
+                        const int slot = issued % kSlots;
                         const uint32_t par = ((issued / kSlots) & 1) ^ 1;
                         while (!mbar_try_wait(&sm.empty[slot], par)) { if (sm.stop_req) { stopped = true; break; } }
                         if (stopped || sm.stop_req) { stopped = true; break; }
