@@ -67,3 +67,66 @@ def test_unknown_language_is_an_error(micro_v3_peaked, audio30):
     with pytest.raises(NativeError):
         eng.transcribe(audio30, AsrParams(language="xx"))
     eng.close()
+
+
+def test_two_windows_with_context_match_oracle(oracle_mod, tiny_en_peaked):
+    """45 s clip, stream_mode off: the second window is prompted with [prev] + the first window's tokens
+    (no_context=false, whisper.rs:155) - exercises long prompts through the decode kernel."""
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    pcm = synth.synth_audio(45 * 16000, seed=11)
+    ref, _ = _oracle_result(oracle_mod, tiny_en_peaked, pcm, stream_mode=False)
+    eng = WhisperAsr(tiny_en_peaked)
+    st = eng.create_state()
+    res = eng.transcribe_with_state(st, pcm, AsrParams(stream_mode=False))
+    toks, _ = st.result_tokens()
+    assert st.stats()["n_windows"] == ref["n_windows"] == 2
+    assert toks == ref["tokens"]
+    raw = st.raw_segments()
+    assert [(s["t0"], s["t1"], s["text"]) for s in raw] == [(s["t0"], s["t1"], s["text"]) for s in ref["segments"]]
+    exp = post_process(ref["segments"], False)
+    assert res.full_text == exp["full_text"] and len(res.segments) == len(exp["segments"])
+    eng.close()
+
+
+def test_fallback_ladder_runs_on_flat_logits(oracle_mod, micro_v3_random):
+    """Random weights fail the t=0 gates -> best_of=5 sampled decoders at t>0 (host-sampled path).
+    Sampling is not bit-reproducible across implementations, so only the control flow is pinned."""
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    pcm = synth.synth_audio(3 * 16000, seed=5)
+    om = oracle_mod.OracleModel(micro_v3_random)
+    ost = om.new_state()
+    ref = ost.full(pcm, language="zh")
+    eng = WhisperAsr(micro_v3_random)
+    st = eng.create_state()
+    eng.transcribe_with_state(st, pcm, AsrParams(language="zh"))
+    stats = st.stats()
+    assert ref["n_fallbacks"] >= 1 and stats["n_fallbacks"] >= 1
+    assert stats["n_decoded"] > len(st.result_tokens()[0])
+    ost.close(); om.close(); eng.close()
+
+
+def test_transcribe_batch_equals_single(tiny_en_peaked):
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    eng = WhisperAsr(tiny_en_peaked)
+    clips = [synth.synth_audio(seed=1234 + i) for i in range(3)]
+    p = AsrParams(stream_mode=True)
+    singles = [eng.transcribe(c, p) for c in clips]
+    states = [eng.create_state() for _ in clips]
+    batch = eng.transcribe_batch(states, clips, p)
+    assert batch == singles
+    eng.close()
+
+
+def test_large_v3_shapes_two_layers(oracle_mod, audio30):
+    """Every large-v3 kernel shape (d=1280, 20 heads, 128 mels, 51866 vocab) with 2+2 layers."""
+    from tests.conftest import model_path
+    from speaksense_b200 import AsrParams, WhisperAsr
+    path = model_path("large-v3-l2", "peaked", 0)
+    ref, ref_logits = _oracle_result(oracle_mod, path, audio30, language="en", stream_mode=True)
+    eng = WhisperAsr(path)
+    st = eng.create_state()
+    eng.transcribe_with_state(st, audio30, AsrParams(language="en", stream_mode=True, debug_keep_logits=True))
+    toks, _ = st.result_tokens()
+    assert toks == ref["tokens"]
+    assert np.abs(st.debug_logits() - ref_logits).max() < 1e-2
+    eng.close()
