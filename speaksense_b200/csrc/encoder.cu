@@ -1,7 +1,6 @@
 // encoder.cu - the non-GEMM pieces of the audio encoder: LayerNorm (ggml_norm + affine, eps 1e-5,
-// resources/ggml-metal.metal:571-621) producing the f16 GEMM operand, and the row softmax of the
-// unfused attention path (ggml soft_max, ggml-metal.metal:351-435).  Everything else in the encoder is
-// a tcgen05 GEMM epilogue (gemm_sm100.cu).
+// resources/ggml-metal.metal:571-621) producing the f16 GEMM operand, the attention itself is
+// attention_sm100.cu and everything else in the encoder is a tcgen05 GEMM epilogue (gemm_sm100.cu).
 #include "kernels.h"
 
 namespace ss {
@@ -13,12 +12,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 // one warp per row; NV = d / 128 float4 chunks per lane, row kept in registers (two-pass variance)
 template <int NV, bool OUT_F16>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, void *__restrict__ y, int rows,
@@ -68,24 +61,6 @@ void ln_dispatch(const float *x, void *y, int rows, int d, const LNp &ln, cudaSt
     CUDA_CHECK(cudaGetLastError());
 }
 
-// one warp per row of n scores -> f16 probabilities (zero padded to ld_out)
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restrict__ s, long ld_in, __half *__restrict__ p, long ld_out,
-                                                            long rows, int n) {
-    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const float *sr = s + row * ld_in;
-    __half *pr = p + row * ld_out;
-    float m = -INFINITY;
-    for (int j = lane; j < n; j += 32) m = fmaxf(m, sr[j]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int j = lane; j < n; j += 32) sum += __expf(sr[j] - m);
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    for (int j = lane; j < ld_out; j += 32) pr[j] = __float2half_rn(j < n ? __expf(sr[j] - m) * inv : 0.f);
-}
-
 __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float *__restrict__ x, __half *__restrict__ y, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
 }
@@ -97,10 +72,6 @@ void layernorm_f16_enqueue(const float *x, __half *y, int rows, int d, const LNp
 }
 void layernorm_f32_enqueue(const float *x, float *y, int rows, int d, const LNp &ln, cudaStream_t st, int *launches) {
     ln_dispatch<false>(x, y, rows, d, ln, st); (*launches)++;
-}
-void softmax_rows_enqueue(const float *s, long ld_in, __half *p, long ld_out, long rows, int n, cudaStream_t st, int *launches) {
-    softmax_rows_kernel<<<(unsigned)ceil_div<long>(rows, 8), 256, 0, st>>>(s, ld_in, p, ld_out, rows, n);
-    CUDA_CHECK(cudaGetLastError()); (*launches)++;
 }
 void f32_to_f16_enqueue(const float *x, __half *y, size_t n, cudaStream_t st, int *launches) {
     f32_to_f16_kernel<<<(unsigned)std::min<size_t>(ceil_div<size_t>(n, 256), 148 * 8), 256, 0, st>>>(x, y, n);

@@ -47,6 +47,7 @@ std::shared_ptr<Engine> finish_open(unsigned char *d_arena, size_t bytes, int de
     e->device = device; e->path = path;
     bind_model(e->model, d_arena, bytes, device);
     gemm_init();
+    attention_init();
     return e;
 }
 
@@ -187,7 +188,7 @@ State *state_new(const std::shared_ptr<Engine> &e) {
     auto s = std::make_unique<State>();
     s->engine = e;
     const HParams &hp = e->model.hp;
-    const size_t T = hp.n_audio_ctx, d = hp.n_audio_state, H = hp.n_audio_head, dd = hp.n_text_state;
+    const size_t T = hp.n_audio_ctx, d = hp.n_audio_state, dd = hp.n_text_state;
     CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto &ev : s->ev) CUDA_CHECK(cudaEventCreate(&ev));
     s->d_max = dmalloc<int>(1);
@@ -195,7 +196,6 @@ State *state_new(const std::shared_ptr<Engine> &e) {
     s->x1 = dmalloc<__half>((2 * T + 2) * d);
     CUDA_CHECK(cudaMemset(s->x1, 0, (2 * T + 2) * d * 2));
     s->x = dmalloc<float>(T * d); s->xn = dmalloc<__half>(T * d); s->qkv = dmalloc<__half>(T * 3 * d);
-    s->S = dmalloc<float>(H * T * (T + 4)); s->P = dmalloc<__half>(H * T * (T + 36));
     s->att = dmalloc<__half>(T * d); s->ff = dmalloc<__half>(T * 4 * d);
     s->enc_out = dmalloc<float>(T * d); s->enc16 = dmalloc<__half>(T * d);
     s->cross_k = dmalloc<__half>((size_t)hp.n_text_layer * T * dd); s->cross_v = dmalloc<__half>((size_t)hp.n_text_layer * T * dd);
@@ -216,7 +216,7 @@ State::~State() {
         cudaFree(b.self_k); cudaFree(b.self_v); cudaFree(d->d_mp);
         cudaFreeHost(d->h_ctl); cudaFreeHost(d->h_tok);
     }
-    void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, P, att, ff, enc16, x, S, enc_out, cross_k, cross_v, keep};
+    void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, att, ff, enc16, x, enc_out, cross_k, cross_v, keep};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_pcm) cudaFreeHost(h_pcm);
     if (h_logits) cudaFreeHost(h_logits);
@@ -293,7 +293,6 @@ void run_encode(State &s, int seek) {
         GemmEpilogue ep; ep.bias = m.conv2.b; ep.gelu = 1; ep.pos = m.e_pos; ep.pos_rows = T; ep.out = s.x; ep.out_type = GEMM_OUT_F32; ep.out_ld = d;
         gemm_enqueue(A, B, T, d, 3 * d, false, ep, st, nl);
     }
-    const long ldS = T + 4, ldP = T + 36;
     for (int il = 0; il < hp.n_audio_layer; il++) {
         const EncLayer &L = m.enc[il];
         layernorm_f16_enqueue(s.x, s.xn, T, d, L.attn_ln, st, nl);
@@ -303,19 +302,7 @@ void run_encode(State &s, int seek) {
             GemmEpilogue ep; ep.bias = L.qkv.b; ep.out = s.qkv; ep.out_ld = 3 * d;
             gemm_enqueue(A, B, T, 3 * d, d, false, ep, st, nl);
         }
-        {   // S = Q K^T / sqrt(64), all heads batched
-            GemmOperand A; A.ptr = s.qkv; A.rows = T; A.ld = 3 * d; A.batch0 = H; A.stride0 = 64;
-            GemmOperand B; B.ptr = s.qkv + d; B.rows = T; B.ld = 3 * d; B.batch0 = H; B.stride0 = 64;
-            GemmEpilogue ep; ep.alpha = 1.0f / sqrtf(64.0f); ep.alpha_cols = T; ep.out = s.S; ep.out_type = GEMM_OUT_F32; ep.out_ld = ldS; ep.out_stride0 = (long)T * ldS;
-            gemm_enqueue(A, B, T, T, 64, false, ep, st, nl);
-        }
-        softmax_rows_enqueue(s.S, ldS, s.P, ldP, (long)H * T, T, st, nl);
-        {   // O = P V  (V consumed MN-major straight from the QKV buffer)
-            GemmOperand A; A.ptr = s.P; A.rows = T; A.ld = ldP; A.batch0 = H; A.stride0 = (long)T * ldP;
-            GemmOperand B; B.ptr = s.qkv + 2 * d; B.rows = T; B.ld = 3 * d; B.batch0 = H; B.stride0 = 64;
-            GemmEpilogue ep; ep.out = s.att; ep.out_ld = d; ep.out_stride0 = 64;
-            gemm_enqueue(A, B, T, 64, (int)ldP, true, ep, st, nl);
-        }
+        attention_enqueue(s.qkv, s.att, 1, T, H, 1.0f / sqrtf(64.0f), st, nl);   // fused: S and P never leave the SM
         {
             GemmOperand A; A.ptr = s.att; A.rows = T; A.ld = d;
             GemmOperand B; B.ptr = L.o.w; B.rows = d; B.ld = d;

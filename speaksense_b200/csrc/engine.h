@@ -58,8 +58,8 @@ struct State {
     float *d_pcm = nullptr; size_t pcm_cap = 0; size_t n_resident = 0; float *h_pcm = nullptr; size_t h_pcm_cap = 0;
     float *d_mel = nullptr; size_t mel_cap = 0; int n_len = 0, n_len_org = 0; int *d_max = nullptr;
     // encoder scratch (one window)
-    __half *win = nullptr, *x1 = nullptr, *xn = nullptr, *qkv = nullptr, *P = nullptr, *att = nullptr, *ff = nullptr, *enc16 = nullptr;
-    float *x = nullptr, *S = nullptr, *enc_out = nullptr;
+    __half *win = nullptr, *x1 = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *enc16 = nullptr;
+    float *x = nullptr, *enc_out = nullptr;
     __half *cross_k = nullptr, *cross_v = nullptr;
     // decoders
     std::vector<std::unique_ptr<Decoder>> dec;

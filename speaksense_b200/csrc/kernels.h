@@ -45,12 +45,17 @@ struct GemmEpilogue {
 void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int K, bool b_mn_major,
                   const GemmEpilogue &ep, cudaStream_t st, int *launches);
 void gemm_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes
+// 4-D TMA descriptor (inner, rows, batch0, batch1) of an f16 operand with 128-byte swizzle; shared with attention_sm100.cu
+void make_tensor_map_4d(void *cu_tensor_map /* CUtensorMap* */, const GemmOperand &op, long inner, long rows, int box_inner, int box_rows);
+
+// ---------------------------------------------------------------- fused encoder attention (attention_sm100.cu)
+void attention_init();
+// qkv: [clips][T][3*H*64] f16 (Q | K | V) -> out: [clips][T][H*64] f16 = softmax(Q K^T * scale) V per head
+void attention_enqueue(const __half *qkv, __half *out, int clips, int T, int H, float scale, cudaStream_t st, int *launches);
 
 // ---------------------------------------------------------------- encoder helpers (encoder.cu)
 void layernorm_f16_enqueue(const float *x, __half *y, int rows, int d, const LNp &ln, cudaStream_t st, int *launches);
 void layernorm_f32_enqueue(const float *x, float *y, int rows, int d, const LNp &ln, cudaStream_t st, int *launches);
-// rows of `n` f32 scores (ld_in) -> f16 probabilities, zero padded to ld_out
-void softmax_rows_enqueue(const float *s, long ld_in, __half *p, long ld_out, long rows, int n, cudaStream_t st, int *launches);
 void f32_to_f16_enqueue(const float *x, __half *y, size_t n, cudaStream_t st, int *launches);
 
 // ---------------------------------------------------------------- decoder (decoder.cu)
