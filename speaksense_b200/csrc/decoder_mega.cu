@@ -690,7 +690,7 @@ __device__ void build_segtab() {
 __device__ __forceinline__ const uint8_t *seg_base(const MegaParams &P, const SegTab &s, int kind, int il) {
     if (kind == SEG_XK || kind == SEG_XV) {
         const int h = blockIdx.x / P.xsplit;
-        return reinterpret_cast<const uint8_t *>((kind == SEG_XK ? P.cross_k : P.cross_v) + (size_t)il * P.T * P.d + ((size_t)h * P.T + s.row0) * 64);
+        return reinterpret_cast<const uint8_t *>((kind == SEG_XK ? P.cross_k : P.cross_v) + (size_t)il * 2 * P.T * P.d + ((size_t)h * P.T + s.row0) * 64);
     }
     const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : kind == SEG_FC1 ? 4 : 5;
     const __half *w = kind == SEG_LM ? P.tok_emb : P.layer[il].w[widx];
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
                     for (int ch = 0; ch < seg.n_chunks; ch++) {
                         const int slot = issued % kSlots;
                         const uint32_t par = ((issued / kSlots) & 1) ^ 1;
-                        while (!mbar_try_wait(&sm.empty[slot], par)) { if (sm.stop_req) { stopped = true; break; } }
+                        while (!mbar_try_wait(&sm.empty[slot], par)) { if (sm.stop_req) { stopped = true; break; } __nanosleep(128); }   // do not out-prioritise the consumer warps of this scheduler
                         if (stopped || sm.stop_req) { stopped = true; break; }
                         const int rbase = ch * seg.rows_per_chunk;
                         const uint32_t bytes = (uint32_t)min(seg.rows_per_chunk, seg.rows - rbase) * seg.row_bytes;

@@ -198,7 +198,8 @@ State *state_new(const std::shared_ptr<Engine> &e) {
     s->x = dmalloc<float>(T * d); s->xn = dmalloc<__half>(T * d); s->qkv = dmalloc<__half>(T * 3 * d);
     s->att = dmalloc<__half>(T * d); s->ff = dmalloc<__half>(T * 4 * d);
     s->enc_out = dmalloc<float>(T * d); s->enc16 = dmalloc<__half>(T * d);
-    s->cross_k = dmalloc<__half>((size_t)hp.n_text_layer * T * dd); s->cross_v = dmalloc<__half>((size_t)hp.n_text_layer * T * dd);
+    s->cross_k = dmalloc<__half>((size_t)hp.n_text_layer * 2 * T * dd);   // [layer][K | V][head][T][64]
+    s->cross_v = s->cross_k + T * dd;
     s->h_logits = hmalloc<float>(hp.n_vocab);
     decode_mega_configure();
     s->mega_grid = decode_mega_grid(e->device);
@@ -216,7 +217,7 @@ State::~State() {
         cudaFree(b.self_k); cudaFree(b.self_v); cudaFree(d->d_mp);
         cudaFreeHost(d->h_ctl); cudaFreeHost(d->h_tok);
     }
-    void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, att, ff, enc16, x, enc_out, cross_k, cross_v, keep};
+    void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, att, ff, enc16, x, enc_out, cross_k, keep};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h_pcm) cudaFreeHost(h_pcm);
     if (h_logits) cudaFreeHost(h_logits);
@@ -328,15 +329,19 @@ void run_encode(State &s, int seek) {
     // cross-attention K/V for every decoder layer, written head-major into the persistent cache
     const int dd = hp.n_text_state;
     const float s4 = powf((float)(dd / hp.n_text_head), -0.25f);
-    for (int il = 0; il < hp.n_text_layer; il++) {
-        const DecLayer &L = m.dec[il];
+    {   // one launch for all decoder layers: A = encoder output (shared), B = the stacked [K | V] projection of layer l
+        const int Ld = hp.n_text_layer;
+        const long wstride = Ld > 1 ? (long)(m.dec[1].ckv.w - m.dec[0].ckv.w) : (long)2 * dd * d;
+        const long bstride = Ld > 1 ? (long)(m.dec[1].ckv.b - m.dec[0].ckv.b) : (long)2 * dd;
+        for (int il = 0; il < Ld; il++)
+            if (m.dec[il].ckv.w != m.dec[0].ckv.w + (long)il * wstride || m.dec[il].ckv.b != m.dec[0].ckv.b + (long)il * bstride)
+                SS_THROW(-9, "decoder layers are not equally spaced in the weight arena");
         GemmOperand A; A.ptr = s.enc16; A.rows = T; A.ld = d;
-        GemmOperand Bk; Bk.ptr = L.ckv.w; Bk.rows = dd; Bk.ld = d;
-        GemmEpilogue ek; ek.alpha = s4; ek.alpha_cols = dd; ek.out = s.cross_k + (size_t)il * T * dd; ek.head_major = 1; ek.head_rows = T;
-        gemm_enqueue(A, Bk, T, dd, d, false, ek, st, nl);
-        GemmOperand Bv; Bv.ptr = L.ckv.w + (size_t)dd * d; Bv.rows = dd; Bv.ld = d;
-        GemmEpilogue evv; evv.bias = L.ckv.b + dd; evv.out = s.cross_v + (size_t)il * T * dd; evv.head_major = 1; evv.head_rows = T;
-        gemm_enqueue(A, Bv, T, dd, d, false, evv, st, nl);
+        GemmOperand B; B.ptr = m.dec[0].ckv.w; B.rows = 2 * dd; B.ld = d; B.batch0 = Ld; B.stride0 = wstride;
+        GemmEpilogue ep; ep.a_broadcast = 1; ep.bias = m.dec[0].ckv.b; ep.bias_stride0 = bstride;   // K rows have zero bias
+        ep.alpha = s4; ep.alpha_cols = dd;                                                        // K pre-scaled by head_dim^-1/4
+        ep.out = s.cross_k; ep.head_major = 1; ep.head_rows = T; ep.out_stride0 = (long)2 * T * dd;
+        gemm_enqueue(A, B, T, 2 * dd, d, false, ep, st, nl);
     }
     CUDA_CHECK(cudaGetLastError());
 }

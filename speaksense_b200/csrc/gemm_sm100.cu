@@ -4,10 +4,10 @@
 // mul_mm / im2col / add / gelu / cpy): conv stem as implicit GEMM over an overlapping-row TMA view,
 // QKV / out / MLP projections, QK^T, PV and the cross-KV projection all go through this kernel.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global).  128 x BN output tile, BLOCK_K = 64 (one
-// 128-byte swizzle atom), kStages-deep mbarrier ring; two CTAs are co-resident per SM so one tile's
-// epilogue overlaps the other's main loop.
+// Persistent CTAs of 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  128 x BN output tiles (BN = 128 or 256), BLOCK_K = 64
+// (one 128-byte swizzle atom), 4-stage mbarrier ring, two accumulators in TMEM so that a tile's epilogue
+// overlaps the next tile's main loop.
 #include <cuda.h>
 
 #include "kernels.h"
@@ -25,7 +25,9 @@ using namespace ptx;
 
 struct GemmDev {
     int M, N, K;
-    int nb0;                    // inner batch count (blockIdx.z = b1 * nb0 + b0)
+    int nb0, nbatch;            // inner batch count (z = b1 * nb0 + b0), total batches
+    int a_bcast;                // A is shared by every batch (cross-KV: one activation, 32 layers of weights)
+    long bias_stride0;          // bias elements between inner batches
     const float *bias; float alpha; int alpha_cols; int gelu;
     const float *pos; int pos_rows; int residual; int out_f16;
     void *out; long out_ld, out_stride0, out_stride1; int head_major; long head_rows; int out_row_offset;
@@ -37,31 +39,36 @@ __device__ __forceinline__ float gelu_ggml(float x) {
     return r16(0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh))));
 }
 
-template <int BN, int kStages, bool B_MN>
-__global__ void __launch_bounds__(kThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+// Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, + gridDim.x, ...
+// The smem ring (TMA <-> MMA) keeps running across tile boundaries and the accumulator is double-buffered in
+// TMEM (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i + 1.
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr uint32_t kABytes = BM * BK * 2;            // 16 KB
     constexpr uint32_t kBBytes = BN * BK * 2;
-    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;    // power of two >= 32
+    constexpr uint32_t kTmemCols = 2 * BN;               // 256 or 512: two accumulators
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = smem + kStages * kABytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(sB + kStages * kBBytes);
     uint64_t *empty = full + kStages;
-    uint64_t *tmem_full = empty + kStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *tmem_full = empty + kStages;      // [2]
+    uint64_t *tmem_empty = tmem_full + 2;       // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-    const int b0 = blockIdx.z % p.nb0, b1 = blockIdx.z / p.nb0;
     const int nkb = (p.K + BK - 1) / BK;
+    const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
+    const int tiles_mn = tiles_n * tiles_m;
+    const int total = tiles_mn * p.nbatch;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -75,100 +82,114 @@ __global__ void __launch_bounds__(kThreads) gemm_tcgen05_kernel(const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], kABytes + kBBytes);
-                tma_load_4d(&tmA, &full[s], sA + s * kABytes, kb * BK, m0, b0, b1);
-                if (B_MN) tma_load_4d(&tmB, &full[s], sB + s * kBBytes, n0, kb * BK, b0, b1);
-                else      tma_load_4d(&tmB, &full[s], sB + s * kBBytes, kb * BK, n0, b0, b1);
+            uint32_t it = 0;     // running k-block counter across tiles (ring position)
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int z = t / tiles_mn, r = t - z * tiles_mn;
+                const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN;
+                const int b0 = z % p.nb0, b1 = z / p.nb0;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % kStages;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], kABytes + kBBytes);
+                    tma_load_4d(&tmA, &full[s], sA + s * kABytes, kb * BK, m0, p.a_bcast ? 0 : b0, p.a_bcast ? 0 : b1);
+                    tma_load_4d(&tmB, &full[s], sB + s * kBBytes, kb * BK, n0, b0, b1);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b F16 (0),
-            // a K-major, b major bit 16, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                mbar_wait(&full[s], ph);
+            // both K-major, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t it = 0, i = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, i++) {
+                const uint32_t acc = i & 1;
+                mbar_wait(&tmem_empty[acc], ((i >> 1) & 1) ^ 1);      // epilogue drained this accumulator
                 tcgen05_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * kABytes));
-                const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * kBBytes));
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % kStages;
+                    mbar_wait(&full[s], (it / kStages) & 1);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * kABytes));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * kBBytes));
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++) {
-                    // K-major: +32 B per UMMA_K inside the swizzle atom; MN-major: +16 k-rows = 2048 B
-                    const uint64_t ad = adesc + (uint64_t)((k * 32) >> 4);
-                    const uint64_t bd = bdesc + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4);
-                    tcgen05_mma_f16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; k++)     // +32 B per UMMA_K inside the 128-byte swizzle atom
+                        tcgen05_mma_f16(tmem_base + acc * BN, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc, (kb | k) ? 1u : 0u);
+                    tcgen05_commit(&empty[s]);
                 }
-                tcgen05_commit(&empty[s]);
+                tcgen05_commit(&tmem_full[acc]);
             }
-            tcgen05_commit(tmem_full);
         }
     } else {
         // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) ----------------
         const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
-        mbar_wait(tmem_full, 0);
-        tcgen05_fence_after();
-        const long zoff = (long)b0 * p.out_stride0 + (long)b1 * p.out_stride1;
-        const bool row_ok = m < p.M;
+        uint32_t i = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, i++) {
+            const int z = t / tiles_mn, r = t - z * tiles_mn;
+            const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN;
+            const int b0 = z % p.nb0, b1 = z / p.nb0;
+            const uint32_t acc = i & 1;
+            const int m = m0 + q * 32 + lane;
+            mbar_wait(&tmem_full[acc], (i >> 1) & 1);
+            tcgen05_fence_after();
+            const long zoff = (long)b0 * p.out_stride0 + (long)b1 * p.out_stride1;
+            const float *bias = p.bias ? p.bias + (long)b0 * p.bias_stride0 : nullptr;
+            const bool row_ok = m < p.M;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            const int nb = n0 + c;
-            if (!row_ok || nb >= p.N) continue;
-            const int nvalid = min(32, p.N - nb);
-            float v[32];
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t rr[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), rr);
+                const int nb = n0 + c;
+                if (!row_ok || nb >= p.N) continue;
+                const int nvalid = min(32, p.N - nb);
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                float x = __uint_as_float(r[j]);
-                const int n = nb + j;
-                if (j < nvalid) {
-                    if (p.bias) x += __ldg(p.bias + n);
-                    if (n < p.alpha_cols) x *= p.alpha;
-                    if (p.gelu) x = gelu_ggml(x);
-                    if (p.pos) x += __ldg(p.pos + (size_t)(m % p.pos_rows) * p.N + n);
+                for (int j = 0; j < 32; j++) {
+                    float x = __uint_as_float(rr[j]);
+                    const int n = nb + j;
+                    if (j < nvalid) {
+                        if (bias) x += __ldg(bias + n);
+                        if (n < p.alpha_cols) x *= p.alpha;
+                        if (p.gelu) x = gelu_ggml(x);
+                        if (p.pos) x += __ldg(p.pos + (size_t)(m % p.pos_rows) * p.N + n);
+                    }
+                    v[j] = x;
                 }
-                v[j] = x;
-            }
-            long idx;
-            if (p.head_major) idx = ((long)(nb >> 6) * p.head_rows + m) * 64 + (nb & 63) + zoff;
-            else idx = (long)(m + p.out_row_offset) * p.out_ld + nb + zoff;
-            if (p.out_f16) {
-                __half *o = reinterpret_cast<__half *>(p.out) + idx;
-                if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                long idx;
+                if (p.head_major) idx = ((long)(nb >> 6) * p.head_rows + m) * 64 + (nb & 63) + zoff;
+                else idx = (long)(m + p.out_row_offset) * p.out_ld + nb + zoff;
+                if (p.out_f16) {
+                    __half *o = reinterpret_cast<__half *>(p.out) + idx;
+                    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                        __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-                        uint4 u;
-                        u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
-                        u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
-                        *reinterpret_cast<uint4 *>(o + j) = u;
+                        for (int j = 0; j < 32; j += 8) {
+                            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                            uint4 u;
+                            u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
+                            u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
+                            *reinterpret_cast<uint4 *>(o + j) = u;
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid; j++) o[j] = __float2half_rn(v[j]);
                     }
                 } else {
-                    for (int j = 0; j < nvalid; j++) o[j] = __float2half_rn(v[j]);
-                }
-            } else {
-                float *o = reinterpret_cast<float *>(p.out) + idx;
-                if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                    float *o = reinterpret_cast<float *>(p.out) + idx;
+                    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (p.residual) { const float4 g = *reinterpret_cast<const float4 *>(o + j); f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w; }
-                        *reinterpret_cast<float4 *>(o + j) = f;
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (p.residual) { const float4 g = *reinterpret_cast<const float4 *>(o + j); f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w; }
+                            *reinterpret_cast<float4 *>(o + j) = f;
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid; j++) o[j] = p.residual ? o[j] + v[j] : v[j];
                     }
-                } else {
-                    for (int j = 0; j < nvalid; j++) o[j] = p.residual ? o[j] + v[j] : v[j];
                 }
             }
+            tcgen05_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
         }
-        tcgen05_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
@@ -184,7 +205,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn g_encode = nullptr;
 
 template <int BN, int kStages>
-constexpr size_t smem_bytes() { return 1024 + (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + (2 * kStages + 1) * 8 + 16; }
+constexpr size_t smem_bytes() { return 1024 + (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + (2 * kStages + 4) * 8 + 16; }
 
 void make_map(CUtensorMap *map, const GemmOperand &op, long inner, long rows, int box_inner, int box_rows) {
     cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)op.batch0, (cuuint64_t)op.batch1};
@@ -202,14 +223,15 @@ void make_map(CUtensorMap *map, const GemmOperand &op, long inner, long rows, in
     if (rc != CUDA_SUCCESS) SS_THROW(-4, "cuTensorMapEncodeTiled failed with %d (inner %ld rows %ld ld %ld)", (int)rc, inner, rows, op.ld);
 }
 
-template <int BN, int kStages, bool B_MN>
-void launch(const GemmOperand &A, const GemmOperand &B, const GemmDev &p, int nbatch, cudaStream_t st) {
+int g_sms = 0;
+
+template <int BN, int kStages>
+void launch(const GemmOperand &A, const GemmOperand &B, const GemmDev &p, cudaStream_t st) {
     CUtensorMap ta, tb;
     make_map(&ta, A, p.K, A.rows, BK, BM);
-    if (B_MN) make_map(&tb, B, p.N, B.rows, 64, BK);   // [K rows][N contiguous]
-    else make_map(&tb, B, p.K, B.rows, BK, BN);
-    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), nbatch);
-    gemm_tcgen05_kernel<BN, kStages, B_MN><<<grid, kThreads, smem_bytes<BN, kStages>(), st>>>(ta, tb, p);
+    make_map(&tb, B, p.K, B.rows, BK, BN);
+    const int total = ceil_div(p.N, BN) * ceil_div(p.M, BM) * p.nbatch;
+    gemm_tcgen05_kernel<BN, kStages><<<std::min(total, g_sms), kThreads, smem_bytes<BN, kStages>(), st>>>(ta, tb, p);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -228,27 +250,32 @@ void gemm_init() {
         if (!fn || qres != cudaDriverEntryPointSuccess) SS_THROW(-4, "cuTensorMapEncodeTiled is not available in this driver");
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128, 3>()));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<64, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<64, 4>()));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128, 4>()));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<256, 4>()));
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
 }
 
 void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int K, bool b_mn_major, const GemmEpilogue &ep,
                   cudaStream_t st, int *launches) {
     GemmDev p{};
-    p.M = M; p.N = N; p.K = K; p.nb0 = (int)A.batch0;
+    p.M = M; p.N = N; p.K = K;
     p.bias = ep.bias; p.alpha = ep.alpha; p.alpha_cols = ep.alpha_cols; p.gelu = ep.gelu; p.pos = ep.pos; p.pos_rows = ep.pos_rows > 0 ? ep.pos_rows : 1;
     p.residual = ep.residual; p.out_f16 = ep.out_type == GEMM_OUT_F16; p.out = ep.out; p.out_ld = ep.out_ld;
     p.out_stride0 = ep.out_stride0; p.out_stride1 = ep.out_stride1; p.head_major = ep.head_major; p.head_rows = ep.head_rows;
     p.out_row_offset = ep.out_row_offset;
     if (p.residual && p.out_f16) SS_THROW(-9, "residual epilogue needs an f32 output");
-    if (A.batch0 != B.batch0 || A.batch1 != B.batch1) SS_THROW(-9, "GEMM batch mismatch");
-    const int nbatch = (int)(A.batch0 * A.batch1);
-    if (b_mn_major) {
-        if (N > 64) SS_THROW(-9, "MN-major B supports N <= 64");
-        launch<64, 4, true>(A, B, p, nbatch, st);
-    } else {
-        launch<128, 3, false>(A, B, p, nbatch, st);
-    }
+    p.a_bcast = ep.a_broadcast; p.bias_stride0 = ep.bias_stride0;
+    if (!p.a_bcast && (A.batch0 != B.batch0 || A.batch1 != B.batch1)) SS_THROW(-9, "GEMM batch mismatch");
+    p.nb0 = (int)B.batch0; p.nbatch = (int)(B.batch0 * B.batch1);
+    if (b_mn_major) SS_THROW(-1, "MN-major B is only supported inside the fused attention kernel");
+    if (!g_sms) gemm_init();
+    // tile width: rounds of the persistent grid x relative tile cost (a 128x256 tile costs ~1.6x a 128x128 one)
+    const long t128 = (long)ceil_div(N, 128) * ceil_div(M, BM) * p.nbatch, t256 = (long)ceil_div(N, 256) * ceil_div(M, BM) * p.nbatch;
+    const double c128 = (double)ceil_div<long>(t128, g_sms), c256 = 1.6 * (double)ceil_div<long>(t256, g_sms);
+    if (N >= 256 && c256 < c128) launch<256, 4>(A, B, p, st);
+    else launch<128, 4>(A, B, p, st);
     (*launches)++;
 }
 

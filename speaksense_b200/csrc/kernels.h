@@ -40,6 +40,8 @@ struct GemmEpilogue {
     int head_major = 0;              // out index = ((n/64) * head_rows + m) * 64 + n%64 (+ batch strides)
     long head_rows = 0;
     int out_row_offset = 0;          // rows shift (padded conv layouts)
+    int a_broadcast = 0;             // A has no batch dimension (B / bias / out do)
+    long bias_stride0 = 0;           // bias elements between inner batches
 };
 // D[b][M][N] = A[b][M][K] . B[b][N][K]^T  (B K-major) or A . B[b][K][N] (b_mn_major)
 void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int K, bool b_mn_major,
@@ -93,7 +95,7 @@ struct MegaParams {   // device-resident descriptor of one decoder sequence (dec
     ss_u64 *xA, *xB, *xC, *q1, *kcur, *vcur, *att1, *q2, *att2, *hbuf, *part, *stats;
     float *logits; TokData *tok_out; float *keep; int keep_cap;
     __half *self_k, *self_v;              // [layer][head][n_text_ctx][64]
-    const __half *cross_k, *cross_v;      // [layer][head][n_audio_ctx][64]
+    const __half *cross_k, *cross_v;      // [layer][K | V][head][n_audio_ctx][64]: layer stride 2*T*d, V = K + T*d
     long long *prof;             // optional [grid][8] cycle counters (SS_MEGA_PROF=1), else null
     int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
     int suppress_blank, tdrz, tid0_init;
