@@ -19,7 +19,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+enum : int { EPI_F16_BIAS = 0, EPI_F16_BIAS_GELU, EPI_F32_RESID, EPI_F32_GELU_POS, EPI_F16_HEADMAJOR, EPI_F32_PLAIN };
 
 using namespace ptx;
 
@@ -42,7 +43,7 @@ __device__ __forceinline__ float gelu_ggml(float x) {
 // Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, + gridDim.x, ...
 // The smem ring (TMA <-> MMA) keeps running across tile boundaries and the accumulator is double-buffered in
 // TMEM (2 x BN columns), so the epilogue of tile i overlaps the main loop of tile i + 1.
-template <int BN, int kStages>
+template <int BN, int kStages, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -121,8 +122,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             }
         }
     } else {
-        // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) ----------------
+        // ---------------- epilogue: warps w and w+4 own TMEM lanes [32q, 32q+32), q = w & 3, and split the columns ----------------
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;                  // 0: columns [0, BN/2), 1: [BN/2, BN)
         uint32_t i = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, i++) {
             const int z = t / tiles_mn, r = t - z * tiles_mn;
@@ -136,29 +138,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             const float *bias = p.bias ? p.bias + (long)b0 * p.bias_stride0 : nullptr;
             const bool row_ok = m < p.M;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
                 uint32_t rr[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), rr);
                 const int nb = n0 + c;
                 if (!row_ok || nb >= p.N) continue;
                 const int nvalid = min(32, p.N - nb);
                 float v[32];
+                if (bias && nvalid == 32) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    float x = __uint_as_float(rr[j]);
-                    const int n = nb + j;
-                    if (j < nvalid) {
-                        if (bias) x += __ldg(bias + n);
-                        if (n < p.alpha_cols) x *= p.alpha;
-                        if (p.gelu) x = gelu_ggml(x);
-                        if (p.pos) x += __ldg(p.pos + (size_t)(m % p.pos_rows) * p.N + n);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + nb + j));
+                        v[j] = __uint_as_float(rr[j]) + b4.x; v[j + 1] = __uint_as_float(rr[j + 1]) + b4.y;
+                        v[j + 2] = __uint_as_float(rr[j + 2]) + b4.z; v[j + 3] = __uint_as_float(rr[j + 3]) + b4.w;
                     }
-                    v[j] = x;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(rr[j]) + ((bias && j < nvalid) ? __ldg(bias + nb + j) : 0.f);
+                }
+                if (EPI == EPI_F16_HEADMAJOR || EPI == EPI_F32_PLAIN) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) if (nb + j < p.alpha_cols) v[j] *= p.alpha;
+                }
+                if (EPI == EPI_F16_BIAS_GELU || EPI == EPI_F32_GELU_POS) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = gelu_ggml(v[j]);
+                }
+                if (EPI == EPI_F32_GELU_POS) {
+                    const float *pr = p.pos + (size_t)(m % p.pos_rows) * p.N + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) if (j < nvalid) v[j] += __ldg(pr + j);
                 }
                 long idx;
-                if (p.head_major) idx = ((long)(nb >> 6) * p.head_rows + m) * 64 + (nb & 63) + zoff;
+                if (EPI == EPI_F16_HEADMAJOR) idx = ((long)(nb >> 6) * p.head_rows + m) * 64 + (nb & 63) + zoff;
                 else idx = (long)(m + p.out_row_offset) * p.out_ld + nb + zoff;
-                if (p.out_f16) {
+                if (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU || EPI == EPI_F16_HEADMAJOR) {
                     __half *o = reinterpret_cast<__half *>(p.out) + idx;
                     if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
@@ -176,14 +190,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
                 } else {
                     float *o = reinterpret_cast<float *>(p.out) + idx;
                     if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                        if (EPI == EPI_F32_RESID) {
+                            float4 g[8];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (p.residual) { const float4 g = *reinterpret_cast<const float4 *>(o + j); f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w; }
-                            *reinterpret_cast<float4 *>(o + j) = f;
+                            for (int j = 0; j < 8; j++) g[j] = *reinterpret_cast<const float4 *>(o + 4 * j);     // all residual loads in flight
+#pragma unroll
+                            for (int j = 0; j < 8; j++) *reinterpret_cast<float4 *>(o + 4 * j) = make_float4(v[4 * j] + g[j].x, v[4 * j + 1] + g[j].y, v[4 * j + 2] + g[j].z, v[4 * j + 3] + g[j].w);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
                     } else {
-                        for (int j = 0; j < nvalid; j++) o[j] = p.residual ? o[j] + v[j] : v[j];
+                        for (int j = 0; j < nvalid; j++) o[j] = EPI == EPI_F32_RESID ? o[j] + v[j] : v[j];
                     }
                 }
             }
@@ -225,14 +243,23 @@ void make_map(CUtensorMap *map, const GemmOperand &op, long inner, long rows, in
 
 int g_sms = 0;
 
-template <int BN, int kStages>
+template <int BN, int kStages, int EPI>
 void launch(const GemmOperand &A, const GemmOperand &B, const GemmDev &p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kStages, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, kStages>()));
+        configured = true;
+    }
     CUtensorMap ta, tb;
     make_map(&ta, A, p.K, A.rows, BK, BM);
     make_map(&tb, B, p.K, B.rows, BK, BN);
     const int total = ceil_div(p.N, BN) * ceil_div(p.M, BM) * p.nbatch;
-    gemm_tcgen05_kernel<BN, kStages><<<std::min(total, g_sms), kThreads, smem_bytes<BN, kStages>(), st>>>(ta, tb, p);
+    gemm_tcgen05_kernel<BN, kStages, EPI><<<std::min(total, g_sms), kThreads, smem_bytes<BN, kStages>(), st>>>(ta, tb, p);
     CUDA_CHECK(cudaGetLastError());
+}
+template <int EPI>
+void launch_bn(bool wide, const GemmOperand &A, const GemmOperand &B, const GemmDev &p, cudaStream_t st) {
+    if (wide) launch<256, 4, EPI>(A, B, p, st); else launch<128, 4, EPI>(A, B, p, st);
 }
 
 }  // namespace
@@ -250,8 +277,6 @@ void gemm_init() {
         if (!fn || qres != cudaDriverEntryPointSuccess) SS_THROW(-4, "cuTensorMapEncodeTiled is not available in this driver");
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<128, 4>()));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<256, 4>()));
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -274,8 +299,22 @@ void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int 
     // tile width: rounds of the persistent grid x relative tile cost (a 128x256 tile costs ~1.6x a 128x128 one)
     const long t128 = (long)ceil_div(N, 128) * ceil_div(M, BM) * p.nbatch, t256 = (long)ceil_div(N, 256) * ceil_div(M, BM) * p.nbatch;
     const double c128 = (double)ceil_div<long>(t128, g_sms), c256 = 1.6 * (double)ceil_div<long>(t256, g_sms);
-    if (N >= 256 && c256 < c128) launch<256, 4>(A, B, p, st);
-    else launch<128, 4>(A, B, p, st);
+    const bool wide = N >= 256 && c256 < c128;
+    if (ep.head_major) {
+        if (!p.out_f16 || ep.gelu || ep.pos || ep.residual) SS_THROW(-9, "unsupported epilogue combination");
+        launch_bn<EPI_F16_HEADMAJOR>(wide, A, B, p, st);
+    } else if (p.out_f16) {
+        if (ep.pos || ep.residual || ep.alpha_cols) SS_THROW(-9, "unsupported epilogue combination");
+        if (ep.gelu) launch_bn<EPI_F16_BIAS_GELU>(wide, A, B, p, st); else launch_bn<EPI_F16_BIAS>(wide, A, B, p, st);
+    } else if (ep.residual) {
+        if (ep.gelu || ep.pos || ep.alpha_cols) SS_THROW(-9, "unsupported epilogue combination");
+        launch_bn<EPI_F32_RESID>(wide, A, B, p, st);
+    } else if (ep.gelu && ep.pos) {
+        launch_bn<EPI_F32_GELU_POS>(wide, A, B, p, st);
+    } else {
+        if (ep.gelu || ep.pos) SS_THROW(-9, "unsupported epilogue combination");
+        launch_bn<EPI_F32_PLAIN>(wide, A, B, p, st);
+    }
     (*launches)++;
 }
 
