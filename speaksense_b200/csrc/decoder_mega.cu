@@ -683,6 +683,7 @@ __device__ void build_segtab() {
             s.row0 = (int)((long)cta * N / ncta); s.rows = (int)((long)(cta + 1) * N / ncta) - s.row0; s.row_bytes = K * 2;
         }
         s.rows_per_chunk = max(1, kChunkBytes / s.row_bytes);
+        if (s.rows > s.rows_per_chunk && s.rows_per_chunk > 8) s.rows_per_chunk &= ~7;   // multi-chunk slices: whole passes of a 4-warp team (2 rows per warp)
         s.n_chunks = (s.rows + s.rows_per_chunk - 1) / s.rows_per_chunk;
         sm.seg[kind] = s;
     }
