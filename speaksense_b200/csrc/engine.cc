@@ -215,6 +215,8 @@ State::~State() {
         MegaParams &b = d->mp;
         cudaFree(b.ctl); cudaFree(d->d_ll); cudaFree(b.logits); cudaFree(b.tok_out); if (b.prof) cudaFree(b.prof);
         cudaFree(b.self_k); cudaFree(b.self_v); cudaFree(d->d_mp);
+        if (d->alt_k) cudaFree(d->alt_k);
+        if (d->alt_v) cudaFree(d->alt_v);
         cudaFreeHost(d->h_ctl); cudaFreeHost(d->h_tok);
     }
     void *ptrs[] = {d_pcm, d_mel, d_max, win, x1, xn, qkv, att, ff, enc16, x, enc_out, cross_k, keep};
@@ -535,6 +537,76 @@ static void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos) {
     CUDA_CHECK(cudaMemcpy2DAsync(to.mp.self_v, pitch, from.mp.self_v, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
 }
 
+// ---- beam search (whisper_full's BEAM_SEARCH strategy; the reference itself always asks for Greedy{best_of:5},
+// whisper.rs:132 - this is the beam_size>1 extension BASELINE config 5 names)
+struct BeamCandidate { int decoder_idx, seek_delta; bool has_ts; Sequence seq; };
+
+// whisper_sample_token_topk: the k most likely tokens (log-prob descending, id ascending on ties), each carrying the
+// same timestamp summary (tid / pt / ptsum) sample_token_host computes
+static std::vector<TokData> sample_topk_host(const Model &m, const Decoder &dc, int k) {
+    const Vocab &v = m.vocab; const int nv = m.hp.n_vocab;
+    std::vector<int> ids(nv);
+    for (int i = 0; i < nv; i++) ids[i] = i;
+    k = std::min(k, nv);
+    std::partial_sort(ids.begin(), ids.begin() + k, ids.end(), [&](int a, int b) {
+        return dc.logprobs[a] > dc.logprobs[b] || (dc.logprobs[a] == dc.logprobs[b] && a < b);
+    });
+    double sum_ts = 0.0, max_ts = 0.0; int tid = 0;
+    for (int i = v.beg; i < nv; i++) { sum_ts += dc.probs[i]; if (max_ts < dc.probs[i]) { max_ts = dc.probs[i]; tid = i; } }
+    std::vector<TokData> out;
+    for (int a = 0; a < k; a++) {
+        TokData t{ids[a], tid, dc.probs[ids[a]], dc.logprobs[ids[a]], (float)(max_ts / (sum_ts + 1e-10)), (float)sum_ts};
+        if (t.id >= v.beg) { t.tid = t.id; t.pt = t.p; }
+        out.push_back(t);
+    }
+    return out;
+}
+
+static bool same_tokens(const Sequence &a, const Sequence &b) {
+    if (a.tokens.size() != b.tokens.size()) return false;
+    for (size_t i = 0; i < a.tokens.size(); i++) if (a.tokens[i].id != b.tokens[i].id) return false;
+    return true;
+}
+
+// hand the best candidates to the live decoders (skipping duplicates of the one just taken) and move each decoder's
+// self-attention cache to follow its new sequence. The shuffle is two-phase like whisper.cpp's temporary sequence ids:
+// every moved cache is first copied into the destination decoder's second buffer, then the buffers are swapped.
+static void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i, int n_past) {
+    std::stable_sort(cands.begin(), cands.end(), [](const BeamCandidate &a, const BeamCandidate &b) {
+        return a.seq.sum_logprobs_all > b.seq.sum_logprobs_all;
+    });
+    const HParams &hp = s.engine->model.hp;
+    const size_t kv = (size_t)hp.n_text_layer * hp.n_text_ctx * hp.n_text_state;
+    size_t cur_c = 0;
+    std::vector<int> src(n_cur, -1);
+    for (int j = 0; j < n_cur; j++) {
+        Decoder &dc = *s.dec[j];
+        if (dc.completed || dc.failed) continue;
+        if (cur_c >= cands.size()) cur_c = 0;
+        const BeamCandidate &c = cands[cur_c++];
+        while (cands.size() > cur_c && i > 0 && same_tokens(cands[cur_c].seq, c.seq)) ++cur_c;
+        dc.seek_delta = c.seek_delta; dc.has_ts = c.has_ts; dc.seq = c.seq;
+        src[j] = c.decoder_idx;
+    }
+    const size_t pitch = (size_t)hp.n_text_ctx * 64 * 2, width = (size_t)n_past * 64 * 2, height = (size_t)hp.n_text_layer * hp.n_text_head;
+    for (int j = 0; j < n_cur; j++) {
+        if (src[j] < 0 || src[j] == j) continue;
+        Decoder &to = *s.dec[j]; const Decoder &from = *s.dec[src[j]];
+        if (!to.alt_k) {
+            to.alt_k = dmalloc<__half>(kv); to.alt_v = dmalloc<__half>(kv);
+            CUDA_CHECK(cudaMemsetAsync(to.alt_k, 0, kv * 2, s.stream)); CUDA_CHECK(cudaMemsetAsync(to.alt_v, 0, kv * 2, s.stream));
+        }
+        CUDA_CHECK(cudaMemcpy2DAsync(to.alt_k, pitch, from.mp.self_k, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
+        CUDA_CHECK(cudaMemcpy2DAsync(to.alt_v, pitch, from.mp.self_v, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));
+    }
+    for (int j = 0; j < n_cur; j++) {
+        if (src[j] < 0 || src[j] == j) continue;
+        Decoder &to = *s.dec[j];
+        std::swap(to.mp.self_k, to.alt_k); std::swap(to.mp.self_v, to.alt_v);
+        to.mp_dirty = true;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // whisper_full
 // ------------------------------------------------------------------------------------------------
@@ -544,7 +616,8 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
     s.raw.clear(); s.out.clear(); s.full_text.clear(); s.result_tokens.clear();
     s.n_fallbacks = 0; s.n_decoded = 0; s.n_windows = 0; s.n_launches = 0; s.n_keep = 0; s.h_keep.clear();
     s.ms_mel = s.ms_enc = s.ms_dec = 0;
-    if (P.beam_size > 1) SS_THROW(-1, "beam search is not implemented in this build (beam_size=%d)", P.beam_size);
+    const bool beam = P.beam_size > 1;
+    if (P.beam_size > kMaxDecoders || P.best_of > kMaxDecoders) SS_THROW(-1, "beam_size / best_of above %d", kMaxDecoders);
 
     int lang = 0;
     if (v.multilingual) { lang = lang_id(P.language.c_str()); if (lang < 0) SS_THROW(-6, "unknown language '%s'", P.language.c_str()); }
@@ -567,7 +640,7 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
     if (P.temperature_inc > 0.0f) { for (float t = P.temperature; t < 1.0f + 1e-6f; t += P.temperature_inc) temps.push_back(t); }
     else temps.push_back(P.temperature);
 
-    int n_decoders = std::max(1, P.best_of);
+    const int n_decoders = std::max(1, beam ? std::max(P.best_of, P.beam_size) : P.best_of);
     if (P.no_context) s.prompt_past.clear();
 
     std::vector<int> prompt_init = {v.sot};
@@ -590,7 +663,7 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
         int best_decoder_id = 0;
         for (size_t it = 0; it < temps.size(); it++) {
             const float t_cur = temps[it];
-            const int n_cur = t_cur > 0.0f ? n_decoders : 1;
+            const int n_cur = std::max(1, beam ? (t_cur > 0.0f ? P.best_of : P.beam_size) : (t_cur > 0.0f ? n_decoders : 1));
             if (it > 0) s.n_fallbacks++;
             while ((int)s.dec.size() < n_cur) new_decoder(s, false);
             for (int j = 0; j < n_cur; j++) {
@@ -608,7 +681,7 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
             const int n_prompt = (int)prompt.size();
 
             CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
-            if (t_cur < 1e-6f) {
+            if (!beam && t_cur < 1e-6f) {
                 // ---------------- greedy at temperature 0: whole loop on the device ----------------
                 Decoder &dc = *s.dec[0];
                 set_sampling(dc, P, tid0_init);
@@ -639,7 +712,7 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
                     s.n_keep += nk;
                 }
             } else {
-                // ---------------- t > 0: best_of sampled decoders, host-side sampling ----------------
+                // ------- t > 0: best_of sampled decoders; beam search at any temperature: host-side sampling -------
                 for (int j = 0; j < n_cur; j++) set_sampling(*s.dec[j], P, tid0_init);
                 step_host_sampled(s, *s.dec[0], prompt.data(), n_prompt, 0);
                 s.n_decoded += n_prompt - 1;
@@ -648,13 +721,24 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
                     kv_copy(s, *s.dec[0], *s.dec[j], n_prompt);
                     s.dec[j]->probs = s.dec[0]->probs; s.dec[j]->logits = s.dec[0]->logits; s.dec[j]->logprobs = s.dec[0]->logprobs;
                 }
+                std::vector<BeamCandidate> cands;
                 for (int i = 0; i < n_max; i++) {
+                    cands.clear();
                     for (int j = 0; j < n_cur; j++) {
                         Decoder &dc = *s.dec[j];
                         if (dc.completed || dc.failed) continue;
-                        dc.seq.tokens.push_back(sample_token_host(m, dc, false));
-                        dc.seq.sum_logprobs_all += dc.seq.tokens.back().plog;
+                        if (!beam) {
+                            dc.seq.tokens.push_back(sample_token_host(m, dc, false));
+                            dc.seq.sum_logprobs_all += dc.seq.tokens.back().plog;
+                        } else {
+                            for (const TokData &t : sample_topk_host(m, dc, P.beam_size)) {
+                                cands.push_back({j, dc.seek_delta, dc.has_ts, dc.seq});
+                                cands.back().seq.tokens.push_back(t);
+                                cands.back().seq.sum_logprobs_all += t.plog;
+                            }
+                        }
                     }
+                    if (beam) beam_advance(s, cands, n_cur, i, n_prompt + i);
                     for (int j = 0; j < n_cur; j++) {
                         Decoder &dc = *s.dec[j];
                         if (dc.completed || dc.failed) continue;

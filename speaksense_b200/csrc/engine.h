@@ -27,6 +27,8 @@ struct FullParams {   // == build_params (whisper.rs:131-173) + overrides (:60-7
     bool keep_logits = false;
 };
 
+constexpr int kMaxDecoders = 8;   // WHISPER_MAX_DECODERS
+
 struct Sequence {
     std::vector<TokData> tokens;
     int result_len = 0;
@@ -43,7 +45,8 @@ struct Decoder {
     Sequence seq;
     int seek_delta = 0;
     bool failed = false, completed = false, has_ts = false;
-    std::vector<float> probs, logits, logprobs;   // host-sampled fallback path
+    std::vector<float> probs, logits, logprobs;   // host-sampled fallback / beam path
+    __half *alt_k = nullptr, *alt_v = nullptr;    // second self-KV buffer: target of the beam-search cache shuffle
     std::mt19937 rng{0};
 };
 

@@ -130,3 +130,39 @@ def test_large_v3_shapes_two_layers(oracle_mod, audio30):
     assert toks == ref["tokens"]
     assert np.abs(st.debug_logits() - ref_logits).max() < 1e-2
     eng.close()
+
+
+@pytest.mark.parametrize("fixture,lang,beam", [("tiny_en_peaked", None, 5), ("micro_v3_peaked", "zh", 5), ("tiny_en_peaked", None, 2)])
+def test_beam_search_matches_oracle(request, oracle_mod, audio30, fixture, lang, beam):
+    """beam_size>1 (BASELINE config 5; an extension - the reference always asks for Greedy{best_of:5}, whisper.rs:132):
+    the host-driven beam loop with the device KV shuffle selects the same sequence as the oracle's whisper_full."""
+    from speaksense_b200 import AsrParams, WhisperAsr
+    path = request.getfixturevalue(fixture)
+    om = oracle_mod.OracleModel(path)
+    ost = om.new_state()
+    ref = ost.full(audio30, language=lang, stream_mode=False, beam_size=beam)
+    greedy = ost.full(audio30, language=lang, stream_mode=True)
+    ost.close(); om.close()
+    eng = WhisperAsr(path)
+    st = eng.create_state()
+    res = eng.transcribe_with_state(st, audio30, AsrParams(language=lang, stream_mode=False, beam_size=beam))
+    toks, plogs = st.result_tokens()
+    assert toks == ref["tokens"]
+    assert np.allclose(plogs, ref["plogs"], atol=1e-2)
+    exp = post_process(ref["segments"], False)
+    assert [(s.text, s.speaker_id, s.start, s.end) for s in res.segments] == exp["segments"]
+    assert st.stats()["n_fallbacks"] == ref["n_fallbacks"]
+    assert toks == greedy["tokens"]          # on a peaked model the best beam is the greedy path
+    # the greedy device path still works on the same state afterwards (KV buffers were swapped around by the beam shuffle)
+    again = eng.transcribe_with_state(st, audio30, AsrParams(language=lang, stream_mode=True))
+    assert st.result_tokens()[0] == greedy["tokens"] and again.full_text != ""
+    st.close(); eng.close()
+
+
+def test_beam_size_above_limit_is_rejected(tiny_en_peaked, audio30):
+    from speaksense_b200 import AsrParams, WhisperAsr
+    from speaksense_b200._native import NativeError
+    eng = WhisperAsr(tiny_en_peaked)
+    with pytest.raises(NativeError):
+        eng.transcribe(audio30, AsrParams(beam_size=9))
+    eng.close()
