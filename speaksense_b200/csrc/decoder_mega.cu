@@ -34,12 +34,16 @@ namespace {
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kMegaThreads = kConsumerThreads + 32;
-constexpr int kSlots = 7;
-constexpr int kChunkBytes = 23040;      // 9 rows of d = 1280: a CTA's whole slice of a d-row matrix is one chunk
+constexpr int kChunkRows = 16;        // weight rows (of d halfs) per ring chunk = one m16 MMA tile
+constexpr int kRowPad = 16;           // bytes of padding between rows in a slot: ldmatrix of 8 rows hits 8 different bank groups
+constexpr int kSlots = 4;
+constexpr int kChunkBytes = kChunkRows * (1280 * 2 + kRowPad);   // 41216
 constexpr int kMaxXs = 5120;          // largest mat-vec input (4 * d, d <= 1280)
-constexpr int kMaxRowsPerCta = 512;   // per phase, x KQ partials
+constexpr int kMaxRowsPerCta = 512;   // per phase
+constexpr int kMaxTiles = 24;         // chunks per phase (LM head: n_vocab / grid / 16)
 constexpr int kMaxScores = 512;
 constexpr int kMaxJ = 5;              // d / 8 / 32 uint4 chunks per lane, d <= 1280
+constexpr int kMaxKSteps = 10;        // k16 steps per warp: d / 8 warps / 16, d <= 1280
 typedef unsigned long long u64;
 
 enum SegKind : int { SEG_QKV = 0, SEG_O, SEG_CQ, SEG_XK, SEG_XV, SEG_CO, SEG_FC1, SEG_FC2, SEG_LM, SEG_COUNT };
@@ -47,11 +51,13 @@ enum SegKind : int { SEG_QKV = 0, SEG_O, SEG_CQ, SEG_XK, SEG_XV, SEG_CO, SEG_FC1
 struct DecState {   // replicated per CTA (thread-uniform, lives in shared memory)
     int pos, token, n_sampled, has_ts, seek_delta, result_len, last_id, penult_id, n_kept, failed, completed, done;
 };
-struct SegTab { int row0, rows, row_bytes, rows_per_chunk, n_chunks; };
+struct SegTab { int row0, rows, row_bytes, rows_per_chunk, n_chunks, prows; };   // prows: rows of d halfs (FC2: 4 per output row)
 
 struct __align__(128) MegaSmem {
     uint8_t ring[kSlots][kChunkBytes];
-    float xs[kMaxXs];               // raw input vector of the current phase
+    float xs[1280];                 // raw f32 input vector of a LayerNorm phase (also: cross-attn partials, sampling records)
+    alignas(16) __half xh[kMaxXs];  // the mat-vec operand: f16, after LayerNorm where the phase has one
+    alignas(16) float part[kMaxTiles][kConsumerWarps][16];   // per-warp K-slice partial sums of every tile of the phase
     float lnw[1280], lnb[1280];     // LayerNorm affine of the current phase (cp.async, overlapped with the poll)
     float bias[kMaxRowsPerCta];     // bias slice of this CTA's rows for the current phase
     float xown[256];                // this CTA's rows of the residual stream (stashed when the stream is polled)
@@ -69,7 +75,7 @@ struct __align__(128) MegaSmem {
     volatile int stop_req;      // consumers -> producer: stop issuing
     volatile int prod_done;     // producer -> consumers: `issued` is final
     volatile uint32_t issued;
-    long long prof[8];          // thread-0 cycle counters: poll, gemv, total
+    long long prof[24];         // thread-0 cycle counters: poll, gemv rows, x load, total, then one per phase kind
 };
 
 extern __shared__ __align__(128) uint8_t mega_smem_raw[];
@@ -149,9 +155,11 @@ __device__ __forceinline__ ulonglong2 ll_load2(const u64 *p) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
 }
-// poll n (even) flagged floats into dst (shared); every thread spins only on its own words.
+// poll n (even) flagged floats into dst (shared; f32, or f16 when TO_HALF - the values of the non-LayerNorm
+// phases are f16-representable by construction); every thread spins only on its own words.
 // Returns this thread's {sum, sum of squares} of what it fetched (LayerNorm statistics for free).
-__device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, float *dst) {
+template <bool TO_HALF>
+__device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, void *dst) {
     const int n2 = n >> 1, tid = threadIdx.x;
     float s = 0.f, s2 = 0.f;
     const long long t0 = clock64();
@@ -173,8 +181,8 @@ __device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, f
             const int i = base + tid + j * kConsumerThreads;
             if (i < n2) {
                 const float a = __uint_as_float((uint32_t)v[j].x), b = __uint_as_float((uint32_t)v[j].y);
-                reinterpret_cast<float2 *>(dst)[i] = make_float2(a, b);
-                s += a + b; s2 += a * a + b * b;
+                if (TO_HALF) reinterpret_cast<__half2 *>(dst)[i] = __floats2half2_rn(a, b);
+                else { reinterpret_cast<float2 *>(dst)[i] = make_float2(a, b); s += a + b; s2 += a * a + b * b; }
             }
         }
     }
@@ -245,6 +253,61 @@ __device__ __noinline__ float2 embed_xs() {
     return make_float2(s, s2);
 }
 
+// The tensor-core part of a mat-vec phase.  Every warp owns one eighth of K for ALL rows of the CTA's slice, so its B
+// fragments (the x side of mma.m16n8k16) stay in registers for the whole phase; the A fragments come out of the ring
+// with ldmatrix (rows are kRowPad bytes off bank alignment).  Column n of B carries x quarter n & 3: FC2 views its
+// 4d-long rows as 4 rows of d, output row r = sum over q of C[4r + q][q]; for the other matrices all columns equal x.
+// Per tile, the lanes holding the wanted column leave their 16 row sums in sm.part[tile][warp].
+template <int KS>
+__device__ __noinline__ uint32_t gemv_tiles(uint32_t cons, int n_chunks, int row_bytes, int kq, int d) {
+    MegaSmem &sm = SM;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kwarp = warp * (d >> 3);
+    const int qsel = kq == 4 ? ((lane >> 2) & 3) : 0;
+    const bool owner = (lane & 3) == (qsel >> 1);
+    uint32_t bf[2 * KS];
+    {
+        const __half *xq = sm.xh + qsel * d + kwarp + 2 * (lane & 3);
+#pragma unroll
+        for (int j = 0; j < KS; j++) {
+            bf[2 * j] = *reinterpret_cast<const uint32_t *>(xq + 16 * j);
+            bf[2 * j + 1] = *reinterpret_cast<const uint32_t *>(xq + 16 * j + 8);
+        }
+    }
+    const uint32_t pitch = (uint32_t)row_bytes + kRowPad;
+    const uint32_t a_off = (uint32_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * pitch + (uint32_t)(kwarp + 8 * (lane >> 4)) * 2;
+    for (int ch = 0; ch < n_chunks; ch++) {
+        const int slot = cons % kSlots;
+        mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
+        const uint32_t abase = smem_u32(sm.ring[slot]) + a_off;
+        uint32_t af[KS][4];
+#pragma unroll
+        for (int j = 0; j < KS; j++)
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 32u * j));
+        constexpr int NA = KS >= 4 ? 4 : KS;     // independent accumulator sets
+        float cc[NA][4];
+#pragma unroll
+        for (int i = 0; i < NA; i++) { cc[i][0] = 0.f; cc[i][1] = 0.f; cc[i][2] = 0.f; cc[i][3] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < KS; j++)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(cc[j % NA][0]), "+f"(cc[j % NA][1]), "+f"(cc[j % NA][2]), "+f"(cc[j % NA][3])
+                         : "r"(af[j][0]), "r"(af[j][1]), "r"(af[j][2]), "r"(af[j][3]), "r"(bf[2 * j]), "r"(bf[2 * j + 1]));
+#pragma unroll
+        for (int i = 1; i < NA; i++) { cc[0][0] += cc[i][0]; cc[0][1] += cc[i][1]; cc[0][2] += cc[i][2]; cc[0][3] += cc[i][3]; }
+        if (owner) {
+            float *pp = &sm.part[ch][warp][lane >> 2];
+            pp[0] = (qsel & 1) ? cc[0][1] : cc[0][0];
+            pp[8] = (qsel & 1) ? cc[0][3] : cc[0][2];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[slot]);
+        cons++;
+    }
+    return cons;
+}
+
 // One mat-vec phase, start to finish: prefetch static operands, poll the input vector, (LayerNorm), rows
 // of this CTA's slice straight out of the ring, epilogue, flagged stores of the outputs.
 //   kind  : SEG_QKV / SEG_O / SEG_CQ / SEG_CO / SEG_FC1 / SEG_FC2 / SEG_LM
@@ -265,85 +328,51 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uin
     if (kind == SEG_LM) prefetch_ln(P.lnf_w, P.lnf_b, d);
     else prefetch_ln(has_ln ? P.layer[il].lnw[lidx] : nullptr, has_ln ? P.layer[il].lnb[lidx] : nullptr, d);
     // ---- input vector
-    float2 ss;
+    float2 ss = make_float2(0.f, 0.f);
     if (kind == SEG_QKV && il == 0) ss = embed_xs();
     else {
         const u64 *src = kind == SEG_QKV || kind == SEG_LM ? P.xA : kind == SEG_O ? P.att1 : kind == SEG_CQ ? P.xB : kind == SEG_CO ? P.att2
                          : kind == SEG_FC1 ? P.xC : P.hbuf;
-        ss = poll_vec(src, kind == SEG_FC2 ? 4 * d : d, ep_in, sm.xs);
+        if (has_ln) ss = poll_vec<false>(src, d, ep_in, sm.xs);
+        else poll_vec<true>(src, kq * d, ep_in, sm.xh);
     }
     float mean = 0.f, rstd = 1.f;
     if (has_ln) {
-        const float2 t = consumer_sum2(ss);     // also publishes sm.xs to every consumer thread
+        asm volatile("cp.async.wait_group 0;" ::: "memory");     // LayerNorm affine (issued before the poll) has landed
+        const float2 t = consumer_sum2(ss);     // its barriers also publish sm.xs / lnw / lnb to every consumer thread
         mean = t.x / d;
         rstd = rsqrtf(fmaxf(t.y / d - mean * mean, 0.f) + 1e-5f);
         if (kind != SEG_LM && tid < own.rows) sm.xown[tid] = sm.xs[own.row0 + tid];
     } else consumer_sync();
+    // bias slice only now: before the barrier above the previous phase's epilogue may still have been reading sm.bias
     prefetch_bias(kind == SEG_LM ? nullptr : P.layer[il].b[widx], seg.row0, seg.rows);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");     // LayerNorm affine landed (bias may still be in flight)
-    consumer_sync();
     const long long tg0 = clock64();
     if (has_ln) {   // normalise once, cooperatively (ggml_norm + affine), rounded to f16 for the mat-vec
-        for (int i = tid; i < d; i += kConsumerThreads) sm.xs[i] = r16((sm.xs[i] - mean) * rstd * sm.lnw[i] + sm.lnb[i]);
+        for (int i = tid; i < d; i += kConsumerThreads) sm.xh[i] = __float2half_rn((sm.xs[i] - mean) * rstd * sm.lnw[i] + sm.lnb[i]);
         consumer_sync();
     }
-    // ---- the slice of x this lane multiplies with, in registers.  Multi-chunk segments are processed by two
-    //      teams of four warps on alternating chunks, every warp keeping two rows in flight.
-    const int nteams = seg.n_chunks >= 2 ? 2 : 1;
-    const int wpt = kConsumerWarps / nteams;
-    const int team = warp / wpt, tw = warp % wpt;
-    const int quarter = tw & (kq - 1);
-    const int group = kq == 1 ? tw : (tw >> 2);
-    const int ngroups = wpt / kq;
-    const int nchunk = d >> 3;
-    float4 xa[kMaxJ], xb[kMaxJ];
-    {
-        const float4 *x4 = reinterpret_cast<const float4 *>(sm.xs + quarter * d);
-#pragma unroll
-        for (int j = 0; j < kMaxJ; j++) {
-            const int c = lane + 32 * j;
-            if (c < nchunk) { xa[j] = x4[2 * c]; xb[j] = x4[2 * c + 1]; }
-            else { xa[j] = make_float4(0, 0, 0, 0); xb[j] = xa[j]; }
-        }
-    }
-    // ---- rows out of the ring
-    if (tid == 0) sm.prof[2] += clock64() - tg0;
-    for (int ch = 0; ch < seg.n_chunks; ch++) {
-        const int slot = cons % kSlots;
-        mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
-        if (nteams == 1 || (ch & 1) == team) {
-            const int rbase = ch * seg.rows_per_chunk;
-            const int nrows = min(seg.rows_per_chunk, seg.rows - rbase);
-            const uint8_t *cbase = sm.ring[slot] + (size_t)quarter * d * 2;
-            for (int r0 = group; r0 < nrows; r0 += 2 * ngroups) {
-                const int r1 = r0 + ngroups;
-                const bool has1 = r1 < nrows;
-                const uint4 *w0 = reinterpret_cast<const uint4 *>(cbase + (size_t)r0 * seg.row_bytes);
-                const uint4 *w1 = reinterpret_cast<const uint4 *>(cbase + (size_t)(has1 ? r1 : r0) * seg.row_bytes);
-                uint4 u0[kMaxJ], u1[kMaxJ];
-#pragma unroll
-                for (int j = 0; j < kMaxJ; j++) {
-                    const int c = lane + 32 * j;
-                    if (c < nchunk) { u0[j] = w0[c]; u1[j] = w1[c]; } else { u0[j] = make_uint4(0, 0, 0, 0); u1[j] = u0[j]; }
-                }
-                float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                for (int j = 0; j < kMaxJ; j++) { a0 = dot8(u0[j], xa[j], xb[j], a0); a1 = dot8(u1[j], xa[j], xb[j], a1); }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
-                if (lane == 0) {
-                    sm.acc[(rbase + r0) * kq + quarter] = a0;
-                    if (has1) sm.acc[(rbase + r1) * kq + quarter] = a1;
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[slot]);
-        cons++;
+    // ---- the tiles of this CTA's slice out of the ring (K-steps per warp known at compile time: registers, not local memory)
+    switch (d >> 7) {      // host side guarantees d % 128 == 0 and d <= 1280
+#define SS_KS(n) case n: cons = gemv_tiles<n>(cons, seg.n_chunks, seg.row_bytes, kq, d); break;
+        SS_KS(1) SS_KS(2) SS_KS(3) SS_KS(4) SS_KS(5) SS_KS(6) SS_KS(7) SS_KS(8) SS_KS(9)
+#undef SS_KS
+        default: cons = gemv_tiles<10>(cons, seg.n_chunks, seg.row_bytes, kq, d); break;
     }
     if (tid == 0) sm.prof[1] += clock64() - tg0;
     asm volatile("cp.async.wait_all;" ::: "memory");
     consumer_sync();
+    // ---- fold the eight K-slices (and FC2's four quarters) of every output row
+    for (int R = tid; R < seg.rows; R += kConsumerThreads) {
+        float a = 0.f;
+        for (int q = 0; q < kq; q++) {
+            const int pr = R * kq + q;
+            const float *pp = &sm.part[pr / kChunkRows][0][pr % kChunkRows];
+#pragma unroll
+            for (int w = 0; w < kConsumerWarps; w++) a += pp[w * 16];
+        }
+        sm.acc[R] = a;
+    }
+    if (kind == SEG_LM) { consumer_sync(); return cons; }   // lm_epilogue reads other threads' rows
     // ---- epilogue
     if (kind == SEG_QKV) {
         const int pos = sm.st.pos;
@@ -362,7 +391,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uin
         }
     } else if (kind != SEG_LM && tid < seg.rows) {
         const int row = seg.row0 + tid;
-        if (kind == SEG_FC2) ll_store(P.xA + row, sm.xown[tid] + (sm.acc[4 * tid] + sm.acc[4 * tid + 1] + sm.acc[4 * tid + 2] + sm.acc[4 * tid + 3]) + sm.bias[tid], ep_out);
+        if (kind == SEG_FC2) ll_store(P.xA + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
         else if (kind == SEG_O) ll_store(P.xB + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
         else if (kind == SEG_CO) ll_store(P.xC + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
         else if (kind == SEG_CQ) ll_store(P.q2 + row, r16((sm.acc[tid] + sm.bias[tid]) * P.s4), ep_out);
@@ -488,7 +517,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     float lmax = -INFINITY;
     for (int ch = 0; ch < sk.n_chunks; ch++) {
         const int slot = cons % kSlots;
-        mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
+        { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); if (tid == 0) sm.prof[14] += clock64() - tw0; }
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
         lmax = attn_scores<true>(sm.ring[slot], nk, kbase, qa, qb, lmax);
         __syncwarp();
@@ -515,7 +544,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     if (tid == 0) { ll_store(out, m, ep); ll_store(out + 1, l, ep); }
     if (sp != 0) return cons;
     // ---- split 0 folds all ns (<= 8) partial records of head h
-    poll_vec(P.part + (size_t)h * ns * 66, ns * 66, ep, sm.xs);
+    poll_vec<false>(P.part + (size_t)h * ns * 66, ns * 66, ep, sm.xs);
     consumer_sync();
     if (tid < 64) {
         float M = -INFINITY;
@@ -599,7 +628,7 @@ __device__ __noinline__ void sample_and_update(int seek, int seek_end, int n_max
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
     const int tid = threadIdx.x, lane = tid & 31, ncta = gridDim.x;
-    poll_vec(P.stats, ncta * 8, ep, sm.xs);
+    poll_vec<false>(P.stats, ncta * 8, ep, sm.xs);
     consumer_sync();
     if (tid < 32) {
         MaxIdx mt{-INFINITY, 0x7fffffff}, ms{-INFINITY, 0x7fffffff};
@@ -677,14 +706,16 @@ __device__ void build_segtab() {
                 const int sp = cta % P.xsplit, per = (P.T + P.xsplit - 1) / P.xsplit;
                 s.row0 = sp * per; s.rows = max(0, min(P.T, s.row0 + per) - s.row0);
             }
+            s.prows = s.rows;
+            s.rows_per_chunk = max(1, kChunkBytes / s.row_bytes);
         } else {
             const int N = kind == SEG_QKV ? 3 * d : kind == SEG_FC1 ? 4 * d : kind == SEG_LM ? P.n_vocab : d;
-            const int K = kind == SEG_FC2 ? 4 * d : d;
-            s.row0 = (int)((long)cta * N / ncta); s.rows = (int)((long)(cta + 1) * N / ncta) - s.row0; s.row_bytes = K * 2;
+            const int kq = kind == SEG_FC2 ? 4 : 1;
+            s.row0 = (int)((long)cta * N / ncta); s.rows = (int)((long)(cta + 1) * N / ncta) - s.row0;
+            s.row_bytes = d * 2; s.prows = s.rows * kq;      // rows of d halfs: FC2's 4d-long rows count as 4
+            s.rows_per_chunk = kChunkRows;
         }
-        s.rows_per_chunk = max(1, kChunkBytes / s.row_bytes);
-        if (s.rows > s.rows_per_chunk && s.rows_per_chunk > 8) s.rows_per_chunk &= ~7;   // multi-chunk slices: whole passes of a 4-warp team (2 rows per warp)
-        s.n_chunks = (s.rows + s.rows_per_chunk - 1) / s.rows_per_chunk;
+        s.n_chunks = (s.prows + s.rows_per_chunk - 1) / s.rows_per_chunk;
         sm.seg[kind] = s;
     }
 }
@@ -695,7 +726,7 @@ __device__ __forceinline__ const uint8_t *seg_base(const MegaParams &P, const Se
     }
     const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : kind == SEG_FC1 ? 4 : 5;
     const __half *w = kind == SEG_LM ? P.tok_emb : P.layer[il].w[widx];
-    return reinterpret_cast<const uint8_t *>(w) + (size_t)s.row0 * s.row_bytes;
+    return reinterpret_cast<const uint8_t *>(w) + (size_t)s.row0 * (kind == SEG_FC2 ? 4 : 1) * s.row_bytes;
 }
 
 }  // namespace
@@ -725,7 +756,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     if (tid == 0) {
         for (int s = 0; s < kSlots; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
         sm.stop_req = 0; sm.prod_done = 0; sm.issued = 0;
-        for (int i = 0; i < 8; i++) sm.prof[i] = 0;
+        for (int i = 0; i < 24; i++) sm.prof[i] = 0;
         DecState st;
         st.pos = pos_start; st.token = ctl->token; st.n_sampled = ctl->n_sampled; st.has_ts = ctl->has_ts; st.seek_delta = ctl->seek_delta;
         st.result_len = ctl->result_len; st.last_id = ctl->last_id; st.penult_id = ctl->penult_id; st.n_kept = ctl->n_kept;
@@ -738,33 +769,47 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 
     if (warp == kConsumerWarps) {
         // ======================= producer =======================
-        if (lane == 0) {
-            uint64_t policy;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-            uint32_t issued = 0;
-            bool stopped = false;
-            for (int t = 0; t < steps_left && !stopped; t++) {
-                const int jrel = pos_start - pos0 + t;
-                const bool need_logits = all_logits || jrel >= n_prompt - 1;
-                const int nseg = L * (SEG_LM) + (need_logits ? 1 : 0);
-                for (int si = 0; si < nseg && !stopped; si++) {
-                    const int layer = si / SEG_LM, kind = si < L * SEG_LM ? si % SEG_LM : SEG_LM;
-                    const SegTab seg = sm.seg[kind];
-                    const uint8_t *base = seg_base(P, seg, kind, layer < L ? layer : 0);
-                    for (int ch = 0; ch < seg.n_chunks; ch++) {
-                        const int slot = issued % kSlots;
-                        const uint32_t par = ((issued / kSlots) & 1) ^ 1;
+        // Lane 0 tracks the ring; weight chunks go out as one bulk copy per row (lane r copies row r) so that rows land
+        // kRowPad bytes apart, cross-attention K/V chunks as one contiguous copy.
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        uint32_t issued = 0;
+        bool stopped = false;
+        for (int t = 0; t < steps_left && !stopped; t++) {
+            const int jrel = pos_start - pos0 + t;
+            const bool need_logits = all_logits || jrel >= n_prompt - 1;
+            const int nseg = L * (SEG_LM) + (need_logits ? 1 : 0);
+            for (int si = 0; si < nseg && !stopped; si++) {
+                const int layer = si / SEG_LM, kind = si < L * SEG_LM ? si % SEG_LM : SEG_LM;
+                const SegTab seg = sm.seg[kind];
+                const uint8_t *base = seg_base(P, seg, kind, layer < L ? layer : 0);
+                const bool padded = !(kind == SEG_XK || kind == SEG_XV);
+                for (int ch = 0; ch < seg.n_chunks; ch++) {
+                    const int slot = issued % kSlots;
+                    const uint32_t par = ((issued / kSlots) & 1) ^ 1;
+                    const int rbase = ch * seg.rows_per_chunk;
+                    const int nrows = min(seg.rows_per_chunk, seg.prows - rbase);
+                    if (lane == 0) {
                         while (!mbar_try_wait(&sm.empty[slot], par)) { if (sm.stop_req) { stopped = true; break; } __nanosleep(128); }   // do not out-prioritise the consumer warps of this scheduler
-                        if (stopped || sm.stop_req) { stopped = true; break; }
-                        const int rbase = ch * seg.rows_per_chunk;
-                        const uint32_t bytes = (uint32_t)min(seg.rows_per_chunk, seg.rows - rbase) * seg.row_bytes;
-                        mbar_expect_tx(&sm.full[slot], bytes);
-                        bulk_g2s(sm.ring[slot], base + (size_t)rbase * seg.row_bytes, bytes, &sm.full[slot], policy);
-                        issued++;
+                        if (sm.stop_req) stopped = true;
+                        if (!stopped) mbar_expect_tx(&sm.full[slot], (uint32_t)nrows * seg.row_bytes);
                     }
+                    stopped = __shfl_sync(0xffffffffu, (int)stopped, 0) != 0;
+                    __syncwarp();
+                    if (stopped) break;
+                    if (padded) {
+                        if (lane < nrows)
+                            bulk_g2s(sm.ring[slot] + (size_t)lane * (seg.row_bytes + kRowPad), base + (size_t)(rbase + lane) * seg.row_bytes,
+                                     (uint32_t)seg.row_bytes, &sm.full[slot], policy);
+                    } else if (lane == 0) {
+                        bulk_g2s(sm.ring[slot], base + (size_t)rbase * seg.row_bytes, (uint32_t)nrows * seg.row_bytes, &sm.full[slot], policy);
+                    }
+                    issued++;
                 }
             }
-            // hand the issue count to the consumers so that they can drain in-flight copies before exit
+        }
+        // hand the issue count to the consumers so that they can drain in-flight copies before exit
+        if (lane == 0) {
             sm.issued = issued;
             __threadfence_block();
             sm.prod_done = 1;
@@ -786,15 +831,18 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 #pragma unroll 1
         for (int il = 0; il < L; il++) {
             const uint32_t ep = ep0 + (uint32_t)il;
-            cons = gemv_phase(cons, SEG_QKV, il, ep, ep);
-            self_attn(il, ep);
-            cons = gemv_phase(cons, SEG_O, il, ep, ep);
-            cons = gemv_phase(cons, SEG_CQ, il, ep, ep);
-            cons = cross_attn(cons, ep);
-            cons = gemv_phase(cons, SEG_CO, il, ep, ep);
-            cons = gemv_phase(cons, SEG_FC1, il, ep, ep);
-            cons = gemv_phase(cons, SEG_FC2, il, ep, ep + 1);
+            long long tp = clock64();
+#define SS_PROF_PHASE(k) { const long long tn = clock64(); if (tid == 0) sm.prof[4 + (k)] += tn - tp; tp = tn; }
+            cons = gemv_phase(cons, SEG_QKV, il, ep, ep);       SS_PROF_PHASE(0)
+            self_attn(il, ep);                                  SS_PROF_PHASE(1)
+            cons = gemv_phase(cons, SEG_O, il, ep, ep);         SS_PROF_PHASE(2)
+            cons = gemv_phase(cons, SEG_CQ, il, ep, ep);        SS_PROF_PHASE(3)
+            cons = cross_attn(cons, ep);                        SS_PROF_PHASE(4)
+            cons = gemv_phase(cons, SEG_CO, il, ep, ep);        SS_PROF_PHASE(5)
+            cons = gemv_phase(cons, SEG_FC1, il, ep, ep);       SS_PROF_PHASE(6)
+            cons = gemv_phase(cons, SEG_FC2, il, ep, ep + 1);   SS_PROF_PHASE(7)
         }
+        long long tp = clock64();
 
         // ---------------- final LN + LM head + per-CTA softmax statistics ----------------
         const uint32_t epL = ep0 + (uint32_t)L;
@@ -809,12 +857,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         }
         if (jrel < n_prompt - 1) {   // prompt token: feed the next one
             consumer_sync();
-            if (tid == 0) { sm.st.token = ctl->prompt[jrel + 1]; sm.st.pos = sm.st.pos + 1; }
+            if (tid == 0) { sm.st.token = ctl->prompt[jrel + 1]; sm.st.pos = sm.st.pos + 1; sm.prof[12] += clock64() - tp; }
             consumer_sync();
             continue;
         }
-        if (!do_sample) { consumer_sync(); if (tid == 0) sm.st.done = 1; consumer_sync(); break; }
+        if (!do_sample) { consumer_sync(); if (tid == 0) { sm.st.done = 1; sm.prof[12] += clock64() - tp; } consumer_sync(); break; }
         sample_and_update(seek, seek_end, n_max, epL);
+        SS_PROF_PHASE(8)
+#undef SS_PROF_PHASE
     }
 
     // ---------------- shutdown: stop the producer, drain copies still in flight, publish the state ----------------
@@ -827,7 +877,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         const DecState st = sm.st;
         if (P.prof) {
             sm.prof[3] = clock64() - t_begin;
-            for (int i = 0; i < 8; i++) P.prof[(size_t)cta * 8 + i] = sm.prof[i];
+            for (int i = 0; i < 24; i++) P.prof[(size_t)cta * 24 + i] = sm.prof[i];
         }
         if (cta == 0) {
             ctl->pos = st.pos; ctl->token = st.token; ctl->n_sampled = st.n_sampled; ctl->has_ts = st.has_ts; ctl->seek_delta = st.seek_delta;

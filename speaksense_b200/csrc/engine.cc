@@ -144,8 +144,8 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     b.d = hp.n_text_state; b.H = hp.n_text_head; b.L = hp.n_text_layer; b.T = hp.n_audio_ctx; b.ctx = hp.n_text_ctx; b.n_vocab = hp.n_vocab;
     b.xsplit = std::max(1, std::min(8, s.mega_grid / b.H));
     b.s4 = powf((float)(b.d / b.H), -0.25f);
-    if (ceil_div(hp.n_vocab, s.mega_grid) > 500 || ceil_div(b.T, b.xsplit) > 500 || b.ctx > 500 || ceil_div(4 * b.d, s.mega_grid) > 250 ||
-        b.H > s.mega_grid || s.mega_grid * 8 > 5120 || (b.d & 127))
+    if (ceil_div(hp.n_vocab, s.mega_grid) > 384 || ceil_div(b.T, b.xsplit) > 322 || b.ctx > 500 || ceil_div(4 * b.d, s.mega_grid) > 250 ||
+        b.H > s.mega_grid || s.mega_grid * 8 > 1280 || (b.d & 127))
         SS_THROW(-3, "device has too few / too many SMs (%d) for the decode kernel's per-CTA work buffers", s.mega_grid);
     b.tok_emb = m.tok_emb; b.d_pos = m.d_pos; b.lnf_w = m.d_ln.w; b.lnf_b = m.d_ln.b;
     for (int i = 0; i < hp.n_text_layer; i++) {
@@ -171,7 +171,7 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     CUDA_CHECK(cudaMemset(b.self_k, 0, kv * 2)); CUDA_CHECK(cudaMemset(b.self_v, 0, kv * 2));
     b.cross_k = s.cross_k; b.cross_v = s.cross_v;
     b.keep = with_keep ? s.keep : nullptr; b.keep_cap = with_keep ? s.keep_cap : 0;
-    b.prof = getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 8) : nullptr;
+    b.prof = getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 24) : nullptr;
     b.eot = v.eot; b.sot = v.sot; b.translate = v.translate; b.transcribe = v.transcribe; b.solm = v.solm; b.prev = v.prev;
     b.nosp = v.nosp; b.not_ = v.not_; b.beg = v.beg; b.blank = v.blank;
     b.suppress_blank = 1; b.tdrz = 0; b.tid0_init = -1;
@@ -395,12 +395,14 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     float total = 0.f; CUDA_CHECK(cudaEventElapsedTime(&total, s.ev[2], s.ev[3]));
     s.n_launches += 1;
     if (d.mp.prof) {
-        std::vector<long long> h((size_t)s.mega_grid * 8);
+        std::vector<long long> h((size_t)s.mega_grid * 24);
         CUDA_CHECK(cudaMemcpy(h.data(), d.mp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
-        const char *names[4] = {"poll (flag wait)", "gemv (xr + rows)", "gemv xr load", "total"};
-        for (int k = 0; k < 4; k++) {
+        const char *names[23] = {"poll (flag wait)", "gemv (xr + rows)", "gemv xr load", "total", "phase QKV", "phase self-attn", "phase O", "phase CQ",
+                                 "phase cross-attn", "phase CO", "phase FC1", "phase FC2", "phase LM+sample", "gemv wait ring full", "cross K wait ring full", "-",
+                                 "FC1 poll", "FC1 LN stats", "FC1 normalise", "FC1 B frags", "FC1 tiles", "FC1 barrier", "FC1 fold+epilogue"};
+        for (int k = 0; k < 23; k++) {
             long long mn = h[k], mx = h[k]; double sum = 0;
-            for (int c = 0; c < s.mega_grid; c++) { long long v = h[(size_t)c * 8 + k]; mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)v; }
+            for (int c = 0; c < s.mega_grid; c++) { long long v = h[(size_t)c * 24 + k]; mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)v; }
             fprintf(stderr, "[mega prof] %-20s cycles/step: min %.0f mean %.0f max %.0f\n", names[k], (double)mn / n_steps, sum / s.mega_grid / n_steps, (double)mx / n_steps);
         }
     }
