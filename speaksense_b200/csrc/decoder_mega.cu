@@ -34,17 +34,16 @@ namespace {
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kMegaThreads = kConsumerThreads + 32;
-constexpr int kChunkRows = 16;        // weight rows (of d halfs) per ring chunk = one m16 MMA tile
-constexpr int kRowPad = 16;           // bytes of padding between rows in a slot: ldmatrix of 8 rows hits 8 different bank groups
+constexpr int kChunkRows = 16;        // weight rows (of d halfs) per ring chunk: one row pair (= one m16 MMA tile) per consumer warp
 constexpr int kSlots = 4;
-constexpr int kChunkBytes = kChunkRows * (1280 * 2 + kRowPad);   // 41216
+constexpr int kChunkBytes = kChunkRows * 1280 * 2;   // 40960
 constexpr int kMaxXs = 5120;          // largest mat-vec input (4 * d, d <= 1280)
-constexpr int kMaxRowsPerCta = 512;   // per phase
-constexpr int kMaxTiles = 24;         // chunks per phase (LM head: n_vocab / grid / 16)
+constexpr int kMaxRowsPerCta = 512;   // per phase (LM head: n_vocab / grid)
 constexpr int kMaxScores = 512;
-constexpr int kMaxJ = 5;              // d / 8 / 32 uint4 chunks per lane, d <= 1280
-constexpr int kMaxKSteps = 10;        // k16 steps per warp: d / 8 warps / 16, d <= 1280
+constexpr int kMaxJ = 5;              // flagged pairs per thread and poll batch
+constexpr int kPre = 3;               // chunks per phase whose bias / residual operands are prefetched into registers
 typedef unsigned long long u64;
+constexpr int kProfN = 96;
 
 enum SegKind : int { SEG_QKV = 0, SEG_O, SEG_CQ, SEG_XK, SEG_XV, SEG_CO, SEG_FC1, SEG_FC2, SEG_LM, SEG_COUNT };
 
@@ -52,20 +51,19 @@ struct DecState {   // replicated per CTA (thread-uniform, lives in shared memor
     int pos, token, n_sampled, has_ts, seek_delta, result_len, last_id, penult_id, n_kept, failed, completed, done;
 };
 struct SegTab { int row0, rows, row_bytes, rows_per_chunk, n_chunks, prows; };   // prows: rows of d halfs (FC2: 4 per output row)
+struct RowPre { float b0, b1, b2, r0, r1, r2; };   // bias / residual of the rows a finishing lane publishes in chunks 0..2
 
 struct __align__(128) MegaSmem {
     uint8_t ring[kSlots][kChunkBytes];
-    float xs[1280];                 // raw f32 input vector of a LayerNorm phase (also: cross-attn partials, sampling records)
-    alignas(16) __half xh[kMaxXs];  // the mat-vec operand: f16, after LayerNorm where the phase has one
-    alignas(16) float part[kMaxTiles][kConsumerWarps][16];   // per-warp K-slice partial sums of every tile of the phase
-    float lnw[1280], lnb[1280];     // LayerNorm affine of the current phase (cp.async, overlapped with the poll)
-    float bias[kMaxRowsPerCta];     // bias slice of this CTA's rows for the current phase
-    float xown[256];                // this CTA's rows of the residual stream (stashed when the stream is polled)
+    alignas(16) __half xin[2][kMaxXs];   // the f16 mat-vec operand (after LayerNorm where the phase has one), double-buffered by phase parity
+    float xs[1280];                 // scratch of the attention / sampling phases (partials, per-CTA records)
     alignas(16) MegaParams P;       // descriptor copy: no pointer chasing through L2 on the critical path
-    alignas(16) float acc[kMaxRowsPerCta];
+    alignas(16) float acc[kMaxRowsPerCta];      // LM-head rows of this CTA
+    alignas(16) float p4[256];                  // FC2: the four quarter-row partial sums of every output row
     alignas(16) float sc[kMaxScores];
     alignas(16) float red[kConsumerWarps][64];
     alignas(16) float red1[32];
+    alignas(16) float2 red2[kConsumerWarps];    // LayerNorm {sum, sum of squares} per warp
     alignas(16) float qkv[192];                 // q / current k / current v of this CTA's head
     int redi[32];
     alignas(16) uint64_t full[kSlots];
@@ -75,7 +73,7 @@ struct __align__(128) MegaSmem {
     volatile int stop_req;      // consumers -> producer: stop issuing
     volatile int prod_done;     // producer -> consumers: `issued` is final
     volatile uint32_t issued;
-    long long prof[24];         // thread-0 cycle counters: poll, gemv rows, x load, total, then one per phase kind
+    long long prof[kProfN];     // thread-0 cycle counters: [0..23] totals / per phase kind, [24 + kind * 8 + stage] per-stage breakdown
 };
 
 extern __shared__ __align__(128) uint8_t mega_smem_raw[];
@@ -162,7 +160,8 @@ template <bool TO_HALF>
 __device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, void *dst) {
     const int n2 = n >> 1, tid = threadIdx.x;
     float s = 0.f, s2 = 0.f;
-    const long long t0 = clock64();
+    const bool prof_on = SM.P.prof != nullptr && tid == 0;
+    const long long t0 = prof_on ? clock64() : 0;
     for (int base = 0; base < n2; base += kConsumerThreads * kMaxJ) {
         ulonglong2 v[kMaxJ];
         bool all;
@@ -186,20 +185,8 @@ __device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, v
             }
         }
     }
-    if (tid == 0) SM.prof[0] += clock64() - t0;
+    if (prof_on) SM.prof[0] += clock64() - t0;
     return make_float2(s, s2);
-}
-
-// static (weight-side) small operands of a mat-vec phase, fetched with cp.async while the input is polled
-__device__ __forceinline__ void prefetch_ln(const float *lw, const float *lb, int d) {
-    MegaSmem &sm = SM;
-    if (lw) for (int i = threadIdx.x; i < (d >> 2); i += kConsumerThreads) { cp_async16(&sm.lnw[4 * i], lw + 4 * i); cp_async16(&sm.lnb[4 * i], lb + 4 * i); }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void prefetch_bias(const float *bias, int row0, int rows) {
-    MegaSmem &sm = SM;
-    if (bias) for (int R = threadIdx.x; R < rows; R += kConsumerThreads) cp_async4(&sm.bias[R], bias + row0 + R);
-    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // block-wide (256 consumer threads) reductions; result broadcast
@@ -237,55 +224,77 @@ __device__ __forceinline__ float consumer_max(float v) {
     return t;
 }
 
-// token embedding + positional embedding -> sm.xs; returns the thread's {sum, sumsq}
-__device__ __noinline__ float2 embed_xs() {
-    MegaSmem &sm = SM;
-    const MegaParams &P = sm.P;
-    const int d = P.d, tid = threadIdx.x;
-    const __half *e = P.tok_emb + (size_t)sm.st.token * d;
-    const float *pe = P.d_pos + (size_t)sm.st.pos * d;
-    float v[kMaxJ];
-#pragma unroll
-    for (int j = 0; j < kMaxJ; j++) { const int i = tid + j * kConsumerThreads; v[j] = i < d ? __half2float(__ldg(e + i)) + __ldg(pe + i) : 0.f; }
-    float s = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < kMaxJ; j++) { const int i = tid + j * kConsumerThreads; if (i < d) { sm.xs[i] = v[j]; s += v[j]; s2 += v[j] * v[j]; } }
-    return make_float2(s, s2);
+__device__ __forceinline__ float ll_value(const u64 *p) {      // a flagged word this CTA has already seen valid
+    u64 w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return __uint_as_float((uint32_t)w);
 }
 
-// The tensor-core part of a mat-vec phase.  Every warp owns one eighth of K for ALL rows of the CTA's slice, so its B
-// fragments (the x side of mma.m16n8k16) stay in registers for the whole phase; the A fragments come out of the ring
-// with ldmatrix (rows are kRowPad bytes off bank alignment).  Column n of B carries x quarter n & 3: FC2 views its
-// 4d-long rows as 4 rows of d, output row r = sum over q of C[4r + q][q]; for the other matrices all columns equal x.
-// Per tile, the lanes holding the wanted column leave their 16 row sums in sm.part[tile][warp].
+// index, inside the CTA's slice, of the row (FC2: quarter row) that finishing lane `l01` of `warp` publishes in chunk `ch`.
+// FC2: warp w works on quarter w & 3 of the rows {2 * (w >> 2), 2 * (w >> 2) + 1} of every 4-row chunk.
+__device__ __forceinline__ int tile_row(int kind, int ch, int warp, int l01) {
+    return kind == SEG_FC2 ? kChunkRows * ch + 4 * (2 * (warp >> 2) + l01) + (warp & 3) : kChunkRows * ch + 2 * warp + l01;
+}
+
+// what a finishing lane does with one finished row
+__device__ __forceinline__ void row_epilogue(int kind, int il, int R, float val, float bias, float res, uint32_t ep_out) {
+    MegaSmem &sm = SM;
+    const MegaParams &P = sm.P;
+    const int row = sm.seg[kind].row0 + R, d = P.d;
+    if (kind == SEG_FC2) { sm.p4[R] = val; return; }
+    if (kind == SEG_LM) { sm.acc[R] = val; return; }
+    const float v = val + bias;
+    if (kind == SEG_QKV) {
+        const int pos = sm.st.pos;
+        if (row < d) ll_store(P.q1 + row, r16(v * P.s4), ep_out);
+        else if (row < 2 * d) {
+            const int n = row - d; const __half hk = __float2half_rn(v * P.s4);
+            (P.self_k + (size_t)il * P.ctx * d)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
+        } else {
+            const int n = row - 2 * d; const __half hv = __float2half_rn(v);
+            (P.self_v + (size_t)il * P.ctx * d)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
+        }
+    } else if (kind == SEG_O) ll_store(P.xB + row, res + v, ep_out);
+    else if (kind == SEG_CO) ll_store(P.xC + row, res + v, ep_out);
+    else if (kind == SEG_CQ) ll_store(P.q2 + row, r16(v * P.s4), ep_out);
+    else ll_store(P.hbuf + row, gelu16(v), ep_out);
+}
+
+// The tensor-core part of a mat-vec phase.  A chunk of the ring holds 16 weight rows (of d halfs); consumer warp w owns
+// rows 2w, 2w+1 of every chunk and needs nobody else: a row is viewed as 8 interleaved K slices, so that one m16n8k16
+// tile = {2 rows} x {8 slices} and column n of the B operand carries the x values of slice n - the wanted products are
+// the diagonal C[8 * row + slice][slice].  Per k-step (128 halfs = 256 B of a row) ldmatrix reads two contiguous 128-byte
+// segments per row (conflict-free, no padding) and the warp's B fragments are 128 consecutive x values (2 per lane, twice),
+// held in registers for the whole phase.  No cross-warp reduction, no CTA barrier: the two finishing lanes of the warp
+// run the epilogue and publish the rows themselves.
 template <int KS>
-__device__ __noinline__ uint32_t gemv_tiles(uint32_t cons, int n_chunks, int row_bytes, int kq, int d) {
+__device__ __noinline__ uint32_t gemv_tiles(uint32_t cons, int kind, int il, uint32_t ep_out, const __half *xq, RowPre pre) {
     MegaSmem &sm = SM;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kwarp = warp * (d >> 3);
-    const int qsel = kq == 4 ? ((lane >> 2) & 3) : 0;
-    const bool owner = (lane & 3) == (qsel >> 1);
+    const SegTab seg = sm.seg[kind];
     uint32_t bf[2 * KS];
-    {
-        const __half *xq = sm.xh + qsel * d + kwarp + 2 * (lane & 3);
 #pragma unroll
-        for (int j = 0; j < KS; j++) {
-            bf[2 * j] = *reinterpret_cast<const uint32_t *>(xq + 16 * j);
-            bf[2 * j + 1] = *reinterpret_cast<const uint32_t *>(xq + 16 * j + 8);
-        }
+    for (int j = 0; j < KS; j++) {
+        bf[2 * j] = *reinterpret_cast<const uint32_t *>(xq + 128 * j + 2 * lane);
+        bf[2 * j + 1] = *reinterpret_cast<const uint32_t *>(xq + 128 * j + 64 + 2 * lane);
     }
-    const uint32_t pitch = (uint32_t)row_bytes + kRowPad;
-    const uint32_t a_off = (uint32_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * pitch + (uint32_t)(kwarp + 8 * (lane >> 4)) * 2;
-    for (int ch = 0; ch < n_chunks; ch++) {
+    // ldmatrix.x4 row addresses: lanes 8m..8m+7 feed matrix m = (row of the pair: m & 1, k half: m >> 1), slice = lane & 7
+    const int mi = lane >> 3;
+    const uint32_t a_off = (uint32_t)tile_row(kind, 0, warp, mi & 1) * (uint32_t)seg.row_bytes + 128u * (uint32_t)(mi >> 1) + 16u * (uint32_t)(lane & 7);
+    const int g = lane >> 2;
+    const bool diag = (lane & 3) == (g >> 1);
+    const bool prof_on = sm.P.prof != nullptr && tid == 0;
+    for (int ch = 0; ch < seg.n_chunks; ch++) {
         const int slot = cons % kSlots;
-        mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
+        if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[13] += clock64() - tw0; }
+        else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const uint32_t abase = smem_u32(sm.ring[slot]) + a_off;
         uint32_t af[KS][4];
 #pragma unroll
         for (int j = 0; j < KS; j++)
             asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 32u * j));
-        constexpr int NA = KS >= 4 ? 4 : KS;     // independent accumulator sets
+                         : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 256u * j));
+        constexpr int NA = KS >= 2 ? 2 : 1;     // independent accumulator sets
         float cc[NA][4];
 #pragma unroll
         for (int i = 0; i < NA; i++) { cc[i][0] = 0.f; cc[i][1] = 0.f; cc[i][2] = 0.f; cc[i][3] = 0.f; }
@@ -294,109 +303,157 @@ __device__ __noinline__ uint32_t gemv_tiles(uint32_t cons, int n_chunks, int row
             asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                          : "+f"(cc[j % NA][0]), "+f"(cc[j % NA][1]), "+f"(cc[j % NA][2]), "+f"(cc[j % NA][3])
                          : "r"(af[j][0]), "r"(af[j][1]), "r"(af[j][2]), "r"(af[j][3]), "r"(bf[2 * j]), "r"(bf[2 * j + 1]));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[slot]);      // every ldmatrix of this warp has been consumed by an issued mma
+        cons++;
 #pragma unroll
         for (int i = 1; i < NA; i++) { cc[0][0] += cc[i][0]; cc[0][1] += cc[i][1]; cc[0][2] += cc[i][2]; cc[0][3] += cc[i][3]; }
-        if (owner) {
-            float *pp = &sm.part[ch][warp][lane >> 2];
-            pp[0] = (qsel & 1) ? cc[0][1] : cc[0][0];
-            pp[8] = (qsel & 1) ? cc[0][3] : cc[0][2];
+        float v0 = diag ? ((g & 1) ? cc[0][1] : cc[0][0]) : 0.f;      // row 2w   : sum over its 8 slices
+        float v1 = diag ? ((g & 1) ? cc[0][3] : cc[0][2]) : 0.f;      // row 2w+1
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+        if (lane < 2) {
+            const int R = tile_row(kind, ch, warp, lane);
+            if (R < seg.prows) {
+                float b = 0.f, r = 0.f;
+                if (kind != SEG_FC2 && kind != SEG_LM) {
+                    if (ch == 0) { b = pre.b0; r = pre.r0; } else if (ch == 1) { b = pre.b1; r = pre.r1; } else if (ch == 2) { b = pre.b2; r = pre.r2; }
+                    else {      // more chunks per phase than prefetch registers (fewer SMs than the design point)
+                        const MegaParams &P = sm.P;
+                        const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : 4;
+                        b = __ldg(P.layer[il].b[widx] + seg.row0 + R);
+                        if (kind == SEG_O) r = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)sm.st.token * P.d + seg.row0 + R)) + __ldg(P.d_pos + (size_t)sm.st.pos * P.d + seg.row0 + R)
+                                                       : ll_value(P.xA + seg.row0 + R);
+                        else if (kind == SEG_CO) r = ll_value(P.xB + seg.row0 + R);
+                    }
+                }
+                row_epilogue(kind, il, R, lane ? v1 : v0, b, r, ep_out);
+            }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[slot]);
-        cons++;
     }
     return cons;
 }
 
-// One mat-vec phase, start to finish: prefetch static operands, poll the input vector, (LayerNorm), rows
-// of this CTA's slice straight out of the ring, epilogue, flagged stores of the outputs.
+// One mat-vec phase, start to finish: poll the input vector (every thread a few flagged pairs), LayerNorm where the
+// phase has one (statistics: one shuffle reduction + one CTA barrier; every thread normalises the values it polled),
+// f16 operand to shared memory, one CTA barrier, then the warps run gemv_tiles independently.
 //   kind  : SEG_QKV / SEG_O / SEG_CQ / SEG_CO / SEG_FC1 / SEG_FC2 / SEG_LM
-//   ep_in : epoch the input carries; outputs are published with ep_out
-__device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uint32_t ep_in, uint32_t ep_out) {
+//   ep_in : epoch the input carries; outputs are published with ep_out;  ph: running phase count (operand buffer parity)
+__device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uint32_t ep_in, uint32_t ep_out, uint32_t ph) {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int d = P.d;
     const SegTab seg = sm.seg[kind];
     const bool has_ln = kind == SEG_QKV || kind == SEG_CQ || kind == SEG_FC1 || kind == SEG_LM;
-    const int kq = kind == SEG_FC2 ? 4 : 1;
     const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : kind == SEG_FC1 ? 4 : 5;
     const int lidx = kind == SEG_QKV ? 0 : kind == SEG_CQ ? 1 : 2;
-    const SegTab own = sm.seg[SEG_O];          // partition of the d residual rows
-    // ---- static operands: LayerNorm affine now (lands while the input is polled); the bias slice after the
-    //      first CTA barrier of this phase (the previous phase's epilogue may still be reading sm.bias)
-    if (kind == SEG_LM) prefetch_ln(P.lnf_w, P.lnf_b, d);
-    else prefetch_ln(has_ln ? P.layer[il].lnw[lidx] : nullptr, has_ln ? P.layer[il].lnb[lidx] : nullptr, d);
-    // ---- input vector
-    float2 ss = make_float2(0.f, 0.f);
-    if (kind == SEG_QKV && il == 0) ss = embed_xs();
-    else {
-        const u64 *src = kind == SEG_QKV || kind == SEG_LM ? P.xA : kind == SEG_O ? P.att1 : kind == SEG_CQ ? P.xB : kind == SEG_CO ? P.att2
-                         : kind == SEG_FC1 ? P.xC : P.hbuf;
-        if (has_ln) ss = poll_vec<false>(src, d, ep_in, sm.xs);
-        else poll_vec<true>(src, kq * d, ep_in, sm.xh);
-    }
-    float mean = 0.f, rstd = 1.f;
-    if (has_ln) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");     // LayerNorm affine (issued before the poll) has landed
-        const float2 t = consumer_sum2(ss);     // its barriers also publish sm.xs / lnw / lnb to every consumer thread
-        mean = t.x / d;
-        rstd = rsqrtf(fmaxf(t.y / d - mean * mean, 0.f) + 1e-5f);
-        if (kind != SEG_LM && tid < own.rows) sm.xown[tid] = sm.xs[own.row0 + tid];
-    } else consumer_sync();
-    // bias slice only now: before the barrier above the previous phase's epilogue may still have been reading sm.bias
-    prefetch_bias(kind == SEG_LM ? nullptr : P.layer[il].b[widx], seg.row0, seg.rows);
-    const long long tg0 = clock64();
-    if (has_ln) {   // normalise once, cooperatively (ggml_norm + affine), rounded to f16 for the mat-vec
-        for (int i = tid; i < d; i += kConsumerThreads) sm.xh[i] = __float2half_rn((sm.xs[i] - mean) * rstd * sm.lnw[i] + sm.lnb[i]);
-        consumer_sync();
-    }
-    // ---- the tiles of this CTA's slice out of the ring (K-steps per warp known at compile time: registers, not local memory)
-    switch (d >> 7) {      // host side guarantees d % 128 == 0 and d <= 1280
-#define SS_KS(n) case n: cons = gemv_tiles<n>(cons, seg.n_chunks, seg.row_bytes, kq, d); break;
-        SS_KS(1) SS_KS(2) SS_KS(3) SS_KS(4) SS_KS(5) SS_KS(6) SS_KS(7) SS_KS(8) SS_KS(9)
-#undef SS_KS
-        default: cons = gemv_tiles<10>(cons, seg.n_chunks, seg.row_bytes, kq, d); break;
-    }
-    if (tid == 0) sm.prof[1] += clock64() - tg0;
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    consumer_sync();
-    // ---- fold the eight K-slices (and FC2's four quarters) of every output row
-    for (int R = tid; R < seg.rows; R += kConsumerThreads) {
-        float a = 0.f;
-        for (int q = 0; q < kq; q++) {
-            const int pr = R * kq + q;
-            const float *pp = &sm.part[pr / kChunkRows][0][pr % kChunkRows];
+    __half *buf = sm.xin[ph & 1];
+    const bool prof_on = P.prof != nullptr && tid == 0;
+    long long tq = prof_on ? clock64() : 0;
+#define SS_STAGE(k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + kind * 8 + (k)] += tn - tq; tq = tn; }
+    // ---- static / already-valid operands of the epilogue, fetched now so that their L2 latency hides behind the poll
+    RowPre pre = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float fb = 0.f, fr = 0.f;      // FC2: bias and residual of output row `tid` (folded after the tiles)
+    const int tok = sm.st.token, pos = sm.st.pos;
+    if (kind == SEG_FC2) {
+        if (tid < seg.rows) { fb = __ldg(P.layer[il].b[5] + seg.row0 + tid); fr = ll_value(P.xC + seg.row0 + tid); }
+    } else if (kind != SEG_LM && lane < 2) {
+        const float *bias = P.layer[il].b[widx];
+        float bb[kPre], rr[kPre];
 #pragma unroll
-            for (int w = 0; w < kConsumerWarps; w++) a += pp[w * 16];
-        }
-        sm.acc[R] = a;
-    }
-    if (kind == SEG_LM) { consumer_sync(); return cons; }   // lm_epilogue reads other threads' rows
-    // ---- epilogue
-    if (kind == SEG_QKV) {
-        const int pos = sm.st.pos;
-        __half *sk = P.self_k + (size_t)il * P.ctx * d, *sv = P.self_v + (size_t)il * P.ctx * d;
-        for (int R = tid; R < seg.rows; R += kConsumerThreads) {
-            const int row = seg.row0 + R;
-            const float v = sm.acc[R] + sm.bias[R];
-            if (row < d) ll_store(P.q1 + row, r16(v * P.s4), ep_out);
-            else if (row < 2 * d) {
-                const int n = row - d; const __half hk = __float2half_rn(v * P.s4);
-                sk[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
-            } else {
-                const int n = row - 2 * d; const __half hv = __float2half_rn(v);
-                sv[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
+        for (int c = 0; c < kPre; c++) {
+            const int R = tile_row(kind, c, warp, lane);
+            bb[c] = 0.f; rr[c] = 0.f;
+            if (R < seg.rows) {
+                const int row = seg.row0 + R;
+                bb[c] = __ldg(bias + row);
+                if (kind == SEG_O) rr[c] = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * d + row)) + __ldg(P.d_pos + (size_t)pos * d + row) : ll_value(P.xA + row);
+                else if (kind == SEG_CO) rr[c] = ll_value(P.xB + row);
             }
         }
-    } else if (kind != SEG_LM && tid < seg.rows) {
-        const int row = seg.row0 + tid;
-        if (kind == SEG_FC2) ll_store(P.xA + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
-        else if (kind == SEG_O) ll_store(P.xB + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
-        else if (kind == SEG_CO) ll_store(P.xC + row, sm.xown[tid] + sm.acc[tid] + sm.bias[tid], ep_out);
-        else if (kind == SEG_CQ) ll_store(P.q2 + row, r16((sm.acc[tid] + sm.bias[tid]) * P.s4), ep_out);
-        else ll_store(P.hbuf + row, gelu16(sm.acc[tid] + sm.bias[tid]), ep_out);
+        pre.b0 = bb[0]; pre.b1 = bb[1]; pre.b2 = bb[2]; pre.r0 = rr[0]; pre.r1 = rr[1]; pre.r2 = rr[2];
     }
+    // ---- input vector -> f16 operand in shared memory
+    if (has_ln) {
+        const int n2 = d >> 1;                      // pairs; host side guarantees d <= 1280: at most 3 per thread
+        const float *lw = kind == SEG_LM ? P.lnf_w : P.layer[il].lnw[lidx], *lb = kind == SEG_LM ? P.lnf_b : P.layer[il].lnb[lidx];
+        float2 w2[3], b2[3], xv[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i = tid + k * kConsumerThreads;
+            if (i < n2) { w2[k] = __ldg(reinterpret_cast<const float2 *>(lw) + i); b2[k] = __ldg(reinterpret_cast<const float2 *>(lb) + i); }
+        }
+        if (kind == SEG_QKV && il == 0) {           // token embedding + positional embedding
+            const __half2 *e = reinterpret_cast<const __half2 *>(P.tok_emb + (size_t)tok * d);
+            const float2 *pe = reinterpret_cast<const float2 *>(P.d_pos + (size_t)pos * d);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int i = tid + k * kConsumerThreads;
+                if (i < n2) { const float2 ev = __half22float2(__ldg(e + i)), pv = __ldg(pe + i); xv[k] = make_float2(ev.x + pv.x, ev.y + pv.y); }
+            }
+        } else {
+            const u64 *src = kind == SEG_QKV || kind == SEG_LM ? P.xA : kind == SEG_CQ ? P.xB : P.xC;
+            const long long t0 = prof_on ? clock64() : 0;
+            ulonglong2 v[3];
+            bool all;
+            do {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const int i = tid + k * kConsumerThreads; if (i < n2) v[k] = ll_load2(src + 2 * i); }
+                all = true;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int i = tid + k * kConsumerThreads;
+                    if (i < n2 && ((uint32_t)(v[k].x >> 32) != ep_in || (uint32_t)(v[k].y >> 32) != ep_in)) all = false;
+                }
+            } while (!all);
+#pragma unroll
+            for (int k = 0; k < 3; k++) xv[k] = make_float2(__uint_as_float((uint32_t)v[k].x), __uint_as_float((uint32_t)v[k].y));
+            if (prof_on) sm.prof[0] += clock64() - t0;
+        }
+        SS_STAGE(0)
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const int i = tid + k * kConsumerThreads; if (i < n2) { s1 += xv[k].x + xv[k].y; s2 += xv[k].x * xv[k].x + xv[k].y * xv[k].y; } }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0) sm.red2[warp] = make_float2(s1, s2);
+        consumer_sync();
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; w++) { const float2 t = sm.red2[w]; t1 += t.x; t2 += t.y; }
+        const float mean = t1 / d, rstd = rsqrtf(fmaxf(t2 / d - mean * mean, 0.f) + 1e-5f);
+        SS_STAGE(1)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i = tid + k * kConsumerThreads;
+            if (i < n2) reinterpret_cast<__half2 *>(buf)[i] = __floats2half2_rn((xv[k].x - mean) * rstd * w2[k].x + b2[k].x, (xv[k].y - mean) * rstd * w2[k].y + b2[k].y);
+        }
+    } else {
+        const u64 *src = kind == SEG_O ? P.att1 : kind == SEG_CO ? P.att2 : P.hbuf;
+        poll_vec<true>(src, kind == SEG_FC2 ? 4 * d : d, ep_in, buf);
+        SS_STAGE(0)
+    }
+    consumer_sync();
+    SS_STAGE(2)
+    // ---- the tiles of this CTA's slice out of the ring (k-steps known at compile time: fragments in registers)
+    const __half *xq = buf + (kind == SEG_FC2 ? (warp & 3) * d : 0);
+    switch (d >> 7) {      // host side guarantees d % 128 == 0 and d <= 1280
+#define SS_KS(n) case n: cons = gemv_tiles<n>(cons, kind, il, ep_out, xq, pre); break;
+        SS_KS(1) SS_KS(2) SS_KS(3) SS_KS(4) SS_KS(5) SS_KS(6) SS_KS(7) SS_KS(8) SS_KS(9)
+#undef SS_KS
+        default: cons = gemv_tiles<10>(cons, kind, il, ep_out, xq, pre); break;
+    }
+    if (prof_on) sm.prof[1] += clock64() - tq;
+    SS_STAGE(3)
+    if (kind == SEG_FC2) {      // fold the four quarters of every output row
+        consumer_sync();
+        if (tid < seg.rows) {
+            const float4 q = *reinterpret_cast<const float4 *>(&sm.p4[4 * tid]);
+            ll_store(P.xA + seg.row0 + tid, fr + (((q.x + q.y) + q.z) + q.w) + fb, ep_out);
+        }
+        SS_STAGE(4)
+    } else if (kind == SEG_LM) consumer_sync();     // lm_epilogue reads other warps' rows
+#undef SS_STAGE
     return cons;
 }
 
@@ -469,6 +526,8 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
     const int h = blockIdx.x, tid = threadIdx.x;
     if (h >= P.H) return;
     const int n_past = sm.st.pos, d = P.d, l8 = tid & 7;
+    long long tq = clock64();
+#define SS_STAGE(kd, k) { const long long tn = clock64(); if (tid == 0) sm.prof[24 + (kd) * 8 + (k)] += tn - tq; tq = tn; }
     if (tid < 96) {   // 3 x 64 flagged floats: q, k, v of this head
         const int which = tid >> 5, i2 = tid & 31;
         const u64 *src = (which == 0 ? P.q1 : which == 1 ? P.kcur : P.vcur) + h * 64 + 2 * i2;
@@ -477,6 +536,7 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
         sm.qkv[which * 64 + 2 * i2] = __uint_as_float((uint32_t)v.x); sm.qkv[which * 64 + 2 * i2 + 1] = __uint_as_float((uint32_t)v.y);
     }
     consumer_sync();
+    SS_STAGE(SEG_XV, 0)
     const uint8_t *Kh = reinterpret_cast<const uint8_t *>(P.self_k + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
     const uint8_t *Vh = reinterpret_cast<const uint8_t *>(P.self_v + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
     const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
@@ -487,14 +547,18 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
         if (tid == 0) sm.sc[n_past] = ds;
         lmax = fmaxf(lmax, ds);
     }
+    SS_STAGE(SEG_XV, 1)
     const float m = consumer_max(lmax);
     float lsum = 0.f;
     for (int j = tid; j <= n_past; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; lsum += e; }
     const float l = consumer_sum(lsum);
+    SS_STAGE(SEG_XV, 2)
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     attn_pv<false>(Vh, n_past, 0, acc);
+    SS_STAGE(SEG_XV, 3)
     float o = attn_fold(acc);
     if (tid < 64) { o += sm.sc[n_past] * sm.qkv[128 + tid]; ll_store(P.att1 + h * 64 + tid, r16(o / l), ep); }
+    SS_STAGE(SEG_XV, 4)
 }
 
 // cross-attention; K then V of this CTA's (head, key split) streamed through the ring; split 0 of every head
@@ -506,6 +570,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     if (sk.n_chunks == 0) return cons;
     const int tid = threadIdx.x, lane = tid & 31, l8 = tid & 7;
     const int ns = P.xsplit, h = blockIdx.x / ns, sp = blockIdx.x % ns, n = sk.rows;
+    long long tq = clock64();
     if (tid < 32) {
         const u64 *src = P.q2 + h * 64 + 2 * tid;
         ulonglong2 v;
@@ -513,6 +578,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
         sm.qkv[2 * tid] = __uint_as_float((uint32_t)v.x); sm.qkv[2 * tid + 1] = __uint_as_float((uint32_t)v.y);
     }
     consumer_sync();
+    SS_STAGE(SEG_XK, 0)
     const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
     float lmax = -INFINITY;
     for (int ch = 0; ch < sk.n_chunks; ch++) {
@@ -524,10 +590,12 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
     }
+    SS_STAGE(SEG_XK, 1)
     const float m = consumer_max(lmax);
     float lsum = 0.f;
     for (int j = tid; j < n; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; lsum += e; }
     const float l = consumer_sum(lsum);
+    SS_STAGE(SEG_XK, 2)
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int ch = 0; ch < sk.n_chunks; ch++) {     // the V slice has the same chunking as the K slice
         const int slot = cons % kSlots;
@@ -538,10 +606,12 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
     }
+    SS_STAGE(SEG_XK, 3)
     const float o = attn_fold(acc);
     u64 *out = P.part + ((size_t)h * ns + sp) * 66;
     if (tid < 64) ll_store(out + 2 + tid, o, ep);
     if (tid == 0) { ll_store(out, m, ep); ll_store(out + 1, l, ep); }
+    SS_STAGE(SEG_XK, 4)
     if (sp != 0) return cons;
     // ---- split 0 folds all ns (<= 8) partial records of head h
     poll_vec<false>(P.part + (size_t)h * ns * 66, ns * 66, ep, sm.xs);
@@ -557,6 +627,8 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
         ll_store(P.att2 + h * 64 + tid, r16(oo / Lsum), ep);
     }
     consumer_sync();
+    SS_STAGE(SEG_XK, 5)
+#undef SS_STAGE
     return cons;
 }
 
@@ -756,7 +828,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     if (tid == 0) {
         for (int s = 0; s < kSlots; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
         sm.stop_req = 0; sm.prod_done = 0; sm.issued = 0;
-        for (int i = 0; i < 24; i++) sm.prof[i] = 0;
+        for (int i = 0; i < kProfN; i++) sm.prof[i] = 0;
         DecState st;
         st.pos = pos_start; st.token = ctl->token; st.n_sampled = ctl->n_sampled; st.has_ts = ctl->has_ts; st.seek_delta = ctl->seek_delta;
         st.result_len = ctl->result_len; st.last_id = ctl->last_id; st.penult_id = ctl->penult_id; st.n_kept = ctl->n_kept;
@@ -769,8 +841,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 
     if (warp == kConsumerWarps) {
         // ======================= producer =======================
-        // Lane 0 tracks the ring; weight chunks go out as one bulk copy per row (lane r copies row r) so that rows land
-        // kRowPad bytes apart, cross-attention K/V chunks as one contiguous copy.
+        // Lane 0 tracks the ring and issues one bulk copy per chunk (16 weight rows, or a K / V slice of the cross-attention cache).
         uint64_t policy;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         uint32_t issued = 0;
@@ -783,7 +854,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
                 const int layer = si / SEG_LM, kind = si < L * SEG_LM ? si % SEG_LM : SEG_LM;
                 const SegTab seg = sm.seg[kind];
                 const uint8_t *base = seg_base(P, seg, kind, layer < L ? layer : 0);
-                const bool padded = !(kind == SEG_XK || kind == SEG_XV);
                 for (int ch = 0; ch < seg.n_chunks; ch++) {
                     const int slot = issued % kSlots;
                     const uint32_t par = ((issued / kSlots) & 1) ^ 1;
@@ -797,13 +867,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
                     stopped = __shfl_sync(0xffffffffu, (int)stopped, 0) != 0;
                     __syncwarp();
                     if (stopped) break;
-                    if (padded) {
-                        if (lane < nrows)
-                            bulk_g2s(sm.ring[slot] + (size_t)lane * (seg.row_bytes + kRowPad), base + (size_t)(rbase + lane) * seg.row_bytes,
-                                     (uint32_t)seg.row_bytes, &sm.full[slot], policy);
-                    } else if (lane == 0) {
-                        bulk_g2s(sm.ring[slot], base + (size_t)rbase * seg.row_bytes, (uint32_t)nrows * seg.row_bytes, &sm.full[slot], policy);
-                    }
+                    if (lane == 0) bulk_g2s(sm.ring[slot], base + (size_t)rbase * seg.row_bytes, (uint32_t)nrows * seg.row_bytes, &sm.full[slot], policy);
                     issued++;
                 }
             }
@@ -818,7 +882,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     }
 
     // ======================= consumers =======================
-    uint32_t cons = 0;
+    uint32_t cons = 0, ph = 0;
     const long long t_begin = clock64();
     const uint32_t ep_stride = (uint32_t)L + 1;
 
@@ -833,14 +897,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
             const uint32_t ep = ep0 + (uint32_t)il;
             long long tp = clock64();
 #define SS_PROF_PHASE(k) { const long long tn = clock64(); if (tid == 0) sm.prof[4 + (k)] += tn - tp; tp = tn; }
-            cons = gemv_phase(cons, SEG_QKV, il, ep, ep);       SS_PROF_PHASE(0)
+            cons = gemv_phase(cons, SEG_QKV, il, ep, ep, ph++);       SS_PROF_PHASE(0)
             self_attn(il, ep);                                  SS_PROF_PHASE(1)
-            cons = gemv_phase(cons, SEG_O, il, ep, ep);         SS_PROF_PHASE(2)
-            cons = gemv_phase(cons, SEG_CQ, il, ep, ep);        SS_PROF_PHASE(3)
+            cons = gemv_phase(cons, SEG_O, il, ep, ep, ph++);         SS_PROF_PHASE(2)
+            cons = gemv_phase(cons, SEG_CQ, il, ep, ep, ph++);        SS_PROF_PHASE(3)
             cons = cross_attn(cons, ep);                        SS_PROF_PHASE(4)
-            cons = gemv_phase(cons, SEG_CO, il, ep, ep);        SS_PROF_PHASE(5)
-            cons = gemv_phase(cons, SEG_FC1, il, ep, ep);       SS_PROF_PHASE(6)
-            cons = gemv_phase(cons, SEG_FC2, il, ep, ep + 1);   SS_PROF_PHASE(7)
+            cons = gemv_phase(cons, SEG_CO, il, ep, ep, ph++);        SS_PROF_PHASE(5)
+            cons = gemv_phase(cons, SEG_FC1, il, ep, ep, ph++);       SS_PROF_PHASE(6)
+            cons = gemv_phase(cons, SEG_FC2, il, ep, ep + 1, ph++);   SS_PROF_PHASE(7)
         }
         long long tp = clock64();
 
@@ -848,7 +912,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         const uint32_t epL = ep0 + (uint32_t)L;
         const bool sampling = do_sample && jrel >= n_prompt - 1;
         if (need_logits) {
-            cons = gemv_phase(cons, SEG_LM, 0, epL, epL);
+            cons = gemv_phase(cons, SEG_LM, 0, epL, epL, ph++);
             const bool keep = keep_logits && sm.st.n_kept < P.keep_cap;
             lm_epilogue(keep, sampling, epL);
             consumer_sync();
@@ -877,7 +941,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         const DecState st = sm.st;
         if (P.prof) {
             sm.prof[3] = clock64() - t_begin;
-            for (int i = 0; i < 24; i++) P.prof[(size_t)cta * 24 + i] = sm.prof[i];
+            for (int i = 0; i < kProfN; i++) P.prof[(size_t)cta * kProfN + i] = sm.prof[i];
         }
         if (cta == 0) {
             ctl->pos = st.pos; ctl->token = st.token; ctl->n_sampled = st.n_sampled; ctl->has_ts = st.has_ts; ctl->seek_delta = st.seek_delta;

@@ -144,7 +144,7 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     b.d = hp.n_text_state; b.H = hp.n_text_head; b.L = hp.n_text_layer; b.T = hp.n_audio_ctx; b.ctx = hp.n_text_ctx; b.n_vocab = hp.n_vocab;
     b.xsplit = std::max(1, std::min(8, s.mega_grid / b.H));
     b.s4 = powf((float)(b.d / b.H), -0.25f);
-    if (ceil_div(hp.n_vocab, s.mega_grid) > 384 || ceil_div(b.T, b.xsplit) > 322 || b.ctx > 500 || ceil_div(4 * b.d, s.mega_grid) > 250 ||
+    if (ceil_div(hp.n_vocab, s.mega_grid) > 512 || ceil_div(b.T, b.xsplit) > 512 || b.ctx > 500 || ceil_div(4 * b.d, s.mega_grid) > 250 ||
         b.H > s.mega_grid || s.mega_grid * 8 > 1280 || (b.d & 127))
         SS_THROW(-3, "device has too few / too many SMs (%d) for the decode kernel's per-CTA work buffers", s.mega_grid);
     b.tok_emb = m.tok_emb; b.d_pos = m.d_pos; b.lnf_w = m.d_ln.w; b.lnf_b = m.d_ln.b;
@@ -171,10 +171,11 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     CUDA_CHECK(cudaMemset(b.self_k, 0, kv * 2)); CUDA_CHECK(cudaMemset(b.self_v, 0, kv * 2));
     b.cross_k = s.cross_k; b.cross_v = s.cross_v;
     b.keep = with_keep ? s.keep : nullptr; b.keep_cap = with_keep ? s.keep_cap : 0;
-    b.prof = getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 24) : nullptr;
+    b.prof = getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 96) : nullptr;
     b.eot = v.eot; b.sot = v.sot; b.translate = v.translate; b.transcribe = v.transcribe; b.solm = v.solm; b.prev = v.prev;
     b.nosp = v.nosp; b.not_ = v.not_; b.beg = v.beg; b.blank = v.blank;
     b.suppress_blank = 1; b.tdrz = 0; b.tid0_init = -1;
+    b.dbg = getenv("SS_MEGA_DBG") ? atoi(getenv("SS_MEGA_DBG")) : 0;
     d->d_mp = dmalloc<MegaParams>(1); d->mp_dirty = true;
     d->h_ctl = hmalloc<DecCtl>(1); d->h_tok = hmalloc<TokData>(hp.n_text_ctx);
     memset(d->h_ctl, 0, sizeof(DecCtl));
@@ -395,15 +396,24 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     float total = 0.f; CUDA_CHECK(cudaEventElapsedTime(&total, s.ev[2], s.ev[3]));
     s.n_launches += 1;
     if (d.mp.prof) {
-        std::vector<long long> h((size_t)s.mega_grid * 24);
+        const int PN = 96;
+        std::vector<long long> h((size_t)s.mega_grid * PN);
         CUDA_CHECK(cudaMemcpy(h.data(), d.mp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
-        const char *names[23] = {"poll (flag wait)", "gemv (xr + rows)", "gemv xr load", "total", "phase QKV", "phase self-attn", "phase O", "phase CQ",
-                                 "phase cross-attn", "phase CO", "phase FC1", "phase FC2", "phase LM+sample", "gemv wait ring full", "cross K wait ring full", "-",
-                                 "FC1 poll", "FC1 LN stats", "FC1 normalise", "FC1 B frags", "FC1 tiles", "FC1 barrier", "FC1 fold+epilogue"};
-        for (int k = 0; k < 23; k++) {
+        const char *names[16] = {"poll (flag wait)", "gemv tiles", "-", "total", "phase QKV", "phase self-attn", "phase O", "phase CQ",
+                                 "phase cross-attn", "phase CO", "phase FC1", "phase FC2", "phase LM+sample", "gemv wait ring full", "cross K wait ring full", "-"};
+        const char *kinds[9] = {"QKV", "O", "CQ", "cross", "self", "CO", "FC1", "FC2", "LM"};
+        const char *gst[8] = {"poll", "LN stats", "normalise", "tiles", "barrier", "fold", "epilogue", "-"};
+        const char *ast[8] = {"q poll", "scores", "softmax", "PV", "fold+store", "partials fold", "-", "-"};
+        auto line = [&](int k, const char *nm) {
             long long mn = h[k], mx = h[k]; double sum = 0;
-            for (int c = 0; c < s.mega_grid; c++) { long long v = h[(size_t)c * 24 + k]; mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)v; }
-            fprintf(stderr, "[mega prof] %-20s cycles/step: min %.0f mean %.0f max %.0f\n", names[k], (double)mn / n_steps, sum / s.mega_grid / n_steps, (double)mx / n_steps);
+            for (int c = 0; c < s.mega_grid; c++) { long long v = h[(size_t)c * PN + k]; mn = std::min(mn, v); mx = std::max(mx, v); sum += (double)v; }
+            if (mx == 0) return;
+            fprintf(stderr, "[mega prof] %-26s cycles/step: min %8.0f mean %8.0f max %8.0f\n", nm, (double)mn / n_steps, sum / s.mega_grid / n_steps, (double)mx / n_steps);
+        };
+        for (int k = 0; k < 16; k++) line(k, names[k]);
+        for (int kd = 0; kd < 9; kd++) for (int sg = 0; sg < 8; sg++) {
+            char nm[64]; snprintf(nm, sizeof nm, "%s: %s", kinds[kd], (kd == 3 || kd == 4) ? ast[sg] : gst[sg]);
+            line(24 + kd * 8 + sg, nm);
         }
     }
     return total / n_steps;
