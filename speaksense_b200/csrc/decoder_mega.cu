@@ -51,7 +51,6 @@ struct DecState {   // replicated per CTA (thread-uniform, lives in shared memor
     int pos, token, n_sampled, has_ts, seek_delta, result_len, last_id, penult_id, n_kept, failed, completed, done;
 };
 struct SegTab { int row0, rows, row_bytes, rows_per_chunk, n_chunks, prows; };   // prows: rows of d halfs (FC2: 4 per output row)
-struct RowPre { float b0, b1, b2, r0, r1, r2; };   // bias / residual of the rows a finishing lane publishes in chunks 0..2
 
 struct __align__(128) MegaSmem {
     uint8_t ring[kSlots][kChunkBytes];
@@ -232,59 +231,135 @@ __device__ __forceinline__ float ll_value(const u64 *p) {      // a flagged word
 
 // index, inside the CTA's slice, of the row (FC2: quarter row) that finishing lane `l01` of `warp` publishes in chunk `ch`.
 // FC2: warp w works on quarter w & 3 of the rows {2 * (w >> 2), 2 * (w >> 2) + 1} of every 4-row chunk.
-__device__ __forceinline__ int tile_row(int kind, int ch, int warp, int l01) {
-    return kind == SEG_FC2 ? kChunkRows * ch + 4 * (2 * (warp >> 2) + l01) + (warp & 3) : kChunkRows * ch + 2 * warp + l01;
+template <int KIND>
+__device__ __forceinline__ int tile_row(int ch, int warp, int l01) {
+    return KIND == SEG_FC2 ? kChunkRows * ch + 4 * (2 * (warp >> 2) + l01) + (warp & 3) : kChunkRows * ch + 2 * warp + l01;
 }
 
-// what a finishing lane does with one finished row
-__device__ __forceinline__ void row_epilogue(int kind, int il, int R, float val, float bias, float res, uint32_t ep_out) {
+// One mat-vec phase, start to finish, specialised on the model width (KS = d / 128 k-steps) and the phase kind:
+//   * poll the input vector (every thread a few flagged pairs); LayerNorm where the phase has one (statistics: one shuffle
+//     reduction + one CTA barrier; every thread normalises the values it polled); f16 operand to shared memory; one CTA barrier.
+//   * the tensor-core part.  A chunk of the ring holds 16 weight rows (of d halfs); consumer warp w owns rows 2w, 2w+1 of
+//     every chunk and needs nobody else: a row is viewed as 8 interleaved K slices, so that one m16n8k16 tile =
+//     {2 rows} x {8 slices} and column n of the B operand carries the x values of slice n - the wanted products are the
+//     diagonal C[8 * row + slice][slice].  Per k-step (128 halfs = 256 B of a row) ldmatrix reads two contiguous 128-byte
+//     segments per row (conflict-free, no padding) and the warp's B fragments are 128 consecutive x values (2 per lane,
+//     twice), held in registers for the whole phase.  No cross-warp reduction and no CTA barrier: the two finishing lanes
+//     of the warp run the epilogue and publish the rows themselves (FC2: the four quarters of a row meet in shared memory).
+//   ep_in : epoch the input carries; outputs are published with ep_out;  ph: running phase count (operand buffer parity)
+template <int KS, int KIND>
+__device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_in, uint32_t ep_out, uint32_t ph) {
+    constexpr int D = KS * 128;
+    constexpr bool has_ln = KIND == SEG_QKV || KIND == SEG_CQ || KIND == SEG_FC1 || KIND == SEG_LM;
+    constexpr int widx = KIND == SEG_QKV ? 0 : KIND == SEG_O ? 1 : KIND == SEG_CQ ? 2 : KIND == SEG_CO ? 3 : KIND == SEG_FC1 ? 4 : 5;
+    constexpr int lidx = KIND == SEG_QKV ? 0 : KIND == SEG_CQ ? 1 : 2;
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
-    const int row = sm.seg[kind].row0 + R, d = P.d;
-    if (kind == SEG_FC2) { sm.p4[R] = val; return; }
-    if (kind == SEG_LM) { sm.acc[R] = val; return; }
-    const float v = val + bias;
-    if (kind == SEG_QKV) {
-        const int pos = sm.st.pos;
-        if (row < d) ll_store(P.q1 + row, r16(v * P.s4), ep_out);
-        else if (row < 2 * d) {
-            const int n = row - d; const __half hk = __float2half_rn(v * P.s4);
-            (P.self_k + (size_t)il * P.ctx * d)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
-        } else {
-            const int n = row - 2 * d; const __half hv = __float2half_rn(v);
-            (P.self_v + (size_t)il * P.ctx * d)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
-        }
-    } else if (kind == SEG_O) ll_store(P.xB + row, res + v, ep_out);
-    else if (kind == SEG_CO) ll_store(P.xC + row, res + v, ep_out);
-    else if (kind == SEG_CQ) ll_store(P.q2 + row, r16(v * P.s4), ep_out);
-    else ll_store(P.hbuf + row, gelu16(v), ep_out);
-}
-
-// The tensor-core part of a mat-vec phase.  A chunk of the ring holds 16 weight rows (of d halfs); consumer warp w owns
-// rows 2w, 2w+1 of every chunk and needs nobody else: a row is viewed as 8 interleaved K slices, so that one m16n8k16
-// tile = {2 rows} x {8 slices} and column n of the B operand carries the x values of slice n - the wanted products are
-// the diagonal C[8 * row + slice][slice].  Per k-step (128 halfs = 256 B of a row) ldmatrix reads two contiguous 128-byte
-// segments per row (conflict-free, no padding) and the warp's B fragments are 128 consecutive x values (2 per lane, twice),
-// held in registers for the whole phase.  No cross-warp reduction, no CTA barrier: the two finishing lanes of the warp
-// run the epilogue and publish the rows themselves.
-template <int KS>
-__device__ __noinline__ uint32_t gemv_tiles(uint32_t cons, int kind, int il, uint32_t ep_out, const __half *xq, RowPre pre) {
-    MegaSmem &sm = SM;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const SegTab seg = sm.seg[kind];
-    uint32_t bf[2 * KS];
+    const int row0 = sm.seg[KIND].row0, prows = sm.seg[KIND].prows, n_chunks = sm.seg[KIND].n_chunks;
+    __half *buf = sm.xin[ph & 1];
+    const bool prof_on = P.prof != nullptr && tid == 0;
+    long long tq = prof_on ? clock64() : 0;
+#define SS_STAGE(k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + KIND * 8 + (k)] += tn - tq; tq = tn; }
+    // ---- static / already-valid operands of the epilogue, fetched now so that their L2 latency hides behind the poll
+    float pb[kPre], pr[kPre];       // bias / residual of the rows this (finishing) lane publishes in chunks 0..kPre-1
 #pragma unroll
-    for (int j = 0; j < KS; j++) {
-        bf[2 * j] = *reinterpret_cast<const uint32_t *>(xq + 128 * j + 2 * lane);
-        bf[2 * j + 1] = *reinterpret_cast<const uint32_t *>(xq + 128 * j + 64 + 2 * lane);
+    for (int c = 0; c < kPre; c++) { pb[c] = 0.f; pr[c] = 0.f; }
+    float fb = 0.f, fr = 0.f;      // FC2: bias and residual of output row `tid` (folded after the tiles)
+    const int tok = sm.st.token, pos = sm.st.pos;
+    if (KIND == SEG_FC2) {
+        if (tid < sm.seg[KIND].rows) { fb = __ldg(P.layer[il].b[5] + row0 + tid); fr = ll_value(P.xC + row0 + tid); }
+    } else if (KIND != SEG_LM && lane < 2) {
+        const float *bias = P.layer[il].b[widx] + row0;
+#pragma unroll
+        for (int c = 0; c < kPre; c++) {
+            const int R = tile_row<KIND>(c, warp, lane);
+            if (R < prows) {
+                pb[c] = __ldg(bias + R);
+                if (KIND == SEG_O) pr[c] = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * D + row0 + R)) + __ldg(P.d_pos + (size_t)pos * D + row0 + R) : ll_value(P.xA + row0 + R);
+                else if (KIND == SEG_CO) pr[c] = ll_value(P.xB + row0 + R);
+            }
+        }
+    }
+    // ---- input vector -> f16 operand in shared memory
+    if (has_ln) {
+        constexpr int n2 = D >> 1;                                          // flagged pairs
+        constexpr int NK = (n2 + kConsumerThreads - 1) / kConsumerThreads;   // per thread (<= 3)
+        const float *lw = KIND == SEG_LM ? P.lnf_w : P.layer[il].lnw[lidx], *lb = KIND == SEG_LM ? P.lnf_b : P.layer[il].lnb[lidx];
+        float2 w2[NK], b2[NK], xv[NK];
+#pragma unroll
+        for (int k = 0; k < NK; k++) {      // (indices clamped instead of predicated: the arrays stay in registers)
+            const int i = min(tid + k * kConsumerThreads, n2 - 1);
+            w2[k] = __ldg(reinterpret_cast<const float2 *>(lw) + i); b2[k] = __ldg(reinterpret_cast<const float2 *>(lb) + i);
+        }
+        if (KIND == SEG_QKV && il == 0) {           // token embedding + positional embedding
+            const __half2 *e = reinterpret_cast<const __half2 *>(P.tok_emb + (size_t)tok * D);
+            const float2 *pe = reinterpret_cast<const float2 *>(P.d_pos + (size_t)pos * D);
+#pragma unroll
+            for (int k = 0; k < NK; k++) {
+                const int i = min(tid + k * kConsumerThreads, n2 - 1);
+                const float2 ev = __half22float2(__ldg(e + i)), pv = __ldg(pe + i); xv[k] = make_float2(ev.x + pv.x, ev.y + pv.y);
+            }
+        } else {
+            const u64 *src = KIND == SEG_QKV || KIND == SEG_LM ? P.xA : KIND == SEG_CQ ? P.xB : P.xC;
+            const long long t0 = prof_on ? clock64() : 0;
+            ulonglong2 v[NK];
+            bool all;
+            do {
+#pragma unroll
+                for (int k = 0; k < NK; k++) v[k] = ll_load2(src + 2 * min(tid + k * kConsumerThreads, n2 - 1));
+                all = true;
+#pragma unroll
+                for (int k = 0; k < NK; k++)
+                    if ((uint32_t)(v[k].x >> 32) != ep_in || (uint32_t)(v[k].y >> 32) != ep_in) all = false;
+            } while (!all);
+#pragma unroll
+            for (int k = 0; k < NK; k++) xv[k] = make_float2(__uint_as_float((uint32_t)v[k].x), __uint_as_float((uint32_t)v[k].y));
+            if (prof_on) sm.prof[0] += clock64() - t0;
+        }
+        SS_STAGE(0)
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NK; k++) if (tid + k * kConsumerThreads < n2) { s1 += xv[k].x + xv[k].y; s2 += xv[k].x * xv[k].x + xv[k].y * xv[k].y; }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0) sm.red2[warp] = make_float2(s1, s2);
+        consumer_sync();
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; w++) { const float2 t = sm.red2[w]; t1 += t.x; t2 += t.y; }
+        const float mean = t1 / D, rstd = rsqrtf(fmaxf(t2 / D - mean * mean, 0.f) + 1e-5f);
+        SS_STAGE(1)
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            const int i = tid + k * kConsumerThreads;
+            if (i < n2) reinterpret_cast<__half2 *>(buf)[i] = __floats2half2_rn((xv[k].x - mean) * rstd * w2[k].x + b2[k].x, (xv[k].y - mean) * rstd * w2[k].y + b2[k].y);
+        }
+    } else {
+        const u64 *src = KIND == SEG_O ? P.att1 : KIND == SEG_CO ? P.att2 : P.hbuf;
+        poll_vec<true>(src, KIND == SEG_FC2 ? 4 * D : D, ep_in, buf);
+        SS_STAGE(0)
+    }
+    consumer_sync();
+    SS_STAGE(2)
+    // ---- B fragments: the x side of every k-step, in registers for the whole phase
+    uint32_t bf[2 * KS];
+    {
+        const __half *xq = buf + (KIND == SEG_FC2 ? (warp & 3) * D : 0) + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < KS; j++) {
+            bf[2 * j] = *reinterpret_cast<const uint32_t *>(xq + 128 * j);
+            bf[2 * j + 1] = *reinterpret_cast<const uint32_t *>(xq + 128 * j + 64);
+        }
     }
     // ldmatrix.x4 row addresses: lanes 8m..8m+7 feed matrix m = (row of the pair: m & 1, k half: m >> 1), slice = lane & 7
-    const int mi = lane >> 3;
-    const uint32_t a_off = (uint32_t)tile_row(kind, 0, warp, mi & 1) * (uint32_t)seg.row_bytes + 128u * (uint32_t)(mi >> 1) + 16u * (uint32_t)(lane & 7);
+    const uint32_t a_off = (uint32_t)tile_row<KIND>(0, warp, (lane >> 3) & 1) * (uint32_t)(2 * D) + 128u * (uint32_t)(lane >> 4) + 16u * (uint32_t)(lane & 7);
     const int g = lane >> 2;
-    const bool diag = (lane & 3) == (g >> 1);
-    const bool prof_on = sm.P.prof != nullptr && tid == 0;
-    for (int ch = 0; ch < seg.n_chunks; ch++) {
+    const bool diag = (lane & 3) == (g >> 1), odd = (g & 1) != 0;
+    // where this finishing lane publishes (kinds with one flagged output buffer)
+    u64 *outp = (KIND == SEG_O ? P.xB : KIND == SEG_CO ? P.xC : KIND == SEG_CQ ? P.q2 : P.hbuf) + row0 + tile_row<KIND>(0, warp, lane & 1);
+    const float s4 = P.s4;
+#pragma unroll 1
+    for (int ch = 0; ch < n_chunks; ch++) {
         const int slot = cons % kSlots;
         if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[13] += clock64() - tw0; }
         else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
@@ -308,151 +383,52 @@ __device__ __noinline__ uint32_t gemv_tiles(uint32_t cons, int kind, int il, uin
         cons++;
 #pragma unroll
         for (int i = 1; i < NA; i++) { cc[0][0] += cc[i][0]; cc[0][1] += cc[i][1]; cc[0][2] += cc[i][2]; cc[0][3] += cc[i][3]; }
-        float v0 = diag ? ((g & 1) ? cc[0][1] : cc[0][0]) : 0.f;      // row 2w   : sum over its 8 slices
-        float v1 = diag ? ((g & 1) ? cc[0][3] : cc[0][2]) : 0.f;      // row 2w+1
+        float v0 = diag ? (odd ? cc[0][1] : cc[0][0]) : 0.f;      // row 2w   : sum over its 8 slices
+        float v1 = diag ? (odd ? cc[0][3] : cc[0][2]) : 0.f;      // row 2w+1
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
         if (lane < 2) {
-            const int R = tile_row(kind, ch, warp, lane);
-            if (R < seg.prows) {
-                float b = 0.f, r = 0.f;
-                if (kind != SEG_FC2 && kind != SEG_LM) {
-                    if (ch == 0) { b = pre.b0; r = pre.r0; } else if (ch == 1) { b = pre.b1; r = pre.r1; } else if (ch == 2) { b = pre.b2; r = pre.r2; }
+            const int R = tile_row<KIND>(ch, warp, lane);
+            if (R < prows) {
+                const float val = lane ? v1 : v0;
+                if (KIND == SEG_FC2) sm.p4[R] = val;
+                else if (KIND == SEG_LM) sm.acc[R] = val;
+                else {
+                    float b, r;
+                    if (ch == 0) { b = pb[0]; r = pr[0]; } else if (ch == 1) { b = pb[1]; r = pr[1]; } else if (ch == 2) { b = pb[2]; r = pr[2]; }
                     else {      // more chunks per phase than prefetch registers (fewer SMs than the design point)
-                        const MegaParams &P = sm.P;
-                        const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : 4;
-                        b = __ldg(P.layer[il].b[widx] + seg.row0 + R);
-                        if (kind == SEG_O) r = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)sm.st.token * P.d + seg.row0 + R)) + __ldg(P.d_pos + (size_t)sm.st.pos * P.d + seg.row0 + R)
-                                                       : ll_value(P.xA + seg.row0 + R);
-                        else if (kind == SEG_CO) r = ll_value(P.xB + seg.row0 + R);
+                        b = __ldg(P.layer[il].b[widx] + row0 + R); r = 0.f;
+                        if (KIND == SEG_O) r = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * D + row0 + R)) + __ldg(P.d_pos + (size_t)pos * D + row0 + R) : ll_value(P.xA + row0 + R);
+                        else if (KIND == SEG_CO) r = ll_value(P.xB + row0 + R);
                     }
+                    const float v = val + b;
+                    if (KIND == SEG_QKV) {
+                        const int row = row0 + R;
+                        if (row < D) ll_store(P.q1 + row, r16(v * s4), ep_out);
+                        else if (row < 2 * D) {
+                            const int n = row - D; const __half hk = __float2half_rn(v * s4);
+                            (P.self_k + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
+                        } else {
+                            const int n = row - 2 * D; const __half hv = __float2half_rn(v);
+                            (P.self_v + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
+                        }
+                    } else if (KIND == SEG_O || KIND == SEG_CO) ll_store(outp + kChunkRows * ch, r + v, ep_out);
+                    else if (KIND == SEG_CQ) ll_store(outp + kChunkRows * ch, r16(v * s4), ep_out);
+                    else ll_store(outp + kChunkRows * ch, gelu16(v), ep_out);
                 }
-                row_epilogue(kind, il, R, lane ? v1 : v0, b, r, ep_out);
             }
         }
-    }
-    return cons;
-}
-
-// One mat-vec phase, start to finish: poll the input vector (every thread a few flagged pairs), LayerNorm where the
-// phase has one (statistics: one shuffle reduction + one CTA barrier; every thread normalises the values it polled),
-// f16 operand to shared memory, one CTA barrier, then the warps run gemv_tiles independently.
-//   kind  : SEG_QKV / SEG_O / SEG_CQ / SEG_CO / SEG_FC1 / SEG_FC2 / SEG_LM
-//   ep_in : epoch the input carries; outputs are published with ep_out;  ph: running phase count (operand buffer parity)
-__device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int kind, int il, uint32_t ep_in, uint32_t ep_out, uint32_t ph) {
-    MegaSmem &sm = SM;
-    const MegaParams &P = sm.P;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = P.d;
-    const SegTab seg = sm.seg[kind];
-    const bool has_ln = kind == SEG_QKV || kind == SEG_CQ || kind == SEG_FC1 || kind == SEG_LM;
-    const int widx = kind == SEG_QKV ? 0 : kind == SEG_O ? 1 : kind == SEG_CQ ? 2 : kind == SEG_CO ? 3 : kind == SEG_FC1 ? 4 : 5;
-    const int lidx = kind == SEG_QKV ? 0 : kind == SEG_CQ ? 1 : 2;
-    __half *buf = sm.xin[ph & 1];
-    const bool prof_on = P.prof != nullptr && tid == 0;
-    long long tq = prof_on ? clock64() : 0;
-#define SS_STAGE(k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + kind * 8 + (k)] += tn - tq; tq = tn; }
-    // ---- static / already-valid operands of the epilogue, fetched now so that their L2 latency hides behind the poll
-    RowPre pre = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float fb = 0.f, fr = 0.f;      // FC2: bias and residual of output row `tid` (folded after the tiles)
-    const int tok = sm.st.token, pos = sm.st.pos;
-    if (kind == SEG_FC2) {
-        if (tid < seg.rows) { fb = __ldg(P.layer[il].b[5] + seg.row0 + tid); fr = ll_value(P.xC + seg.row0 + tid); }
-    } else if (kind != SEG_LM && lane < 2) {
-        const float *bias = P.layer[il].b[widx];
-        float bb[kPre], rr[kPre];
-#pragma unroll
-        for (int c = 0; c < kPre; c++) {
-            const int R = tile_row(kind, c, warp, lane);
-            bb[c] = 0.f; rr[c] = 0.f;
-            if (R < seg.rows) {
-                const int row = seg.row0 + R;
-                bb[c] = __ldg(bias + row);
-                if (kind == SEG_O) rr[c] = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * d + row)) + __ldg(P.d_pos + (size_t)pos * d + row) : ll_value(P.xA + row);
-                else if (kind == SEG_CO) rr[c] = ll_value(P.xB + row);
-            }
-        }
-        pre.b0 = bb[0]; pre.b1 = bb[1]; pre.b2 = bb[2]; pre.r0 = rr[0]; pre.r1 = rr[1]; pre.r2 = rr[2];
-    }
-    // ---- input vector -> f16 operand in shared memory
-    if (has_ln) {
-        const int n2 = d >> 1;                      // pairs; host side guarantees d <= 1280: at most 3 per thread
-        const float *lw = kind == SEG_LM ? P.lnf_w : P.layer[il].lnw[lidx], *lb = kind == SEG_LM ? P.lnf_b : P.layer[il].lnb[lidx];
-        float2 w2[3], b2[3], xv[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int i = tid + k * kConsumerThreads;
-            if (i < n2) { w2[k] = __ldg(reinterpret_cast<const float2 *>(lw) + i); b2[k] = __ldg(reinterpret_cast<const float2 *>(lb) + i); }
-        }
-        if (kind == SEG_QKV && il == 0) {           // token embedding + positional embedding
-            const __half2 *e = reinterpret_cast<const __half2 *>(P.tok_emb + (size_t)tok * d);
-            const float2 *pe = reinterpret_cast<const float2 *>(P.d_pos + (size_t)pos * d);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int i = tid + k * kConsumerThreads;
-                if (i < n2) { const float2 ev = __half22float2(__ldg(e + i)), pv = __ldg(pe + i); xv[k] = make_float2(ev.x + pv.x, ev.y + pv.y); }
-            }
-        } else {
-            const u64 *src = kind == SEG_QKV || kind == SEG_LM ? P.xA : kind == SEG_CQ ? P.xB : P.xC;
-            const long long t0 = prof_on ? clock64() : 0;
-            ulonglong2 v[3];
-            bool all;
-            do {
-#pragma unroll
-                for (int k = 0; k < 3; k++) { const int i = tid + k * kConsumerThreads; if (i < n2) v[k] = ll_load2(src + 2 * i); }
-                all = true;
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const int i = tid + k * kConsumerThreads;
-                    if (i < n2 && ((uint32_t)(v[k].x >> 32) != ep_in || (uint32_t)(v[k].y >> 32) != ep_in)) all = false;
-                }
-            } while (!all);
-#pragma unroll
-            for (int k = 0; k < 3; k++) xv[k] = make_float2(__uint_as_float((uint32_t)v[k].x), __uint_as_float((uint32_t)v[k].y));
-            if (prof_on) sm.prof[0] += clock64() - t0;
-        }
-        SS_STAGE(0)
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; k++) { const int i = tid + k * kConsumerThreads; if (i < n2) { s1 += xv[k].x + xv[k].y; s2 += xv[k].x * xv[k].x + xv[k].y * xv[k].y; } }
-        s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if (lane == 0) sm.red2[warp] = make_float2(s1, s2);
-        consumer_sync();
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int w = 0; w < kConsumerWarps; w++) { const float2 t = sm.red2[w]; t1 += t.x; t2 += t.y; }
-        const float mean = t1 / d, rstd = rsqrtf(fmaxf(t2 / d - mean * mean, 0.f) + 1e-5f);
-        SS_STAGE(1)
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int i = tid + k * kConsumerThreads;
-            if (i < n2) reinterpret_cast<__half2 *>(buf)[i] = __floats2half2_rn((xv[k].x - mean) * rstd * w2[k].x + b2[k].x, (xv[k].y - mean) * rstd * w2[k].y + b2[k].y);
-        }
-    } else {
-        const u64 *src = kind == SEG_O ? P.att1 : kind == SEG_CO ? P.att2 : P.hbuf;
-        poll_vec<true>(src, kind == SEG_FC2 ? 4 * d : d, ep_in, buf);
-        SS_STAGE(0)
-    }
-    consumer_sync();
-    SS_STAGE(2)
-    // ---- the tiles of this CTA's slice out of the ring (k-steps known at compile time: fragments in registers)
-    const __half *xq = buf + (kind == SEG_FC2 ? (warp & 3) * d : 0);
-    switch (d >> 7) {      // host side guarantees d % 128 == 0 and d <= 1280
-#define SS_KS(n) case n: cons = gemv_tiles<n>(cons, kind, il, ep_out, xq, pre); break;
-        SS_KS(1) SS_KS(2) SS_KS(3) SS_KS(4) SS_KS(5) SS_KS(6) SS_KS(7) SS_KS(8) SS_KS(9)
-#undef SS_KS
-        default: cons = gemv_tiles<10>(cons, kind, il, ep_out, xq, pre); break;
     }
     if (prof_on) sm.prof[1] += clock64() - tq;
     SS_STAGE(3)
-    if (kind == SEG_FC2) {      // fold the four quarters of every output row
+    if (KIND == SEG_FC2) {      // fold the four quarters of every output row
         consumer_sync();
-        if (tid < seg.rows) {
+        if (tid < sm.seg[KIND].rows) {
             const float4 q = *reinterpret_cast<const float4 *>(&sm.p4[4 * tid]);
-            ll_store(P.xA + seg.row0 + tid, fr + (((q.x + q.y) + q.z) + q.w) + fb, ep_out);
+            ll_store(P.xA + row0 + tid, fr + (((q.x + q.y) + q.z) + q.w) + fb, ep_out);
         }
         SS_STAGE(4)
-    } else if (kind == SEG_LM) consumer_sync();     // lm_epilogue reads other warps' rows
+    } else if (KIND == SEG_LM) consumer_sync();     // lm_epilogue reads other warps' rows
 #undef SS_STAGE
     return cons;
 }
@@ -801,6 +777,68 @@ __device__ __forceinline__ const uint8_t *seg_base(const MegaParams &P, const Se
     return reinterpret_cast<const uint8_t *>(w) + (size_t)s.row0 * (kind == SEG_FC2 ? 4 : 1) * s.row_bytes;
 }
 
+struct ConsArgs { int L, pos0, n_prompt, do_sample, seek, seek_end, n_max, keep_logits, all_logits, steps_left; };
+
+// the consumer warps' decode loop, specialised on the model width (KS = d / 128)
+template <int KS>
+__device__ __noinline__ uint32_t consumer_main(const ConsArgs a) {
+    MegaSmem &sm = SM;
+    const MegaParams &P = sm.P;
+    DecCtl *ctl = P.ctl;
+    const int tid = threadIdx.x;
+    const int L = a.L, pos0 = a.pos0, n_prompt = a.n_prompt, do_sample = a.do_sample, seek = a.seek, seek_end = a.seek_end, n_max = a.n_max,
+              keep_logits = a.keep_logits, all_logits = a.all_logits, steps_left = a.steps_left;
+    uint32_t cons = 0, ph = 0;
+    const uint32_t ep_stride = (uint32_t)L + 1;
+
+    for (int t = 0; t < steps_left; t++) {
+        if (sm.st.done) break;
+        const int jrel = sm.st.pos - pos0;
+        const bool need_logits = all_logits || jrel >= n_prompt - 1;
+        const uint32_t ep0 = 1u + (uint32_t)t * ep_stride;      // epoch of layer il: ep0 + il; LM head input: ep0 + L
+
+#pragma unroll 1
+        for (int il = 0; il < L; il++) {
+            const uint32_t ep = ep0 + (uint32_t)il;
+            long long tp = clock64();
+#define SS_PROF_PHASE(k) { const long long tn = clock64(); if (tid == 0) sm.prof[4 + (k)] += tn - tp; tp = tn; }
+            cons = gemv_phase<KS, SEG_QKV>(cons, il, ep, ep, ph++);       SS_PROF_PHASE(0)
+            self_attn(il, ep);                                  SS_PROF_PHASE(1)
+            cons = gemv_phase<KS, SEG_O>(cons, il, ep, ep, ph++);         SS_PROF_PHASE(2)
+            cons = gemv_phase<KS, SEG_CQ>(cons, il, ep, ep, ph++);        SS_PROF_PHASE(3)
+            cons = cross_attn(cons, ep);                        SS_PROF_PHASE(4)
+            cons = gemv_phase<KS, SEG_CO>(cons, il, ep, ep, ph++);        SS_PROF_PHASE(5)
+            cons = gemv_phase<KS, SEG_FC1>(cons, il, ep, ep, ph++);       SS_PROF_PHASE(6)
+            cons = gemv_phase<KS, SEG_FC2>(cons, il, ep, ep + 1, ph++);   SS_PROF_PHASE(7)
+        }
+        long long tp = clock64();
+
+        // ---------------- final LN + LM head + per-CTA softmax statistics ----------------
+        const uint32_t epL = ep0 + (uint32_t)L;
+        const bool sampling = do_sample && jrel >= n_prompt - 1;
+        if (need_logits) {
+            cons = gemv_phase<KS, SEG_LM>(cons, 0, epL, epL, ph++);
+            const bool keep = keep_logits && sm.st.n_kept < P.keep_cap;
+            lm_epilogue(keep, sampling, epL);
+            consumer_sync();
+            if (keep && tid == 0) sm.st.n_kept = sm.st.n_kept + 1;
+            consumer_sync();
+        }
+        if (jrel < n_prompt - 1) {   // prompt token: feed the next one
+            consumer_sync();
+            if (tid == 0) { sm.st.token = ctl->prompt[jrel + 1]; sm.st.pos = sm.st.pos + 1; sm.prof[12] += clock64() - tp; }
+            consumer_sync();
+            continue;
+        }
+        if (!do_sample) { consumer_sync(); if (tid == 0) { sm.st.done = 1; sm.prof[12] += clock64() - tp; } consumer_sync(); break; }
+        sample_and_update(seek, seek_end, n_max, epL);
+        SS_PROF_PHASE(8)
+#undef SS_PROF_PHASE
+    }
+
+    return cons;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -882,53 +920,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
     }
 
     // ======================= consumers =======================
-    uint32_t cons = 0, ph = 0;
     const long long t_begin = clock64();
-    const uint32_t ep_stride = (uint32_t)L + 1;
-
-    for (int t = 0; t < steps_left; t++) {
-        if (sm.st.done) break;
-        const int jrel = sm.st.pos - pos0;
-        const bool need_logits = all_logits || jrel >= n_prompt - 1;
-        const uint32_t ep0 = 1u + (uint32_t)t * ep_stride;      // epoch of layer il: ep0 + il; LM head input: ep0 + L
-
-#pragma unroll 1
-        for (int il = 0; il < L; il++) {
-            const uint32_t ep = ep0 + (uint32_t)il;
-            long long tp = clock64();
-#define SS_PROF_PHASE(k) { const long long tn = clock64(); if (tid == 0) sm.prof[4 + (k)] += tn - tp; tp = tn; }
-            cons = gemv_phase(cons, SEG_QKV, il, ep, ep, ph++);       SS_PROF_PHASE(0)
-            self_attn(il, ep);                                  SS_PROF_PHASE(1)
-            cons = gemv_phase(cons, SEG_O, il, ep, ep, ph++);         SS_PROF_PHASE(2)
-            cons = gemv_phase(cons, SEG_CQ, il, ep, ep, ph++);        SS_PROF_PHASE(3)
-            cons = cross_attn(cons, ep);                        SS_PROF_PHASE(4)
-            cons = gemv_phase(cons, SEG_CO, il, ep, ep, ph++);        SS_PROF_PHASE(5)
-            cons = gemv_phase(cons, SEG_FC1, il, ep, ep, ph++);       SS_PROF_PHASE(6)
-            cons = gemv_phase(cons, SEG_FC2, il, ep, ep + 1, ph++);   SS_PROF_PHASE(7)
-        }
-        long long tp = clock64();
-
-        // ---------------- final LN + LM head + per-CTA softmax statistics ----------------
-        const uint32_t epL = ep0 + (uint32_t)L;
-        const bool sampling = do_sample && jrel >= n_prompt - 1;
-        if (need_logits) {
-            cons = gemv_phase(cons, SEG_LM, 0, epL, epL, ph++);
-            const bool keep = keep_logits && sm.st.n_kept < P.keep_cap;
-            lm_epilogue(keep, sampling, epL);
-            consumer_sync();
-            if (keep && tid == 0) sm.st.n_kept = sm.st.n_kept + 1;
-            consumer_sync();
-        }
-        if (jrel < n_prompt - 1) {   // prompt token: feed the next one
-            consumer_sync();
-            if (tid == 0) { sm.st.token = ctl->prompt[jrel + 1]; sm.st.pos = sm.st.pos + 1; sm.prof[12] += clock64() - tp; }
-            consumer_sync();
-            continue;
-        }
-        if (!do_sample) { consumer_sync(); if (tid == 0) { sm.st.done = 1; sm.prof[12] += clock64() - tp; } consumer_sync(); break; }
-        sample_and_update(seek, seek_end, n_max, epL);
-        SS_PROF_PHASE(8)
-#undef SS_PROF_PHASE
+    ConsArgs ca{L, pos0, n_prompt, do_sample, seek, seek_end, n_max, keep_logits, all_logits, steps_left};
+    uint32_t cons = 0;
+    switch (P.d >> 7) {      // host side guarantees d % 128 == 0 and d <= 1280 (Whisper widths: 384 .. 1280; 256: test models)
+        case 2: cons = consumer_main<2>(ca); break;
+        case 3: cons = consumer_main<3>(ca); break;
+        case 4: cons = consumer_main<4>(ca); break;
+        case 6: cons = consumer_main<6>(ca); break;
+        case 8: cons = consumer_main<8>(ca); break;
+        default: cons = consumer_main<10>(ca); break;
     }
 
     // ---------------- shutdown: stop the producer, drain copies still in flight, publish the state ----------------
