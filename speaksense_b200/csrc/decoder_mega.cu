@@ -188,38 +188,28 @@ __device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, v
     return make_float2(s, s2);
 }
 
-// block-wide (256 consumer threads) reductions; result broadcast
-__device__ __forceinline__ float consumer_sum(float v) {
+// block-wide (256 consumer threads) reductions; result broadcast.  One CTA barrier each: the scratch row alternates
+// (`which`), and two uses of the same row are always separated by a barrier of the other one.
+__device__ __forceinline__ float consumer_sum(float v, int which = 0) {
     MegaSmem &sm = SM;
     v = warp_sum(v);
-    consumer_sync();
-    if ((threadIdx.x & 31) == 0) sm.red1[threadIdx.x >> 5] = v;
+    float *r = sm.red1 + 8 * which;
+    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
     consumer_sync();
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < kConsumerWarps; i++) t += sm.red1[i];
+    for (int i = 0; i < kConsumerWarps; i++) t += r[i];
     return t;
 }
-__device__ __forceinline__ float2 consumer_sum2(float2 v) {
-    MegaSmem &sm = SM;
-    v.x = warp_sum(v.x); v.y = warp_sum(v.y);
-    consumer_sync();
-    if ((threadIdx.x & 31) == 0) { sm.red1[threadIdx.x >> 5] = v.x; sm.red1[8 + (threadIdx.x >> 5)] = v.y; }
-    consumer_sync();
-    float2 t = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < kConsumerWarps; i++) { t.x += sm.red1[i]; t.y += sm.red1[8 + i]; }
-    return t;
-}
-__device__ __forceinline__ float consumer_max(float v) {
+__device__ __forceinline__ float consumer_max(float v, int which = 1) {
     MegaSmem &sm = SM;
     v = warp_max(v);
+    float *r = sm.red1 + 8 * which;
+    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
     consumer_sync();
-    if ((threadIdx.x & 31) == 0) sm.red1[threadIdx.x >> 5] = v;
-    consumer_sync();
-    float t = sm.red1[0];
+    float t = r[0];
 #pragma unroll
-    for (int i = 1; i < kConsumerWarps; i++) t = fmaxf(t, sm.red1[i]);
+    for (int i = 1; i < kConsumerWarps; i++) t = fmaxf(t, r[i]);
     return t;
 }
 
@@ -280,6 +270,30 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
                 else if (KIND == SEG_CO) pr[c] = ll_value(P.xB + row0 + R);
             }
         }
+    }
+    // ---- A fragments of the first chunk: the weights are static and the producer runs ahead, so they are fetched
+    //      before the input vector has even arrived (ldmatrix.x4 row addresses: lanes 8m..8m+7 feed matrix
+    //      m = (row of the pair: m & 1, k half: m >> 1), slice = lane & 7)
+    const uint32_t a_off = (uint32_t)tile_row<KIND>(0, warp, (lane >> 3) & 1) * (uint32_t)(2 * D) + 128u * (uint32_t)(lane >> 4) + 16u * (uint32_t)(lane & 7);
+    if (n_chunks == 0) return cons;      // (CTA-uniform) no rows of this matrix here: nothing to compute, nothing to publish
+    uint32_t af[KS][4];
+    {
+        const int slot = cons % kSlots;
+        if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[13] += clock64() - tw0; }
+        else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
+        const uint32_t abase = smem_u32(sm.ring[slot]) + a_off;
+#pragma unroll
+        for (int j = 0; j < KS; j++)
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 256u * j));
+        // the fragments are in registers: hand the slot back to the producer now (it refills it while the input is polled).
+        // Consuming every fragment register first guarantees that the ldmatrix reads have completed.
+        uint32_t sink = 0;
+#pragma unroll
+        for (int j = 0; j < KS; j++) sink ^= af[j][0] ^ af[j][1] ^ af[j][2] ^ af[j][3];
+        asm volatile("" ::"r"(sink) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[slot]);
     }
     // ---- input vector -> f16 operand in shared memory
     if (has_ln) {
@@ -351,8 +365,6 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
             bf[2 * j + 1] = *reinterpret_cast<const uint32_t *>(xq + 128 * j + 64);
         }
     }
-    // ldmatrix.x4 row addresses: lanes 8m..8m+7 feed matrix m = (row of the pair: m & 1, k half: m >> 1), slice = lane & 7
-    const uint32_t a_off = (uint32_t)tile_row<KIND>(0, warp, (lane >> 3) & 1) * (uint32_t)(2 * D) + 128u * (uint32_t)(lane >> 4) + 16u * (uint32_t)(lane & 7);
     const int g = lane >> 2;
     const bool diag = (lane & 3) == (g >> 1), odd = (g & 1) != 0;
     // where this finishing lane publishes (kinds with one flagged output buffer)
@@ -360,15 +372,6 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
     const float s4 = P.s4;
 #pragma unroll 1
     for (int ch = 0; ch < n_chunks; ch++) {
-        const int slot = cons % kSlots;
-        if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[13] += clock64() - tw0; }
-        else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
-        const uint32_t abase = smem_u32(sm.ring[slot]) + a_off;
-        uint32_t af[KS][4];
-#pragma unroll
-        for (int j = 0; j < KS; j++)
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 256u * j));
         constexpr int NA = KS >= 2 ? 2 : 1;     // independent accumulator sets
         float cc[NA][4];
 #pragma unroll
@@ -378,9 +381,21 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
             asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                          : "+f"(cc[j % NA][0]), "+f"(cc[j % NA][1]), "+f"(cc[j % NA][2]), "+f"(cc[j % NA][3])
                          : "r"(af[j][0]), "r"(af[j][1]), "r"(af[j][2]), "r"(af[j][3]), "r"(bf[2 * j]), "r"(bf[2 * j + 1]));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[slot]);      // every ldmatrix of this warp has been consumed by an issued mma
+        if (ch > 0) {      // (chunk 0 was released in the prologue)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[cons % kSlots]);      // every ldmatrix of this warp has been consumed by an issued mma
+        }
         cons++;
+        if (ch + 1 < n_chunks) {       // A fragments of the next chunk: in flight while this chunk's rows are reduced and published
+            const int slot = cons % kSlots;
+            if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[13] += clock64() - tw0; }
+            else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
+            const uint32_t abase = smem_u32(sm.ring[slot]) + a_off;
+#pragma unroll
+            for (int j = 0; j < KS; j++)
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 256u * j));
+        }
 #pragma unroll
         for (int i = 1; i < NA; i++) { cc[0][0] += cc[i][0]; cc[0][1] += cc[i][1]; cc[0][2] += cc[i][2]; cc[0][3] += cc[i][3]; }
         float v0 = diag ? (odd ? cc[0][1] : cc[0][0]) : 0.f;      // row 2w   : sum over its 8 slices
@@ -478,6 +493,42 @@ __device__ __forceinline__ void attn_pv(const uint8_t *V, int n, int sc_base, fl
         }
     }
 }
+// ---- cross-attention out of a ring slot: one thread per key for the scores (its 128-byte row is read as eight 16-byte
+// pieces in an order rotated by the key index: the 32 lanes of a load touch every bank group equally), one lane per
+// channel pair and one warp per key residue for P.V
+__device__ __forceinline__ float xattn_scores(const uint8_t *K, int n, int sc_base, float lmax) {
+    MegaSmem &sm = SM;
+    for (int j = threadIdx.x; j < n; j += kConsumerThreads) {
+        const uint8_t *row = K + (size_t)j * 128;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            const int c0 = (c + j) & 7, c1 = (c + 1 + j) & 7;
+            const uint4 k0 = *reinterpret_cast<const uint4 *>(row + c0 * 16), k1 = *reinterpret_cast<const uint4 *>(row + c1 * 16);
+            a0 = dot8(k0, *reinterpret_cast<const float4 *>(sm.qkv + c0 * 8), *reinterpret_cast<const float4 *>(sm.qkv + c0 * 8 + 4), a0);
+            a1 = dot8(k1, *reinterpret_cast<const float4 *>(sm.qkv + c1 * 8), *reinterpret_cast<const float4 *>(sm.qkv + c1 * 8 + 4), a1);
+        }
+        const float ds = a0 + a1;
+        sm.sc[sc_base + j] = ds;
+        lmax = fmaxf(lmax, ds);
+    }
+    return lmax;
+}
+__device__ __forceinline__ void xattn_pv(const uint8_t *V, int n, int sc_base, float &o0, float &o1) {
+    MegaSmem &sm = SM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint8_t *col = V + lane * 4;
+    float b0 = 0.f, b1 = 0.f;
+    int j = warp;
+    for (; j + 8 < n; j += 16) {
+        const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)), vb = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)(j + 8) * 128));
+        const float pa = sm.sc[sc_base + j], pb = sm.sc[sc_base + j + 8];
+        o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); b0 = fmaf(pb, vb.x, b0); b1 = fmaf(pb, vb.y, b1);
+    }
+    if (j < n) { const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)); const float pa = sm.sc[sc_base + j]; o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); }
+    o0 += b0; o1 += b1;
+}
+
 // fold the per-lane P.V partial sums of the CTA into 64 channel sums (thread c < 64 returns channel c)
 __device__ __forceinline__ float attn_fold(float (&acc)[8]) {
     MegaSmem &sm = SM;
@@ -494,16 +545,27 @@ __device__ __forceinline__ float attn_fold(float (&acc)[8]) {
     return o;
 }
 
-// self-attention, one CTA per head: past keys/values from the KV cache in L2, the current token's q/k/v
-// from the flagged exchange buffers
+// self-attention, one CTA per head: past keys/values from the KV cache in L2 (the first 128 positions are fetched into
+// registers BEFORE the poll: their addresses do not depend on the current token, so the L2 latency hides behind the wait
+// for q), the current token's q/k/v from the flagged exchange buffers
 __device__ __noinline__ void self_attn(int il, uint32_t ep) {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
     const int h = blockIdx.x, tid = threadIdx.x;
     if (h >= P.H) return;
-    const int n_past = sm.st.pos, d = P.d, l8 = tid & 7;
-    long long tq = clock64();
-#define SS_STAGE(kd, k) { const long long tn = clock64(); if (tid == 0) sm.prof[24 + (kd) * 8 + (k)] += tn - tq; tq = tn; }
+    const int n_past = sm.st.pos, d = P.d, l8 = tid & 7, r8 = tid >> 3;
+    const bool prof_on = P.prof != nullptr && tid == 0;
+    long long tq = prof_on ? clock64() : 0;
+#define SS_STAGE(kd, k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + (kd) * 8 + (k)] += tn - tq; tq = tn; }
+    const uint8_t *Kh = reinterpret_cast<const uint8_t *>(P.self_k + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
+    const uint8_t *Vh = reinterpret_cast<const uint8_t *>(P.self_v + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
+    uint4 kr[4], vr[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = min(u * 32 + r8, max(n_past - 1, 0));      // clamped: rows past the end are fetched but not used
+        kr[u] = __ldcg(reinterpret_cast<const uint4 *>(Kh + (size_t)j * 128 + l8 * 16));
+        vr[u] = __ldcg(reinterpret_cast<const uint4 *>(Vh + (size_t)j * 128 + l8 * 16));
+    }
     if (tid < 96) {   // 3 x 64 flagged floats: q, k, v of this head
         const int which = tid >> 5, i2 = tid & 31;
         const u64 *src = (which == 0 ? P.q1 : which == 1 ? P.kcur : P.vcur) + h * 64 + 2 * i2;
@@ -513,10 +575,18 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
     }
     consumer_sync();
     SS_STAGE(SEG_XV, 0)
-    const uint8_t *Kh = reinterpret_cast<const uint8_t *>(P.self_k + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
-    const uint8_t *Vh = reinterpret_cast<const uint8_t *>(P.self_v + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
     const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
-    float lmax = attn_scores<false>(Kh, n_past, 0, qa, qb, -INFINITY);
+    float lmax = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = u * 32 + r8;
+        float ds = dot8(kr[u], qa, qb, 0.f);
+        ds += __shfl_xor_sync(0xffffffffu, ds, 1);
+        ds += __shfl_xor_sync(0xffffffffu, ds, 2);
+        ds += __shfl_xor_sync(0xffffffffu, ds, 4);
+        if (j < n_past) { if (l8 == 0) sm.sc[j] = ds; lmax = fmaxf(lmax, ds); }
+    }
+    if (n_past > 128) lmax = attn_scores<false>(Kh + 128 * 128, n_past - 128, 128, qa, qb, lmax);
     if (tid < 32) {   // the current token's own key
         float ds = sm.qkv[tid] * sm.qkv[64 + tid] + sm.qkv[32 + tid] * sm.qkv[96 + tid];
         ds = warp_sum(ds);
@@ -530,7 +600,9 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
     const float l = consumer_sum(lsum);
     SS_STAGE(SEG_XV, 2)
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    attn_pv<false>(Vh, n_past, 0, acc);
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int j = u * 32 + r8; if (j < n_past) axpy8(vr[u], sm.sc[j], acc); }
+    if (n_past > 128) attn_pv<false>(Vh + 128 * 128, n_past - 128, 128, acc);
     SS_STAGE(SEG_XV, 3)
     float o = attn_fold(acc);
     if (tid < 64) { o += sm.sc[n_past] * sm.qkv[128 + tid]; ll_store(P.att1 + h * 64 + tid, r16(o / l), ep); }
@@ -544,9 +616,10 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     const MegaParams &P = sm.P;
     const SegTab sk = sm.seg[SEG_XK];
     if (sk.n_chunks == 0) return cons;
-    const int tid = threadIdx.x, lane = tid & 31, l8 = tid & 7;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int ns = P.xsplit, h = blockIdx.x / ns, sp = blockIdx.x % ns, n = sk.rows;
-    long long tq = clock64();
+    const bool prof_on = P.prof != nullptr && tid == 0;
+    long long tq = prof_on ? clock64() : 0;
     if (tid < 32) {
         const u64 *src = P.q2 + h * 64 + 2 * tid;
         ulonglong2 v;
@@ -555,13 +628,13 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     }
     consumer_sync();
     SS_STAGE(SEG_XK, 0)
-    const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
     float lmax = -INFINITY;
     for (int ch = 0; ch < sk.n_chunks; ch++) {
         const int slot = cons % kSlots;
-        { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); if (tid == 0) sm.prof[14] += clock64() - tw0; }
+        if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[14] += clock64() - tw0; }
+        else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
-        lmax = attn_scores<true>(sm.ring[slot], nk, kbase, qa, qb, lmax);
+        lmax = xattn_scores(sm.ring[slot], nk, kbase, lmax);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
@@ -570,20 +643,23 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     const float m = consumer_max(lmax);
     float lsum = 0.f;
     for (int j = tid; j < n; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; lsum += e; }
-    const float l = consumer_sum(lsum);
+    const float l = consumer_sum(lsum);        // its barrier also publishes the probabilities
     SS_STAGE(SEG_XK, 2)
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float o0 = 0.f, o1 = 0.f;
     for (int ch = 0; ch < sk.n_chunks; ch++) {     // the V slice has the same chunking as the K slice
         const int slot = cons % kSlots;
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
-        attn_pv<true>(sm.ring[slot], nk, kbase, acc);
+        xattn_pv(sm.ring[slot], nk, kbase, o0, o1);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
     }
     SS_STAGE(SEG_XK, 3)
-    const float o = attn_fold(acc);
+    *reinterpret_cast<float2 *>(&sm.red[tid >> 5][2 * lane]) = make_float2(o0, o1);
+    consumer_sync();
+    float o = 0.f;
+    if (tid < 64) for (int w = 0; w < kConsumerWarps; w++) o += sm.red[w][tid];
     u64 *out = P.part + ((size_t)h * ns + sp) * 66;
     if (tid < 64) ll_store(out + 2 + tid, o, ep);
     if (tid == 0) { ll_store(out, m, ep); ll_store(out + 1, l, ep); }
@@ -661,8 +737,8 @@ __device__ __noinline__ void lm_epilogue(bool keep, bool sampling, uint32_t ep) 
         const float x = sm.acc[R];
         if (x > -INFINITY) { sa += expf(x - m_all); if (row0 + R >= P.beg) sb += expf(x - ms.v); }
     }
-    sa = consumer_sum(sa);
-    sb = consumer_sum(sb);
+    sa = consumer_sum(sa, 0);
+    sb = consumer_sum(sb, 1);
     if (tid < 8) {
         u64 *rec = P.stats + (size_t)blockIdx.x * 8;
         const float vals[8] = {mt.v, __int_as_float(mt.i), ms.v, __int_as_float(ms.i), sa, sb, 0.f, 0.f};
