@@ -44,6 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(obj_dir, src + ".o")
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if os.environ.get("SS_MEGA_PROFILE"):     # decode kernel with its cycle counters compiled in (tools/mega_prof.py)
+            cmd.insert(1, "-DSS_MEGA_PROFILE=1")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

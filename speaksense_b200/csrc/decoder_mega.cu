@@ -44,6 +44,10 @@ constexpr int kMaxJ = 5;              // flagged pairs per thread and poll batch
 constexpr int kPre = 3;               // chunks per phase whose bias / residual operands are prefetched into registers
 typedef unsigned long long u64;
 constexpr int kProfN = 96;
+#ifndef SS_MEGA_PROFILE
+#define SS_MEGA_PROFILE 0      // 1: per-phase / per-stage cycle counters (tools/mega_prof.py; costs ~13 % of a step)
+#endif
+constexpr bool kProf = SS_MEGA_PROFILE != 0;
 
 enum SegKind : int { SEG_QKV = 0, SEG_O, SEG_CQ, SEG_XK, SEG_XV, SEG_CO, SEG_FC1, SEG_FC2, SEG_LM, SEG_COUNT };
 
@@ -152,6 +156,38 @@ __device__ __forceinline__ ulonglong2 ll_load2(const u64 *p) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
 }
+// f16-valued exchanges (attention outputs, the MLP hidden vector) travel two per word: {epoch << 32 | half2 bits}
+__device__ __forceinline__ void ll_store_h2(u64 *p, float lo, float hi, uint32_t epoch) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    const u64 w = ((u64)epoch << 32) | (u64)(*reinterpret_cast<const uint32_t *>(&h));
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+// poll n_words (even) packed words into dst (shared, 32 bits = one half2 per word); every thread spins only on its own words
+__device__ __noinline__ void poll_packed(const u64 *buf, int n_words, uint32_t epoch, uint32_t *dst) {
+    const int n2 = n_words >> 1, tid = threadIdx.x;
+    const bool prof_on = kProf && SM.P.prof != nullptr && tid == 0;
+    const long long t0 = prof_on ? clock64() : 0;
+    for (int base = 0; base < n2; base += kConsumerThreads * kMaxJ) {
+        ulonglong2 v[kMaxJ];
+        bool all;
+        do {
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) { const int i = base + tid + j * kConsumerThreads; if (i < n2) v[j] = ll_load2(buf + 2 * i); }
+            all = true;
+#pragma unroll
+            for (int j = 0; j < kMaxJ; j++) {
+                const int i = base + tid + j * kConsumerThreads;
+                if (i < n2 && ((uint32_t)(v[j].x >> 32) != epoch || (uint32_t)(v[j].y >> 32) != epoch)) all = false;
+            }
+        } while (!all);
+#pragma unroll
+        for (int j = 0; j < kMaxJ; j++) {
+            const int i = base + tid + j * kConsumerThreads;
+            if (i < n2) reinterpret_cast<uint2 *>(dst)[i] = make_uint2((uint32_t)v[j].x, (uint32_t)v[j].y);
+        }
+    }
+    if (prof_on) SM.prof[0] += clock64() - t0;
+}
 // poll n (even) flagged floats into dst (shared; f32, or f16 when TO_HALF - the values of the non-LayerNorm
 // phases are f16-representable by construction); every thread spins only on its own words.
 // Returns this thread's {sum, sum of squares} of what it fetched (LayerNorm statistics for free).
@@ -159,7 +195,7 @@ template <bool TO_HALF>
 __device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, void *dst) {
     const int n2 = n >> 1, tid = threadIdx.x;
     float s = 0.f, s2 = 0.f;
-    const bool prof_on = SM.P.prof != nullptr && tid == 0;
+    const bool prof_on = kProf && SM.P.prof != nullptr && tid == 0;
     const long long t0 = prof_on ? clock64() : 0;
     for (int base = 0; base < n2; base += kConsumerThreads * kMaxJ) {
         ulonglong2 v[kMaxJ];
@@ -248,7 +284,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = sm.seg[KIND].row0, prows = sm.seg[KIND].prows, n_chunks = sm.seg[KIND].n_chunks;
     __half *buf = sm.xin[ph & 1];
-    const bool prof_on = P.prof != nullptr && tid == 0;
+    const bool prof_on = kProf && P.prof != nullptr && tid == 0;
     long long tq = prof_on ? clock64() : 0;
 #define SS_STAGE(k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + KIND * 8 + (k)] += tn - tq; tq = tn; }
     // ---- static / already-valid operands of the epilogue, fetched now so that their L2 latency hides behind the poll
@@ -350,7 +386,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
         }
     } else {
         const u64 *src = KIND == SEG_O ? P.att1 : KIND == SEG_CO ? P.att2 : P.hbuf;
-        poll_vec<true>(src, KIND == SEG_FC2 ? 4 * D : D, ep_in, buf);
+        poll_packed(src, KIND == SEG_FC2 ? 2 * D : D / 2, ep_in, reinterpret_cast<uint32_t *>(buf));
         SS_STAGE(0)
     }
     consumer_sync();
@@ -402,6 +438,12 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
         float v1 = diag ? (odd ? cc[0][3] : cc[0][2]) : 0.f;      // row 2w+1
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+        float hid = 0.f, hid_hi = 0.f;
+        if (KIND == SEG_FC1) {       // hidden units leave in pairs (this CTA's slice starts and ends on even rows)
+            const float b1 = ch == 0 ? pb[0] : ch == 1 ? pb[1] : ch == 2 ? pb[2] : (lane < 2 ? __ldg(P.layer[il].b[widx] + row0 + min(tile_row<KIND>(ch, warp, lane), prows - 1)) : 0.f);
+            hid = gelu16((lane ? v1 : v0) + b1);
+            hid_hi = __shfl_down_sync(0xffffffffu, hid, 1);
+        }
         if (lane < 2) {
             const int R = tile_row<KIND>(ch, warp, lane);
             if (R < prows) {
@@ -429,7 +471,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
                         }
                     } else if (KIND == SEG_O || KIND == SEG_CO) ll_store(outp + kChunkRows * ch, r + v, ep_out);
                     else if (KIND == SEG_CQ) ll_store(outp + kChunkRows * ch, r16(v * s4), ep_out);
-                    else ll_store(outp + kChunkRows * ch, gelu16(v), ep_out);
+                    else if (lane == 0) ll_store_h2(P.hbuf + ((row0 + R) >> 1), hid, hid_hi, ep_out);
                 }
             }
         }
@@ -554,7 +596,7 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
     const int h = blockIdx.x, tid = threadIdx.x;
     if (h >= P.H) return;
     const int n_past = sm.st.pos, d = P.d, l8 = tid & 7, r8 = tid >> 3;
-    const bool prof_on = P.prof != nullptr && tid == 0;
+    const bool prof_on = kProf && P.prof != nullptr && tid == 0;
     long long tq = prof_on ? clock64() : 0;
 #define SS_STAGE(kd, k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + (kd) * 8 + (k)] += tn - tq; tq = tn; }
     const uint8_t *Kh = reinterpret_cast<const uint8_t *>(P.self_k + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
@@ -605,7 +647,11 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
     if (n_past > 128) attn_pv<false>(Vh + 128 * 128, n_past - 128, 128, acc);
     SS_STAGE(SEG_XV, 3)
     float o = attn_fold(acc);
-    if (tid < 64) { o += sm.sc[n_past] * sm.qkv[128 + tid]; ll_store(P.att1 + h * 64 + tid, r16(o / l), ep); }
+    if (tid < 64) {
+        o = (o + sm.sc[n_past] * sm.qkv[128 + tid]) / l;
+        const float o_hi = __shfl_down_sync(0xffffffffu, o, 1);
+        if ((tid & 1) == 0) ll_store_h2(P.att1 + h * 32 + (tid >> 1), o, o_hi, ep);
+    }
     SS_STAGE(SEG_XV, 4)
 }
 
@@ -618,7 +664,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     if (sk.n_chunks == 0) return cons;
     const int tid = threadIdx.x, lane = tid & 31;
     const int ns = P.xsplit, h = blockIdx.x / ns, sp = blockIdx.x % ns, n = sk.rows;
-    const bool prof_on = P.prof != nullptr && tid == 0;
+    const bool prof_on = kProf && P.prof != nullptr && tid == 0;
     long long tq = prof_on ? clock64() : 0;
     if (tid < 32) {
         const u64 *src = P.q2 + h * 64 + 2 * tid;
@@ -676,7 +722,8 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
             const float pm = sm.xs[s2 * 66];
             if (pm > -INFINITY) { const float e = __expf(pm - M); Lsum += sm.xs[s2 * 66 + 1] * e; oo += sm.xs[s2 * 66 + 2 + tid] * e; }
         }
-        ll_store(P.att2 + h * 64 + tid, r16(oo / Lsum), ep);
+        const float a = oo / Lsum, a_hi = __shfl_down_sync(0xffffffffu, a, 1);
+        if ((tid & 1) == 0) ll_store_h2(P.att2 + h * 32 + (tid >> 1), a, a_hi, ep);
     }
     consumer_sync();
     SS_STAGE(SEG_XK, 5)
@@ -835,7 +882,8 @@ __device__ void build_segtab() {
         } else {
             const int N = kind == SEG_QKV ? 3 * d : kind == SEG_FC1 ? 4 * d : kind == SEG_LM ? P.n_vocab : d;
             const int kq = kind == SEG_FC2 ? 4 : 1;
-            s.row0 = (int)((long)cta * N / ncta); s.rows = (int)((long)(cta + 1) * N / ncta) - s.row0;
+            const int unit = kind == SEG_FC1 ? 2 : 1;     // FC1 publishes its rows in pairs
+            s.row0 = unit * (int)((long)cta * (N / unit) / ncta); s.rows = unit * (int)((long)(cta + 1) * (N / unit) / ncta) - s.row0;
             s.row_bytes = d * 2; s.prows = s.rows * kq;      // rows of d halfs: FC2's 4d-long rows count as 4
             s.rows_per_chunk = kChunkRows;
         }
@@ -876,8 +924,8 @@ __device__ __noinline__ uint32_t consumer_main(const ConsArgs a) {
 #pragma unroll 1
         for (int il = 0; il < L; il++) {
             const uint32_t ep = ep0 + (uint32_t)il;
-            long long tp = clock64();
-#define SS_PROF_PHASE(k) { const long long tn = clock64(); if (tid == 0) sm.prof[4 + (k)] += tn - tp; tp = tn; }
+            long long tp = kProf ? clock64() : 0;
+#define SS_PROF_PHASE(k) if (kProf) { const long long tn = clock64(); if (tid == 0) sm.prof[4 + (k)] += tn - tp; tp = tn; }
             cons = gemv_phase<KS, SEG_QKV>(cons, il, ep, ep, ph++);       SS_PROF_PHASE(0)
             self_attn(il, ep);                                  SS_PROF_PHASE(1)
             cons = gemv_phase<KS, SEG_O>(cons, il, ep, ep, ph++);         SS_PROF_PHASE(2)
@@ -887,7 +935,7 @@ __device__ __noinline__ uint32_t consumer_main(const ConsArgs a) {
             cons = gemv_phase<KS, SEG_FC1>(cons, il, ep, ep, ph++);       SS_PROF_PHASE(6)
             cons = gemv_phase<KS, SEG_FC2>(cons, il, ep, ep + 1, ph++);   SS_PROF_PHASE(7)
         }
-        long long tp = clock64();
+        long long tp = kProf ? clock64() : 0;
 
         // ---------------- final LN + LM head + per-CTA softmax statistics ----------------
         const uint32_t epL = ep0 + (uint32_t)L;
@@ -902,11 +950,11 @@ __device__ __noinline__ uint32_t consumer_main(const ConsArgs a) {
         }
         if (jrel < n_prompt - 1) {   // prompt token: feed the next one
             consumer_sync();
-            if (tid == 0) { sm.st.token = ctl->prompt[jrel + 1]; sm.st.pos = sm.st.pos + 1; sm.prof[12] += clock64() - tp; }
+            if (tid == 0) { sm.st.token = ctl->prompt[jrel + 1]; sm.st.pos = sm.st.pos + 1; if (kProf) sm.prof[12] += clock64() - tp; }
             consumer_sync();
             continue;
         }
-        if (!do_sample) { consumer_sync(); if (tid == 0) { sm.st.done = 1; sm.prof[12] += clock64() - tp; } consumer_sync(); break; }
+        if (!do_sample) { consumer_sync(); if (tid == 0) { sm.st.done = 1; if (kProf) sm.prof[12] += clock64() - tp; } consumer_sync(); break; }
         sample_and_update(seek, seek_end, n_max, epL);
         SS_PROF_PHASE(8)
 #undef SS_PROF_PHASE

@@ -1,6 +1,7 @@
 """Decode-kernel cycle breakdown (SS_MEGA_PROF=1): python tools/mega_prof.py [shape] [steps]"""
 import os, sys
-os.environ["SS_MEGA_PROF"] = "1"
+if not os.environ.get("SS_NO_PROF"):
+    os.environ["SS_MEGA_PROF"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from speaksense_b200 import AsrParams, WhisperAsr, synth  # noqa: E402
