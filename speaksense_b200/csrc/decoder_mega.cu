@@ -257,6 +257,11 @@ __device__ __forceinline__ float ll_value(const u64 *p) {      // a flagged word
 
 // index, inside the CTA's slice, of the row (FC2: quarter row) that finishing lane `l01` of `warp` publishes in chunk `ch`.
 // FC2: warp w works on quarter w & 3 of the rows {2 * (w >> 2), 2 * (w >> 2) + 1} of every 4-row chunk.
+// Surplus threads of a per-thread batch re-read a word from the start of the vector (instead of predicating the load off, which
+// would push the register arrays to local memory).  They must NOT all pick the same word: 148 CTAs x 4 warps asking one L2
+// sector for the same 16 bytes are served one request per clock (measured: tools/xchg_bench2.cu, d = 256 case).
+__device__ __forceinline__ int wrap_idx(int i, int n) { return i >= n ? i - n : i; }
+
 template <int KIND>
 __device__ __forceinline__ int tile_row(int ch, int warp, int l01) {
     return KIND == SEG_FC2 ? kChunkRows * ch + 4 * (2 * (warp >> 2) + l01) + (warp & 3) : kChunkRows * ch + 2 * warp + l01;
@@ -339,7 +344,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
         float2 w2[NK], b2[NK], xv[NK];
 #pragma unroll
         for (int k = 0; k < NK; k++) {      // (indices clamped instead of predicated: the arrays stay in registers)
-            const int i = min(tid + k * kConsumerThreads, n2 - 1);
+            const int i = wrap_idx(tid + k * kConsumerThreads, n2);
             w2[k] = __ldg(reinterpret_cast<const float2 *>(lw) + i); b2[k] = __ldg(reinterpret_cast<const float2 *>(lb) + i);
         }
         if (KIND == SEG_QKV && il == 0) {           // token embedding + positional embedding
@@ -347,7 +352,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
             const float2 *pe = reinterpret_cast<const float2 *>(P.d_pos + (size_t)pos * D);
 #pragma unroll
             for (int k = 0; k < NK; k++) {
-                const int i = min(tid + k * kConsumerThreads, n2 - 1);
+                const int i = wrap_idx(tid + k * kConsumerThreads, n2);
                 const float2 ev = __half22float2(__ldg(e + i)), pv = __ldg(pe + i); xv[k] = make_float2(ev.x + pv.x, ev.y + pv.y);
             }
         } else {
@@ -357,7 +362,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
             bool all;
             do {
 #pragma unroll
-                for (int k = 0; k < NK; k++) v[k] = ll_load2(src + 2 * min(tid + k * kConsumerThreads, n2 - 1));
+                for (int k = 0; k < NK; k++) v[k] = ll_load2(src + 2 * wrap_idx(tid + k * kConsumerThreads, n2));
                 all = true;
 #pragma unroll
                 for (int k = 0; k < NK; k++)

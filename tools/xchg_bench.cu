@@ -47,15 +47,20 @@ __global__ void __launch_bounds__(256, 1) xchg_kernel(u64 *buf, unsigned *counte
     for (int it = 1; it <= iters; it++) {
         u64 *b = buf + (size_t)(it % 3) * d;
         // publish
-        if (mode == 2) {
+        const int R = mode >= 30 && mode < 40 ? (1 << (mode - 30)) : 1;
+        if (mode >= 30 && mode < 40) {      // R replicas of the vector; CTA c reads replica c % R
+            u64 *bb = buf + (size_t)(it % 3) * d * R;
+            for (int t = tid; t < rows * R; t += 256) ll_store(bb + (size_t)(t / rows) * d + row0 + (t % rows), accv + (t % rows), (unsigned)it);
+            b = bb + (size_t)(cta % R) * d;
+        } else if (mode == 2) {
             if (tid < rows) b[row0 + tid] = (u64)__float_as_uint(accv + tid);
             __syncthreads();
             if (tid == 0) { __threadfence(); atomicAdd(counter + (it % 3) * 32, 1u); }
         } else if (mode >= 10 && mode < 20) { if (tid < rows) ll_store_flavour(b + row0 + tid, accv + tid, (unsigned)it, mode - 10); }
         else if (mode == 21) { if (tid < rows) ll_store(b + row0 + tid, accv + tid, (unsigned)it); }
-        else if (tid < rows) ll_store(b + row0 + tid, accv + tid, (unsigned)it);
+        else for (int t = tid; t < rows; t += 256) ll_store(b + row0 + t, accv + t, (unsigned)it);
         // gather
-        if (mode == 0 || mode == 4 || (mode >= 10 && mode < 20)) {
+        if (mode == 0 || mode == 4 || (mode >= 10 && mode < 20) || (mode >= 30 && mode < 40)) {
             ulonglong2 v[3]; bool all;
             do {
                 all = true;
@@ -141,7 +146,7 @@ int main(int argc, char **argv) {
     cudaSetDevice(dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     u64 *buf; unsigned *counter; long long *out;
-    cudaMalloc(&buf, (size_t)3 * 8192 * 8); cudaMalloc(&counter, 3 * 32 * 4); cudaMalloc(&out, sms * 8);
+    cudaMalloc(&buf, (size_t)3 * 8192 * 8 * 16); cudaMalloc(&counter, 3 * 32 * 4); cudaMalloc(&out, sms * 8);
     long long *h = (long long *)malloc(sms * 8);
     {
         cudaMemset(buf, 0, 4096);
@@ -153,13 +158,14 @@ int main(int argc, char **argv) {
             cudaMemset(buf, 0, 4096);
         }
     }
-    const int modes[] = {0, 1, 2, 3, 4, 10, 11, 12, 13, 14, 15, 20, 21};
-    for (int rep = 0; rep < 2; rep++)
+    const int modes[] = {0, 20};
+    const int grids[] = {2, 4, 8, 16, 32, 64, 100, 148};
+    for (int gi = 0; gi < 8; gi++) { sms = grids[gi];
         for (int mi = 0; mi < (int)(sizeof(modes) / sizeof(int)); mi++) {
             const int mode = modes[mi];
             for (int work = 0; work <= (mode == 4 ? 2000 : 0); work += 1000) {
                 if (mode == 4 && work == 0) continue;
-                cudaMemset(buf, 0, (size_t)3 * 8192 * 8); cudaMemset(counter, 0, 3 * 32 * 4);
+                cudaMemset(buf, 0, (size_t)3 * 8192 * 8 * 16); cudaMemset(counter, 0, 3 * 32 * 4);
                 int dd = d, it = iters, md = mode, wk = work;
                 void *args[] = {&buf, &counter, &dd, &it, &md, &wk, &out};
                 cudaError_t e = cudaLaunchCooperativeKernel((const void *)xchg_kernel, dim3(sms), dim3(256), args, 0, 0);
@@ -171,5 +177,6 @@ int main(int argc, char **argv) {
                 printf("d=%d mode=%d work=%d: %.0f cycles per exchange (%d CTAs)\n", d, mode, work, (double)mx / iters - work, sms);
             }
         }
+    }
     return 0;
 }

@@ -1,0 +1,77 @@
+// xchg_bench2.cu - all-to-all flagged exchange: scaling with CTA count, poll flavour and vector length (bounded spins)
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+typedef unsigned long long u64;
+__device__ __forceinline__ void ll_store(u64 *p, float v, unsigned ep) {
+    const u64 w = ((u64)ep << 32) | (u64)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+template <int FL> __device__ __forceinline__ ulonglong2 ld2(const u64 *p) {
+    ulonglong2 v;
+    if (FL == 0) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    else if (FL == 1) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    else if (FL == 2) asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    else asm volatile("ld.global.cv.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+// every CTA publishes its slice of d flagged words, then gathers all d (each of `pollers` threads polls NP pairs per batch)
+template <int FL>
+__global__ void __launch_bounds__(256, 1) k(u64 *buf, int d, int iters, int pollers, int *err, long long *out) {
+    const int cta = blockIdx.x, ncta = gridDim.x, tid = threadIdx.x;
+    const int row0 = (int)((long)cta * d / ncta), rows = (int)((long)(cta + 1) * d / ncta) - row0;
+    const int n2 = d / 2;
+    __shared__ float xs[8192];
+    float accv = 0.f;
+    cooperative_groups::this_grid().sync();
+    const long long t0 = clock64();
+    for (int it = 1; it <= iters; it++) {
+        u64 *b = buf + (size_t)(it % 3) * d;
+        for (int t = tid; t < rows; t += 256) ll_store(b + row0 + t, accv + t, (unsigned)it);
+        if (tid < pollers) {
+            for (int base = 0; base < n2; base += pollers * 3) {
+                ulonglong2 v[3]; bool all; int spins = 0;
+                do {
+                    all = true;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) { const int i = min(base + tid + q * pollers, n2 - 1); v[q] = ld2<FL>(b + 2 * i); }
+#pragma unroll
+                    for (int q = 0; q < 3; q++) if ((unsigned)(v[q].x >> 32) != (unsigned)it || (unsigned)(v[q].y >> 32) != (unsigned)it) all = false;
+                    if (++spins > 2000000) { *err = 1; all = true; }
+                } while (!all);
+#pragma unroll
+                for (int q = 0; q < 3; q++) { const int i = base + tid + q * pollers; if (i < n2) { xs[2 * i] = __uint_as_float((unsigned)v[q].x); xs[2 * i + 1] = __uint_as_float((unsigned)v[q].y); } }
+            }
+        }
+        __syncthreads();
+        accv = xs[(tid * 7 + it) % d] * 0.5f;
+        __syncthreads();
+        if (*(volatile int *)err) break;
+    }
+    if (tid == 0) out[cta] = clock64() - t0;
+    if (accv == 12345.678f) out[0] = 0;
+}
+int main() {
+    u64 *buf; int *err; long long *out;
+    cudaMalloc(&buf, (size_t)3 * 8192 * 8); cudaMalloc(&err, 4); cudaMalloc(&out, 148 * 8);
+    long long h[148];
+    const int iters = 1000;
+    auto run = [&](int fl, int grid, int d, int pollers) {
+        cudaMemset(buf, 0, (size_t)3 * 8192 * 8); cudaMemset(err, 0, 4);
+        void *args[] = {&buf, &d, (void *)&iters, &pollers, &err, &out};
+        const void *f = fl == 0 ? (const void *)k<0> : fl == 1 ? (const void *)k<1> : fl == 2 ? (const void *)k<2> : (const void *)k<3>;
+        cudaError_t e = cudaLaunchCooperativeKernel(f, dim3(grid), dim3(256), args, 0, 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        int he = 0; cudaMemcpy(&he, err, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, out, grid * 8, cudaMemcpyDeviceToHost);
+        long long mx = 0; for (int i = 0; i < grid; i++) mx = h[i] > mx ? h[i] : mx;
+        printf("ld=%d grid=%3d d=%4d pollers=%3d: %6.0f cycles per exchange%s%s\n", fl, grid, d, pollers, (double)mx / iters, he ? "  [SPIN LIMIT HIT]" : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
+        fflush(stdout);
+    };
+    for (int grid : {2, 4, 8, 16, 32, 64, 100, 148}) run(0, grid, 1280, 256);
+    for (int fl : {1, 2, 3}) run(fl, 148, 1280, 256);
+    for (int d : {256, 512, 2560, 5120}) run(0, 148, d, 256);
+    for (int pollers : {32, 64, 128}) run(0, 148, 1280, pollers);
+    return 0;
+}
