@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 METRIC = "real-time factor (audio-sec/wall-sec) large-v3 30s clip"
 UNIT = "x realtime (audio s / wall s)"
 CLIP_SEC = 30.0
-NCU_DRAM_BYTES_PER_TOKEN = (29.550240e9 + 7.459328e6) / 16   # ncu --set full capture, round 1
+NCU_DRAM_BYTES_PER_TOKEN = (29.549974e9 + 6.441216e6) / 16   # ncu --set full capture of one 16-step launch (profiles/r1b_ncu_decode_mega.txt)
 MODEL_DIR = os.environ.get("SS_MODEL_DIR", "/tmp/ss_models")
 
 
@@ -263,7 +263,7 @@ def main():
     achieved = bytes_tok / (step_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "decode_mega_kernel (persistent cooperative kernel; per-token time of one %d-step launch)" % n_probe,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 16-step launch / 16 (profiles/r1_ncu_decode_mega.txt)
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 16-step launch / 16 (profiles/r1b_ncu_decode_mega.txt)
                 "traffic": NCU_DRAM_BYTES_PER_TOKEN if args.shape == "large-v3" else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_tok, "launch_ms": step_ms,
                 "decode_share_of_step": stage["decode_ms"] / max(ms_total, 1e-9)}
