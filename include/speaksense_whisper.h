@@ -89,6 +89,25 @@ int  ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *con
  * HBM once, ss_transcribe_resident runs the same path without the host->device copy. */
 int  ss_upload_pcm(ss_engine *e, ss_state *s, const float *pcm, size_t n_samples);
 int  ss_transcribe_resident(ss_engine *e, ss_state *s, const ss_params *p);
+/* ---- audio denoise in front of the hot path ----
+ * == DenoiseConfig (src/audio/mod.rs:41-62; defaults :51-61) */
+typedef struct ss_denoise_config {
+    int   frame_size;               /* 2048 (power of two, <= 4096) */
+    float overlap;                  /* 0.75 */
+    float strength;                 /* 0.2 */
+    float noise_gate;               /* 0.003 (StreamAudioProcessor only) */
+    int   enable_noise_reduction;   /* 1     (StreamAudioProcessor only) */
+    float threshold;                /* 0.002 (never read by the reference) */
+} ss_denoise_config;
+void ss_denoise_config_default(ss_denoise_config *c);
+/* == denoise_audio(&samples, &config) (src/audio/mod.rs:507-528), as called per 5 s chunk by the gRPC handler
+ *    (grpc/handlers/asr.rs:196) right before transcribe_with_state: noise-type analysis, spectral subtraction and / or
+ *    Wiener filter over Hann STFT frames, overlap-add with the reference's scaling (unnormalised inverse FFT, x10).
+ *    pcm: HOST f32.  The denoised chunk stays resident in HBM as the state's PCM, so the caller may follow with
+ *    ss_transcribe_resident (no second host->device copy); `out` (HOST, n_samples floats) may be NULL.
+ *    noise_type: 0 stationary, 1 non-stationary, 2 mixed.  Error if n_samples < frame_size (the reference panics). */
+int  ss_denoise_audio(ss_engine *e, ss_state *s, const float *pcm, size_t n_samples, const ss_denoise_config *cfg,
+                      float *out, int *noise_type, float *spectral_variance);
 /* Replays the decode-step CUDA graph n_steps times at positions n_past0.. (dummy tokens) and returns
  * the device time per step (CUDA events on the state's stream): the roofline probe of stage 3. */
 int  ss_bench_decode_steps(ss_engine *e, ss_state *s, int n_steps, int n_past0, float *ms_per_step);

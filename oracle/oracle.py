@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libwhisper_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("whisper_oracle.c", "whisper_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("whisper_oracle.c", "whisper_oracle.h", "audio_oracle.c", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
@@ -195,3 +195,73 @@ class OracleState:
             return np.zeros((0, nv), np.float32)
         p = self.L.wo_kept_logits(self.h, 0)
         return np.ctypeslib.as_array(p, shape=(n, nv)).copy()
+
+
+# ---- audio pre-processing oracle (oracle/audio_oracle.c: /root/reference/src/audio/mod.rs restated) ----
+def _audio_lib():
+    L = lib()
+    if not getattr(L, "_audio_ready", False):
+        L.ao_analyze_noise.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
+        L.ao_denoise_audio.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.ao_estimate_noise_floor.restype = C.c_float
+        L.ao_estimate_noise_floor.argtypes = [C.c_void_p, C.c_size_t]
+        L.ao_normalize_audio.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ao_process_frame.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        L._audio_ready = True
+    return L
+
+
+def analyze_noise(samples, frame_size: int = 2048):
+    """-> (noise type 0 stationary / 1 non-stationary / 2 mixed, normalised spectral variance)"""
+    x = np.ascontiguousarray(samples, dtype=np.float32)
+    nv = C.c_float()
+    t = _audio_lib().ao_analyze_noise(x.ctypes.data, x.size, frame_size, C.byref(nv))
+    return t, float(nv.value)
+
+
+def denoise_audio(samples, frame_size: int = 2048, overlap: float = 0.75, strength: float = 0.2):
+    """reference denoise_audio (audio/mod.rs:507-528) -> (f32 samples, noise type)"""
+    x = np.ascontiguousarray(samples, dtype=np.float32)
+    out = np.zeros_like(x)
+    t = _audio_lib().ao_denoise_audio(x.ctypes.data, x.size, frame_size, overlap, strength, out.ctypes.data)
+    if t < 0:
+        raise ValueError("denoise_audio: fewer samples than one frame (the reference panics here)")
+    return out, t
+
+
+class StreamAudioProcessor:
+    """reference StreamAudioProcessor (audio/mod.rs:80-155): per-chunk peak normalisation, 2048-sample frames,
+    VAD gain, denoise, noise gate; returns the list of processed frames of each call."""
+
+    def __init__(self, frame_size=2048, overlap=0.75, strength=0.2, noise_gate=0.003, enable_noise_reduction=True):
+        self.cfg = (frame_size, overlap, strength, noise_gate, enable_noise_reduction)
+        self.buffer = np.zeros(0, np.float32)
+        self.state = np.zeros(2, np.float32)        # noise_floor, prev_energy
+
+    def _frame(self, frame):
+        fs, ov, st, ng, nr = self.cfg
+        out = np.zeros(fs, np.float32)
+        f = np.ascontiguousarray(frame, np.float32)
+        _audio_lib().ao_process_frame(f.ctypes.data, fs, ov, st, ng, int(nr), self.state.ctypes.data, out.ctypes.data)
+        return out
+
+    def process_chunk(self, chunk):
+        x = np.ascontiguousarray(chunk, np.float32)
+        norm = np.zeros_like(x)
+        _audio_lib().ao_normalize_audio(x.ctypes.data, x.size, norm.ctypes.data)
+        self.buffer = np.concatenate([self.buffer, norm])
+        fs = self.cfg[0]
+        frames = []
+        while self.buffer.size >= fs:
+            frames.append(self._frame(self.buffer[:fs]))
+            self.buffer = self.buffer[fs:]
+        return frames
+
+    def finish(self):
+        fs = self.cfg[0]
+        if self.buffer.size == 0:
+            return []
+        frame = np.zeros(fs, np.float32)
+        frame[:self.buffer.size] = self.buffer
+        self.buffer = np.zeros(0, np.float32)
+        return [self._frame(frame)]

@@ -104,6 +104,21 @@ int ss_upload_pcm(ss_engine *e, ss_state *s, const float *pcm, size_t n) {
         return 0;
     });
 }
+void ss_denoise_config_default(ss_denoise_config *c) {
+    if (!c) return;
+    c->frame_size = 2048; c->overlap = 0.75f; c->strength = 0.2f; c->noise_gate = 0.003f; c->enable_noise_reduction = 1; c->threshold = 0.002f;
+}
+int ss_denoise_audio(ss_engine *e, ss_state *s, const float *pcm, size_t n, const ss_denoise_config *cfg, float *out, int *noise_type, float *spectral_variance) {
+    return guard([&]() -> int {
+        if (!e || !s || !pcm) SS_THROW(SS_ERR_INVALID, "null argument");
+        if (s->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
+        ss_denoise_config c; ss_denoise_config_default(&c);
+        if (cfg) c = *cfg;
+        const int t = denoise_audio(*s->s, pcm, n, c.frame_size, c.overlap, c.strength, out, spectral_variance);
+        if (noise_type) *noise_type = t;
+        return 0;
+    });
+}
 int ss_transcribe_resident(ss_engine *e, ss_state *s, const ss_params *p) {
     return guard([&]() -> int {
         if (!e || !s) SS_THROW(SS_ERR_INVALID, "null argument");

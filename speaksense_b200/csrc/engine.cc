@@ -225,6 +225,8 @@ State::~State() {
     if (h_pcm) cudaFreeHost(h_pcm);
     if (h_logits) cudaFreeHost(h_logits);
     for (auto &e : ev) if (e) cudaEventDestroy(e);
+    if (d_pcm_alt) cudaFree(d_pcm_alt);
+    if (d_dn) cudaFree(d_dn);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -234,6 +236,7 @@ State::~State() {
 void upload_pcm(State &s, const float *pcm, size_t n) {
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     if (n + 1 > s.pcm_cap) {
+        if (s.d_pcm_alt) { cudaFree(s.d_pcm_alt); s.d_pcm_alt = nullptr; }
         if (s.d_pcm) cudaFree(s.d_pcm);
         s.pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
         s.d_pcm = dmalloc<float>(s.pcm_cap);
@@ -248,6 +251,24 @@ void upload_pcm(State &s, const float *pcm, size_t n) {
     s.n_resident = n;
 }
 
+int denoise_audio(State &s, const float *pcm, size_t n, int frame_size, float overlap, float strength, float *out, float *nv_out) {
+    upload_pcm(s, pcm, n);
+    const size_t need = denoise_scratch_floats(n, frame_size, overlap);
+    if (need > s.dn_cap || !s.d_pcm_alt) {
+        if (s.d_dn) cudaFree(s.d_dn);
+        if (s.d_pcm_alt) cudaFree(s.d_pcm_alt);
+        s.dn_cap = need; s.d_dn = dmalloc<float>(need); s.d_pcm_alt = dmalloc<float>(s.pcm_cap);
+    }
+    const int type = denoise_enqueue(s.d_pcm, n, frame_size, overlap, strength, s.d_pcm_alt, s.d_dn, s.stream, &s.n_launches, nv_out);
+    std::swap(s.d_pcm, s.d_pcm_alt);      // the denoised chunk is now the resident PCM (ss_transcribe_resident)
+    if (out) {
+        CUDA_CHECK(cudaMemcpyAsync(s.h_pcm, s.d_pcm, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        memcpy(out, s.h_pcm, n * sizeof(float));
+    } else CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    return type;
+}
+
 void run_log_mel(State &s, const float *pcm, size_t n) {
     const Model &m = s.engine->model;
     CUDA_CHECK(cudaSetDevice(s.engine->device));
@@ -260,6 +281,7 @@ void run_log_mel(State &s, const float *pcm, size_t n) {
         return;
     }
     if (n + 1 > s.pcm_cap) {
+        if (s.d_pcm_alt) { cudaFree(s.d_pcm_alt); s.d_pcm_alt = nullptr; }
         if (s.d_pcm) cudaFree(s.d_pcm);
         s.pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
         s.d_pcm = dmalloc<float>(s.pcm_cap);

@@ -59,6 +59,7 @@ struct State {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // audio / mel
     float *d_pcm = nullptr; size_t pcm_cap = 0; size_t n_resident = 0; float *h_pcm = nullptr; size_t h_pcm_cap = 0;
+    float *d_pcm_alt = nullptr; float *d_dn = nullptr; size_t dn_cap = 0;   // denoise: output buffer (swapped with d_pcm), scratch
     float *d_mel = nullptr; size_t mel_cap = 0; int n_len = 0, n_len_org = 0; int *d_max = nullptr;
     // encoder scratch (one window)
     __half *win = nullptr, *x1 = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *enc16 = nullptr;
@@ -87,6 +88,8 @@ void nccl_unique_id(unsigned char out[128]);
 State *state_new(const std::shared_ptr<Engine> &e);
 
 void upload_pcm(State &s, const float *pcm, size_t n);
+// reference denoise_audio on the device: host PCM in, the denoised chunk stays resident (and is copied to `out` if given)
+int denoise_audio(State &s, const float *pcm, size_t n, int frame_size, float overlap, float strength, float *out, float *nv_out);
 void run_log_mel(State &s, const float *pcm, size_t n);   // pcm == nullptr: use the resident PCM
 float bench_decode_steps(State &s, int n_steps, int n_past0);
 void run_encode(State &s, int seek);

@@ -17,6 +17,12 @@ void mel_window_enqueue(const Model &m, const float *d_mel, int n_len, int seek,
 inline int mel_n_len(size_t n_samples) { return (int)((n_samples + (size_t)kSampleRate * kChunkSec) / kHop); }
 inline int mel_n_len_org(size_t n_samples) { return 1 + (int)(((long)n_samples + kNFft / 2 - kNFft) / kHop); }
 
+// ---------------------------------------------------------------- audio denoise (denoise.cu; reference src/audio/mod.rs:507-735)
+size_t denoise_scratch_floats(size_t n, int frame_size, float overlap);
+// denoise_audio(d_in[0..n)) -> d_out on `st`; returns the noise type (0 stationary / 1 non-stationary / 2 mixed)
+int denoise_enqueue(const float *d_in, size_t n, int frame_size, float overlap, float strength, float *d_out, float *scratch,
+                    cudaStream_t st, int *launches, float *nv_out);
+
 // ---------------------------------------------------------------- tcgen05 GEMM (gemm_sm100.cu)
 struct GemmOperand {        // a K-major (or, for B, MN-major) f16 operand described as up to 4-D strided view
     const __half *ptr = nullptr;
