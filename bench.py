@@ -268,6 +268,21 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_tok, "launch_ms": step_ms,
                 "decode_share_of_step": stage["decode_ms"] / max(ms_total, 1e-9)}
 
+    # ---------------- denoise of one 5 s stream chunk (the gRPC handler's shape), host buffer in,
+    #                  denoised chunk left resident for the transcribe that follows ----------------
+    f1 = None
+    if rank == 0:
+        from speaksense_b200 import denoise_audio
+        chunk = np.ascontiguousarray(pcm[:80000])
+        for _ in range(3):
+            denoise_audio(eng, state, chunk, fetch=False)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            _, ntype, _ = denoise_audio(eng, state, chunk, fetch=False)
+        f1 = {"row": "f1 denoise_audio (src/audio/mod.rs:507-528), one 5 s chunk = 80000 samples, 153 STFT frames of 2048",
+              "gpu_ms_per_chunk_e2e": (time.perf_counter() - t0) / 20 * 1e3, "noise_type": ntype,
+              "h2d_bytes": int(chunk.size * 4), "note": "latency-bound (320 KB chunk); includes H2D, one 8-byte D2H for the noise type, stream sync"}
+
     if rank == 0:
         value = world * args.steps * CLIP_SEC / (ms_total * 1e-3)
         e2e = world * args.steps * CLIP_SEC / (ms_e2e * 1e-3)
@@ -295,6 +310,16 @@ def main():
                                         "tokens_match_gpu": rr["tokens"] == toks}
             except Exception as ex:   # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": "failed: %s" % ex}
+            try:
+                from oracle import oracle
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    oracle.denoise_audio(chunk)
+                f1["cpu_port_ms_per_chunk"] = (time.perf_counter() - t0) / 3 * 1e3
+                f1["cpu_cores"] = 1
+            except Exception:   # noqa: BLE001
+                pass
+        line["next_rows"] = {"f1_denoise": f1}
         print(json.dumps(line), flush=True)
     state.close()
     eng.close()
