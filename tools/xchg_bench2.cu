@@ -29,22 +29,28 @@ __global__ void __launch_bounds__(256, 1) k(u64 *buf, int d, int iters, int poll
     for (int it = 1; it <= iters; it++) {
         u64 *b = buf + (size_t)(it % 3) * d;
         for (int t = tid; t < rows; t += 256) ll_store(b + row0 + t, accv + t, (unsigned)it);
-        if (tid < pollers) {
-            for (int base = 0; base < n2; base += pollers * 3) {
+        const bool pair_mode = pollers < 0;
+        const int np_ = pair_mode ? -pollers : pollers;
+        u64 *go = buf + (size_t)3 * 8192 - 1024 + 2 * (cta >> 1);      // one flag word per CTA pair
+        if (pair_mode && (cta & 1)) {      // odd CTA of a pair: waits for its partner's go flag (stand-in for a DSMEM hand-off)
+            if (tid == 0) { int spins = 0; while ((unsigned)(ld2<FL>(go).x >> 32) != (unsigned)it) { if (++spins > 2000000) { *err = 1; break; } } }
+        } else if (tid < np_) {
+            for (int base = 0; base < n2; base += np_ * 3) {
                 ulonglong2 v[3]; bool all; int spins = 0;
                 do {
                     all = true;
 #pragma unroll
-                    for (int q = 0; q < 3; q++) { const int i = min(base + tid + q * pollers, n2 - 1); v[q] = ld2<FL>(b + 2 * i); }
+                    for (int q = 0; q < 3; q++) { const int i = min(base + tid + q * np_, n2 - 1); v[q] = ld2<FL>(b + 2 * i); }
 #pragma unroll
                     for (int q = 0; q < 3; q++) if ((unsigned)(v[q].x >> 32) != (unsigned)it || (unsigned)(v[q].y >> 32) != (unsigned)it) all = false;
                     if (++spins > 2000000) { *err = 1; all = true; }
                 } while (!all);
 #pragma unroll
-                for (int q = 0; q < 3; q++) { const int i = base + tid + q * pollers; if (i < n2) { xs[2 * i] = __uint_as_float((unsigned)v[q].x); xs[2 * i + 1] = __uint_as_float((unsigned)v[q].y); } }
+                for (int q = 0; q < 3; q++) { const int i = base + tid + q * np_; if (i < n2) { xs[2 * i] = __uint_as_float((unsigned)v[q].x); xs[2 * i + 1] = __uint_as_float((unsigned)v[q].y); } }
             }
         }
         __syncthreads();
+        if (pair_mode && !(cta & 1) && tid == 0) ll_store(go, 1.f, (unsigned)it);
         accv = xs[(tid * 7 + it) % d] * 0.5f;
         __syncthreads();
         if (*(volatile int *)err) break;
@@ -69,9 +75,10 @@ int main() {
         printf("ld=%d grid=%3d d=%4d pollers=%3d: %6.0f cycles per exchange%s%s\n", fl, grid, d, pollers, (double)mx / iters, he ? "  [SPIN LIMIT HIT]" : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
         fflush(stdout);
     };
-    for (int grid : {2, 4, 8, 16, 32, 64, 100, 148}) run(0, grid, 1280, 256);
-    for (int fl : {1, 2, 3}) run(fl, 148, 1280, 256);
-    for (int d : {256, 512, 2560, 5120}) run(0, 148, d, 256);
-    for (int pollers : {32, 64, 128}) run(0, 148, 1280, pollers);
+    for (int rep = 0; rep < 2; rep++) {
+        run(0, 148, 1280, 256);
+        run(0, 148, 1280, -256);      // pairs: 74 CTAs poll the vector, 74 wait for their partner's flag
+        run(0, 74, 1280, 256);
+    }
     return 0;
 }
