@@ -85,6 +85,28 @@ int wo_lang_id(const char *lang) {
     return -1;
 }
 
+/* ggml block-quantised tensor types, QK = 32 (GGML_TYPE 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0): ggml's dequantize_row_*.
+ * The reference's model script fetches such files (script/download-ggml-model.sh:28-51).  NOTE: whisper.cpp multiplies
+ * quantised weights against q8_0-quantised activations; this oracle (like the GPU loader) dequantises to f16 instead. */
+static size_t quant_block_bytes(int tt) { return tt == 2 ? 18 : tt == 3 ? 20 : tt == 6 ? 22 : tt == 7 ? 24 : tt == 8 ? 34 : 0; }
+__attribute__((optimize("fp-contract=off")))      /* x * d + m in two roundings, as ggml's scalar dequantize_row_* and numpy */
+static void dequantize_block(const unsigned char *b, int tt, float *y) {
+    f16 dh; memcpy(&dh, b, 2);
+    const float d = (float)dh;
+    if (tt == 8) { const int8_t *q = (const int8_t *)(b + 2); for (int j = 0; j < 32; j++) y[j] = (float)q[j] * d; return; }
+    float m = 0.f; size_t o = 2;
+    if (tt == 3 || tt == 7) { f16 mh; memcpy(&mh, b + 2, 2); m = (float)mh; o = 4; }
+    uint32_t qh = 0;
+    if (tt == 6 || tt == 7) { memcpy(&qh, b + o, 4); o += 4; }
+    const unsigned char *qs = b + o;
+    for (int j = 0; j < 16; j++) {
+        int x0 = qs[j] & 0x0F, x1 = qs[j] >> 4;
+        if (tt == 6 || tt == 7) { x0 |= (int)((qh >> j) & 1u) << 4; x1 |= (int)((qh >> (j + 16)) & 1u) << 4; }
+        if (tt == 2) { y[j] = (float)(x0 - 8) * d; y[j + 16] = (float)(x1 - 8) * d; }
+        else if (tt == 6) { y[j] = (float)(x0 - 16) * d; y[j + 16] = (float)(x1 - 16) * d; }
+        else { y[j] = (float)x0 * d + m; y[j + 16] = (float)x1 * d + m; }
+    }
+}
 typedef struct { const char *name; int n_dims; int ne[4]; int ttype; const void *data; } tensor_t;
 
 static const tensor_t *find_tensor(const tensor_t *ts, int n, const char *name) {
@@ -191,7 +213,7 @@ wo_model *wo_load(const char *path) {
     while (o < sz) {
         int32_t hdr[3]; NEED(12); memcpy(hdr, blob + o, 12); o += 12;
         int n_dims = hdr[0], nlen = hdr[1], tt = hdr[2];
-        if (n_dims < 1 || n_dims > 4 || nlen <= 0 || nlen > 200 || (tt != 0 && tt != 1)) {
+        if (n_dims < 1 || n_dims > 4 || nlen <= 0 || nlen > 200 || (tt != 0 && tt != 1 && !quant_block_bytes(tt))) {
             set_err("bad tensor header at %zu (n_dims %d, len %d, type %d)", o, n_dims, nlen, tt); free(ts); goto fail; }
         tensor_t *t = &ts[nt];
         size_t ne = 1;
@@ -199,7 +221,18 @@ wo_model *wo_load(const char *path) {
         for (int d = 0; d < n_dims; d++) { memcpy(&t->ne[d], blob + o, 4); o += 4; ne *= (size_t)t->ne[d]; }
         names[nt] = (char *)malloc((size_t)nlen + 1); memcpy(names[nt], blob + o, (size_t)nlen); names[nt][nlen] = 0; o += (size_t)nlen;
         t->name = names[nt]; t->n_dims = n_dims; t->ttype = tt;
-        size_t nb = ne * (tt == 1 ? 2 : 4); NEED(nb);
+        size_t nb = ne * (tt == 1 ? 2 : 4);
+        if (quant_block_bytes(tt)) {      /* block-quantised (whisper.cpp `quantize` output): dequantise once into f16, as the GPU loader does */
+            if (t->ne[0] % 32) { set_err("quantised tensor %s: row length not a multiple of 32", t->name); free(ts); goto fail; }
+            nb = ne / 32 * quant_block_bytes(tt); NEED(nb);
+            f16 *c = (f16 *)malloc(ne * sizeof(f16));   /* leaked with the model */
+            float y[32];
+            for (size_t i = 0; i < ne / 32; i++) { dequantize_block(blob + o + i * quant_block_bytes(tt), tt, y); for (int j = 0; j < 32; j++) c[32 * i + j] = (f16)y[j]; }
+            t->data = c; t->ttype = 1; o += nb;
+            if (++nt == cap) { set_err("too many tensors"); free(ts); goto fail; }
+            continue;
+        }
+        NEED(nb);
         /* the legacy container does not align tensor data; realign into an owned buffer when needed */
         if (((uintptr_t)(blob + o)) % (tt == 1 ? 2 : 4)) {
             void *c = malloc(nb); memcpy(c, blob + o, nb); t->data = c;   /* leaked with the model */

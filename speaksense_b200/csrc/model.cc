@@ -29,7 +29,7 @@ constexpr char kArenaMagic[8] = {'S', 'S', 'A', 'R', 'E', 'N', 'A', '1'};
 struct FileTensor {
     int n_dims = 0;
     int ne[4] = {1, 1, 1, 1};
-    int ttype = 0;   // 0 f32, 1 f16
+    int ttype = 0;   // GGML_TYPE: 0 f32, 1 f16, 2 q4_0, 3 q4_1, 6 q5_0, 7 q5_1, 8 q8_0 (blocks of 32, dequantised at load)
     const unsigned char *data = nullptr;
     size_t count() const { return (size_t)ne[0] * ne[1] * ne[2] * ne[3]; }
 };
@@ -67,6 +67,31 @@ size_t parse_meta(const unsigned char *b, size_t sz, HParams &hp, const float **
     return o;
 }
 
+// ---- ggml block-quantised types (QK = 32): the files whisper.cpp's quantize tool writes and the reference's
+// script/download-ggml-model.sh:28-51 fetches (e.g. large-v3-q5_0).  Weights are dequantised ONCE at load into the f16
+// arena (ggml dequantize_row_*: f16 scale [, f16 min], 4 / 5 / 8-bit codes), then the f16 kernels run unchanged.
+// whisper.cpp itself multiplies such weights against q8_0-quantised activations; that integer path is not restated.
+inline size_t quant_block_bytes(int ttype) { return ttype == 2 ? 18 : ttype == 3 ? 20 : ttype == 6 ? 22 : ttype == 7 ? 24 : ttype == 8 ? 34 : 0; }
+inline float f16_bits_to_f32_host(uint16_t u);
+__attribute__((optimize("fp-contract=off")))      // x * d + m in two roundings, as ggml's scalar dequantize_row_*
+void dequantize_block(const unsigned char *b, int ttype, float *y) {
+    uint16_t dh; memcpy(&dh, b, 2);
+    const float d = f16_bits_to_f32_host(dh);
+    if (ttype == 8) { const int8_t *q = reinterpret_cast<const int8_t *>(b + 2); for (int j = 0; j < 32; j++) y[j] = (float)q[j] * d; return; }
+    float m = 0.f; size_t o = 2;
+    if (ttype == 3 || ttype == 7) { uint16_t mh; memcpy(&mh, b + 2, 2); m = f16_bits_to_f32_host(mh); o = 4; }
+    uint32_t qh = 0;
+    if (ttype == 6 || ttype == 7) { memcpy(&qh, b + o, 4); o += 4; }
+    const unsigned char *qs = b + o;
+    for (int j = 0; j < 16; j++) {
+        int x0 = qs[j] & 0x0F, x1 = qs[j] >> 4;
+        if (ttype == 6 || ttype == 7) { x0 |= (int)((qh >> j) & 1u) << 4; x1 |= (int)((qh >> (j + 16)) & 1u) << 4; }
+        if (ttype == 2) { y[j] = (float)(x0 - 8) * d; y[j + 16] = (float)(x1 - 8) * d; }
+        else if (ttype == 6) { y[j] = (float)(x0 - 16) * d; y[j + 16] = (float)(x1 - 16) * d; }
+        else { y[j] = (float)x0 * d + m; y[j + 16] = (float)x1 * d + m; }
+    }
+}
+
 void parse_file(const std::string &path, ParsedFile &pf) {
     std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f) SS_THROW(-2, "cannot open model file '%s'", path.c_str());
@@ -83,11 +108,15 @@ void parse_file(const std::string &path, ParsedFile &pf) {
         FileTensor t; t.n_dims = hdr[0]; t.ttype = hdr[2];
         int nlen = hdr[1];
         if (t.n_dims < 1 || t.n_dims > 4 || nlen <= 0 || nlen > 256) SS_THROW(-2, "bad tensor header at %zu", o);
-        if (t.ttype != 0 && t.ttype != 1) SS_THROW(-2, "quantised ggml tensor types are not supported (type %d)", t.ttype);
+        if (t.ttype != 0 && t.ttype != 1 && quant_block_bytes(t.ttype) == 0) SS_THROW(-2, "unsupported ggml tensor type %d (f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0 are)", t.ttype);
         if (o + 4 * (size_t)t.n_dims + (size_t)nlen > sz) SS_THROW(-2, "truncated tensor header");
         for (int d = 0; d < t.n_dims; d++) { memcpy(&t.ne[d], b + o, 4); o += 4; }
         std::string name(reinterpret_cast<const char *>(b + o), (size_t)nlen); o += (size_t)nlen;
         size_t nb = t.count() * (t.ttype == 1 ? 2 : 4);
+        if (quant_block_bytes(t.ttype)) {
+            if (t.ne[0] % 32) SS_THROW(-2, "quantised tensor '%s': row length %d is not a multiple of 32", name.c_str(), t.ne[0]);
+            nb = t.count() / 32 * quant_block_bytes(t.ttype);
+        }
         if (o + nb > sz) SS_THROW(-2, "tensor '%s' truncated", name.c_str());
         t.data = b + o; o += nb;
         pf.tensors[name] = t;
@@ -96,6 +125,7 @@ void parse_file(const std::string &path, ParsedFile &pf) {
 
 inline uint16_t f32_to_f16_bits(float f) { __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
 inline float f16_bits_to_f32(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
+inline float f16_bits_to_f32_host(uint16_t u) { return f16_bits_to_f32(u); }
 
 // Walks the arena layout.  With base != nullptr and pf != nullptr it also fills the image.
 struct Walker {
@@ -114,12 +144,17 @@ struct Walker {
         const FileTensor &t = get(name);
         if (t.count() != n) SS_THROW(-2, "tensor '%s' has %zu elements, expected %zu", name.c_str(), t.count(), n);
         if (t.ttype == 0) memcpy(dst, t.data, n * 4);
+        else if (const size_t bb = quant_block_bytes(t.ttype)) { for (size_t i = 0; i < n / 32; i++) dequantize_block(t.data + i * bb, t.ttype, dst + 32 * i); }
         else { const uint16_t *s = reinterpret_cast<const uint16_t *>(t.data); uint16_t v; for (size_t i = 0; i < n; i++) { memcpy(&v, s + i, 2); dst[i] = f16_bits_to_f32(v); } }
     }
     void put_f16(uint16_t *dst, const std::string &name, size_t n) const {
         const FileTensor &t = get(name);
         if (t.count() != n) SS_THROW(-2, "tensor '%s' has %zu elements, expected %zu", name.c_str(), t.count(), n);
         if (t.ttype == 1) memcpy(dst, t.data, n * 2);
+        else if (const size_t bb = quant_block_bytes(t.ttype)) {
+            float y[32];
+            for (size_t i = 0; i < n / 32; i++) { dequantize_block(t.data + i * bb, t.ttype, y); for (int j = 0; j < 32; j++) dst[32 * i + j] = f32_to_f16_bits(y[j]); }
+        }
         else { const unsigned char *s = t.data; float v; for (size_t i = 0; i < n; i++) { memcpy(&v, s + 4 * i, 4); dst[i] = f32_to_f16_bits(v); } }
     }
     const float *f32(const std::string &name, size_t n) {

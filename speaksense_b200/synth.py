@@ -338,6 +338,125 @@ def read_model(path: str) -> dict:
     return {"hparams": hp, "filters": filters, "vocab": vocab, "tensors": tensors}
 
 
+# --------------------------------------------------------------------------------------
+# ggml block-quantised tensor types (QK = 32), as written by whisper.cpp's `quantize` tool
+# (the reference downloads such files: script/download-ggml-model.sh:28-51, e.g. large-v3-q5_0).
+# --------------------------------------------------------------------------------------
+QTYPES = {   # name: (GGML_TYPE in the tensor header, GGML_FTYPE in hparams.ftype, bytes per block of 32)
+    "q4_0": (2, 2, 18), "q4_1": (3, 3, 20), "q5_0": (6, 8, 22), "q5_1": (7, 9, 24), "q8_0": (8, 7, 34)}
+GGML_QNT_VERSION_FACTOR = 1000      # hparams.ftype = ftype + 2 * 1000 for quantisation format version 2
+QUANT_SKIP = ("encoder.conv1.bias", "encoder.conv2.bias", "encoder.positional_embedding", "decoder.positional_embedding")
+
+
+def _round_away(x):
+    return np.sign(x) * np.floor(np.abs(x) + 0.5)
+
+
+def quantize_blocks(x: np.ndarray, qtype: str) -> bytes:
+    """ggml quantize_row_<qtype>_reference over x (f32, size % 32 == 0) -> raw block bytes"""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 32)
+    nb = x.shape[0]
+    if qtype == "q8_0":
+        d = np.abs(x).max(axis=1) / np.float32(127.0)
+        inv = np.where(d > 0, np.float32(1.0) / np.where(d > 0, d, 1), 0).astype(np.float32)
+        q = _round_away(x * inv[:, None]).astype(np.int8)
+        out = np.zeros((nb, 34), np.uint8)
+        out[:, :2] = d.astype("<f2").view(np.uint8).reshape(nb, 2)
+        out[:, 2:] = q.view(np.uint8)
+        return out.tobytes()
+    sym = qtype in ("q4_0", "q5_0")
+    levels = 16 if qtype.startswith("q4") else 32
+    if sym:
+        idx = np.abs(x).argmax(axis=1)
+        mx = x[np.arange(nb), idx]
+        d = mx / np.float32(-(levels // 2))
+        mn = None
+    else:
+        mn, mx = x.min(axis=1), x.max(axis=1)
+        d = (mx - mn) / np.float32(levels - 1)
+    inv = np.where(d != 0, np.float32(1.0) / np.where(d != 0, d, 1), 0).astype(np.float32)
+    if sym:
+        q = np.minimum(levels - 1, (x * inv[:, None] + np.float32(levels // 2 + 0.5)).astype(np.int32).astype(np.int8)).astype(np.uint8)
+    else:
+        q = ((x - mn[:, None]) * inv[:, None] + np.float32(0.5)).astype(np.int32).astype(np.uint8)
+        q = np.minimum(q, levels - 1).astype(np.uint8)
+    lo, hi = q[:, :16], q[:, 16:]
+    qs = ((lo & 0x0F) | ((hi & 0x0F) << 4)).astype(np.uint8)
+    head = [d.astype("<f2").view(np.uint8).reshape(nb, 2)]
+    if not sym:
+        head.append(mn.astype("<f2").view(np.uint8).reshape(nb, 2))
+    if levels == 32:
+        qh = np.zeros(nb, np.uint32)
+        for j in range(16):
+            qh |= ((lo[:, j].astype(np.uint32) & 0x10) >> 4) << j
+            qh |= ((hi[:, j].astype(np.uint32) & 0x10) >> 4) << (j + 16)
+        head.append(qh.astype("<u4").view(np.uint8).reshape(nb, 4))
+    return np.concatenate(head + [qs], axis=1).tobytes()
+
+
+def dequantize_blocks(raw: bytes, qtype: str, count: int) -> np.ndarray:
+    """ggml dequantize_row_<qtype> -> f32 (the specification our loaders follow)"""
+    bs = QTYPES[qtype][2]
+    b = np.frombuffer(raw, np.uint8, (count // 32) * bs).reshape(-1, bs)
+    d = b[:, 0:2].copy().view("<f2").astype(np.float32)[:, 0]
+    o = 2
+    m = None
+    if qtype in ("q4_1", "q5_1"):
+        m = b[:, 2:4].copy().view("<f2").astype(np.float32)[:, 0]; o = 4
+    if qtype == "q8_0":
+        q = b[:, 2:].copy().view(np.int8).astype(np.float32)
+        return (q * d[:, None]).reshape(-1)
+    qh = None
+    if qtype.startswith("q5"):
+        qh = b[:, o:o + 4].copy().view("<u4")[:, 0]; o += 4
+    qs = b[:, o:o + 16]
+    lo, hi = (qs & 0x0F).astype(np.int32), (qs >> 4).astype(np.int32)
+    if qh is not None:
+        j = np.arange(16)
+        lo |= (((qh[:, None] >> j[None, :]) & 1) << 4).astype(np.int32)
+        hi |= (((qh[:, None] >> (j[None, :] + 16)) & 1) << 4).astype(np.int32)
+    q = np.concatenate([lo, hi], axis=1).astype(np.float32)
+    if m is None:
+        return ((q - np.float32(8 if qtype == "q4_0" else 16)) * d[:, None]).reshape(-1)
+    return (q * d[:, None] + m[:, None]).reshape(-1)
+
+
+def quantize_model(src: str, dst: str, qtype: str, dequantized_f16_twin: str | None = None) -> None:
+    """Re-write the f16 synthetic file `src` the way whisper.cpp's quantize tool does: every 2-D tensor (except the
+    skip list) becomes `qtype` blocks, everything else is copied.  With `dequantized_f16_twin` also writes an f16 file
+    whose 2-D tensors hold dequantize(quantize(w)) rounded to f16: an engine that dequantises at load must give
+    bit-identical results on both files."""
+    ttype, ftype, _ = QTYPES[qtype]
+    m = read_model(src)
+    hp: HParams = m["hparams"]
+    outs = [(dst, True)] + ([(dequantized_f16_twin, False)] if dequantized_f16_twin else [])
+    for path, quantised in outs:
+        tmp = path + ".tmp%d" % os.getpid()
+        w = _Writer(tmp)
+        vals = hp.as_list()
+        if quantised:
+            vals[-1] = ftype + 2 * GGML_QNT_VERSION_FACTOR
+        hq = HParams(*vals)
+        w.header(hq, m["filters"], m["vocab"])
+        for name, arr in m["tensors"].items():
+            is_f16 = arr.dtype == np.float16
+            if arr.ndim == 2 and name not in QUANT_SKIP and arr.shape[1] % 32 == 0 and not (arr.shape[0] == 1 or arr.shape[1] == 1):
+                raw = quantize_blocks(arr.astype(np.float32), qtype)
+                if quantised:
+                    nb = name.encode()
+                    w.f.write(struct.pack("<3i", 2, len(nb), ttype))
+                    w.f.write(struct.pack("<2i", arr.shape[1], arr.shape[0]))
+                    w.f.write(nb)
+                    w.f.write(raw)
+                    w.n_tensors += 1
+                else:
+                    w.tensor(name, dequantize_blocks(raw, qtype, arr.size).reshape(arr.shape), True)
+            else:
+                w.tensor(name, arr, is_f16)
+        w.close()
+        os.replace(tmp, path)
+
+
 def ensure_model(path: str, **kw) -> str:
     if not os.path.exists(path):
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
