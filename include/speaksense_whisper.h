@@ -108,6 +108,10 @@ void ss_denoise_config_default(ss_denoise_config *c);
  *    noise_type: 0 stationary, 1 non-stationary, 2 mixed.  Error if n_samples < frame_size (the reference panics). */
 int  ss_denoise_audio(ss_engine *e, ss_state *s, const float *pcm, size_t n_samples, const ss_denoise_config *cfg,
                       float *out, int *noise_type, float *spectral_variance);
+/* == steps 4-5 of StreamAudioProcessor::process_frame (src/audio/mod.rs:131-139) for n_frames independent frames of
+ *    cfg->frame_size samples (the REST path's 2048-sample frames, already scaled by the VAD gain): denoise_audio on the
+ *    single frame + noise gate.  frames / out: HOST, n_frames * frame_size floats.  One launch for all frames. */
+int  ss_denoise_frames(ss_engine *e, ss_state *s, const float *frames, int n_frames, const ss_denoise_config *cfg, float *out);
 /* Replays the decode-step CUDA graph n_steps times at positions n_past0.. (dummy tokens) and returns
  * the device time per step (CUDA events on the state's stream): the roofline probe of stage 3. */
 int  ss_bench_decode_steps(ss_engine *e, ss_state *s, int n_steps, int n_past0, float *ms_per_step);

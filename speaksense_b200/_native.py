@@ -41,6 +41,7 @@ SYMBOLS = [
     ("ss_transcribe_resident", C.c_int, [_P, _P, C.POINTER(SsParams)]),
     ("ss_denoise_config_default", None, [_P]),
     ("ss_denoise_audio", C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    ("ss_denoise_frames", C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     ("ss_bench_decode_steps", C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("ss_transcribe_batch", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t), C.c_int, C.POINTER(SsParams)]),
     ("ss_n_segments_raw", C.c_int, [_P]),

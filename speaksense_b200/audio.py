@@ -57,6 +57,18 @@ def denoise_audio(engine, state, samples, config: Optional[DenoiseConfig] = None
     return out, NOISE_TYPES[t.value], float(nv.value)
 
 
+def denoise_frames(engine, state, frames: np.ndarray, config: Optional[DenoiseConfig] = None) -> np.ndarray:
+    """steps 4-5 of StreamAudioProcessor::process_frame (audio/mod.rs:131-139) for all rows of `frames`
+    ([n_frames, frame_size] f32, already scaled by the VAD gain) in one launch: denoise_audio on each single frame + noise gate"""
+    cfg = config or DenoiseConfig()
+    x = np.ascontiguousarray(frames, dtype=np.float32).reshape(-1, cfg.frame_size)
+    out = np.empty_like(x)
+    c = cfg._native()
+    with state._lock:
+        _native.check(_native.lib().ss_denoise_frames(engine._h, state._h, x.ctypes.data, x.shape[0], C.byref(c), out.ctypes.data))
+    return out
+
+
 class StreamAudioProcessor:
     """StreamAudioProcessor::{new, process_chunk, finish} (audio/mod.rs:80-155).  `callback` receives every
     processed 2048-sample frame, in order.  The scalar recurrences (VAD gain, noise floor) run on the host
@@ -79,14 +91,11 @@ class StreamAudioProcessor:
         with np.errstate(invalid="ignore", divide="ignore"):
             return np.float32(np.float32(sum(e[:cnt], np.float32(0))) / np.float32(cnt))
 
-    def _process_frame(self, frame: np.ndarray) -> np.ndarray:      # mod.rs:111-141
+    def _gain(self, frame: np.ndarray) -> np.float32:      # mod.rs:111-128 (steps 1-2 + the state update)
         pre = frame.copy()
         pre[1:] = frame[1:] - np.float32(0.97) * frame[:-1]
-        energy = np.float32(0)
-        for v in pre:                                     # sequential f32 sum, as Iterator::sum
-            energy = np.float32(energy + v * v)
-        energy = np.float32(energy / np.float32(frame.size))
-        with np.errstate(invalid="ignore", divide="ignore"):
+        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+            energy = np.float32(np.cumsum(pre * pre, dtype=np.float32)[-1] / np.float32(frame.size))      # sequential f32 sum, as Iterator::sum
             threshold = np.float32(self.noise_floor * np.float32(1.2) + self.prev_energy * np.float32(0.1))
             if energy > threshold:
                 gain = np.float32(1.0)
@@ -96,29 +105,50 @@ class StreamAudioProcessor:
             self.prev_energy = energy
             mn = energy if np.isnan(self.noise_floor) else min(energy, self.noise_floor)
             self.noise_floor = np.float32(self.noise_floor * np.float32(0.95) + mn * np.float32(0.05))
-        processed = (frame * gain).astype(np.float32)
-        if self.config.enable_noise_reduction:
-            processed, _, _ = denoise_audio(self.engine, self.state, processed, self.config)
-        processed[np.abs(processed) < np.float32(self.config.noise_gate)] = 0.0      # mod.rs:495-499
-        return processed
+        return gain
+
+    def _process_frames(self, frames: List[np.ndarray]) -> None:
+        """process_frame for a run of frames: the scalar recurrences in order on the host, then ONE launch for steps 3-5"""
+        if not frames:
+            return
+        scaled = np.empty((len(frames), self.frame_size), np.float32)
+        for k, frame in enumerate(frames):
+            if self.noise_floor == 0.0:                       # mod.rs:102-104
+                self.noise_floor = self._estimate_noise_floor(frame)
+            scaled[k] = frame * self._gain(frame)             # step 3
+        cfg = DenoiseConfig(self.frame_size, self.config.overlap, self.config.strength, self.config.noise_gate,
+                            self.config.enable_noise_reduction, self.config.threshold)
+        if self.frame_size != self.config.frame_size:
+            # the reference frames by its fixed 2048 (mod.rs:84) but denoises with config.frame_size: only equal sizes take the
+            # single-window route; anything else goes through the general entry point frame by frame
+            outs = []
+            for row in scaled:
+                o, _, _ = denoise_audio(self.engine, self.state, row, self.config) if self.config.enable_noise_reduction else (row.copy(), None, None)
+                o[np.abs(o) < np.float32(self.config.noise_gate)] = 0.0
+                outs.append(o)
+            out = np.stack(outs)
+        else:
+            out = denoise_frames(self.engine, self.state, scaled, cfg)
+        for row in out:
+            self.callback(row.copy())
 
     def process_chunk(self, chunk) -> None:      # mod.rs:92-109
         x = np.ascontiguousarray(chunk, dtype=np.float32)
         with np.errstate(invalid="ignore", divide="ignore"):
             x = x / (np.max(np.abs(x)) if x.size else np.float32(1.0))      # normalize_audio :408-411
         self.buffer = np.concatenate([self.buffer, x.astype(np.float32)])
+        frames = []
         while self.buffer.size >= self.frame_size:
-            frame, self.buffer = self.buffer[:self.frame_size].copy(), self.buffer[self.frame_size:]
-            if self.noise_floor == 0.0:
-                self.noise_floor = self._estimate_noise_floor(frame)
-            self.callback(self._process_frame(frame))
+            frames.append(self.buffer[:self.frame_size].copy())
+            self.buffer = self.buffer[self.frame_size:]
+        self._process_frames(frames)
 
     def finish(self) -> None:      # mod.rs:143-155
         if self.buffer.size:
             frame = np.zeros(self.frame_size, np.float32)
             frame[:self.buffer.size] = self.buffer
             self.buffer = np.zeros(0, np.float32)
-            self.callback(self._process_frame(frame))
+            self._process_frames([frame])
 
 
 def collect_frames() -> tuple:

@@ -119,6 +119,20 @@ int ss_denoise_audio(ss_engine *e, ss_state *s, const float *pcm, size_t n, cons
         return 0;
     });
 }
+int ss_denoise_frames(ss_engine *e, ss_state *s, const float *frames, int n_frames, const ss_denoise_config *cfg, float *out) {
+    return guard([&]() -> int {
+        if (!e || !s || !frames || !out || n_frames < 0) SS_THROW(SS_ERR_INVALID, "null argument");
+        if (s->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
+        ss_denoise_config c; ss_denoise_config_default(&c);
+        if (cfg) c = *cfg;
+        if (!c.enable_noise_reduction) {      // mod.rs:131-133: only the noise gate applies
+            for (size_t i = 0; i < (size_t)n_frames * c.frame_size; i++) out[i] = fabsf(frames[i]) < c.noise_gate ? 0.0f : frames[i];
+            return 0;
+        }
+        denoise_frames(*s->s, frames, n_frames, c.frame_size, c.strength, c.noise_gate, out);
+        return 0;
+    });
+}
 int ss_transcribe_resident(ss_engine *e, ss_state *s, const ss_params *p) {
     return guard([&]() -> int {
         if (!e || !s) SS_THROW(SS_ERR_INVALID, "null argument");

@@ -158,7 +158,53 @@ __global__ void dn_ola_kernel(const float *frames, int n_fr, int fs, int step, s
     out[i] = nm > 1e-10f ? (o / nm) * 10.0f : o;
 }
 
+// ---- StreamAudioProcessor frames (audio/mod.rs:111-141 steps 4-5), many at once.  denoise_audio on ONE frame of exactly
+// frame_size samples always takes the same route: a single analysis frame has no predecessor, so the spectral variance
+// is 0 -> Stationary -> spectral_subtraction with noise = |X|^2 / 20 (the frame is its own and only noise frame, divided
+// by the constant 20) and a single STFT window; overlap_add of one window divides by w^2 where w^2 > 1e-10.  Frames are
+// independent, so one CTA takes one frame; the noise gate (:495-499) is folded in.
+__global__ void __launch_bounds__(kDnThreads) dn_frames_kernel(const float *in, int fs, int log2fs, float strength, float noise_gate, float *out) {
+    extern __shared__ __align__(16) uint8_t dn_raw[];
+    DnSmem &sm = *reinterpret_cast<DnSmem *>(dn_raw);
+    build_twiddles(sm, fs);
+    load_windowed_fft(sm, in + (size_t)blockIdx.x * fs, fs, log2fs);
+    float2 v[kDnMaxFrame / kDnThreads];
+#pragma unroll
+    for (int q = 0; q < kDnMaxFrame / kDnThreads; q++) {
+        const int i = threadIdx.x + q * kDnThreads;
+        if (i < fs) {
+            const float2 c = sm.x[i];
+            const float power = c.x * c.x + c.y * c.y, noise = power / 20.0f;
+            const float freq_factor = fminf((float)i / (float)fs, 1.0f);
+            const float freq_strength = strength * (1.0f - 0.3f * freq_factor);
+            const float gain = sqrtf(fmaxf(1.0f - 1.0f * powf(noise / (power + 1e-6f), freq_strength), 0.1f));
+            v[q] = make_float2(c.x * gain, c.y * gain);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kDnMaxFrame / kDnThreads; q++) { const int i = threadIdx.x + q * kDnThreads; if (i < fs) sm.x[bitrev(i, log2fs)] = v[q]; }
+    fft_passes(sm, fs, log2fs, true);
+    float *O = out + (size_t)blockIdx.x * fs;
+    for (int j = threadIdx.x; j < fs; j += kDnThreads) {
+        const float w = hann_w(j, fs), o = sm.x[j].x * w, nm = w * w;
+        const float r = nm > 1e-10f ? (o / nm) * 10.0f : o;
+        O[j] = fabsf(r) < noise_gate ? 0.0f : r;
+    }
+}
+
 }  // namespace
+
+void denoise_frames_enqueue(const float *d_in, int n_frames, int fs, float strength, float noise_gate, float *d_out, cudaStream_t st, int *launches) {
+    if (fs < 64 || fs > kDnMaxFrame || (fs & (fs - 1))) SS_THROW(-1, "denoise: frame_size must be a power of two in [64, %d]", kDnMaxFrame);
+    if (n_frames <= 0) return;
+    int log2fs = 0; while ((1 << log2fs) < fs) log2fs++;
+    static bool attr_done = false;
+    if (!attr_done) { CUDA_CHECK(cudaFuncSetAttribute(dn_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DnSmem))); attr_done = true; }
+    dn_frames_kernel<<<n_frames, kDnThreads, sizeof(DnSmem), st>>>(d_in, fs, log2fs, strength, noise_gate, d_out);
+    *launches += 1;
+    CUDA_CHECK(cudaGetLastError());
+}
 
 size_t denoise_scratch_floats(size_t n, int fs, float overlap) {
     const int step = (int)((float)fs * (1.0f - overlap));

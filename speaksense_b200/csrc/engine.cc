@@ -269,6 +269,16 @@ int denoise_audio(State &s, const float *pcm, size_t n, int frame_size, float ov
     return type;
 }
 
+void denoise_frames(State &s, const float *frames, int n_frames, int frame_size, float strength, float noise_gate, float *out) {
+    const size_t n = (size_t)n_frames * frame_size;
+    upload_pcm(s, frames, n);
+    if (!s.d_pcm_alt) s.d_pcm_alt = dmalloc<float>(s.pcm_cap);
+    denoise_frames_enqueue(s.d_pcm, n_frames, frame_size, strength, noise_gate, s.d_pcm_alt, s.stream, &s.n_launches);
+    CUDA_CHECK(cudaMemcpyAsync(s.h_pcm, s.d_pcm_alt, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    memcpy(out, s.h_pcm, n * sizeof(float));
+}
+
 void run_log_mel(State &s, const float *pcm, size_t n) {
     const Model &m = s.engine->model;
     CUDA_CHECK(cudaSetDevice(s.engine->device));

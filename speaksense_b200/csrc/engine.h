@@ -90,6 +90,8 @@ State *state_new(const std::shared_ptr<Engine> &e);
 void upload_pcm(State &s, const float *pcm, size_t n);
 // reference denoise_audio on the device: host PCM in, the denoised chunk stays resident (and is copied to `out` if given)
 int denoise_audio(State &s, const float *pcm, size_t n, int frame_size, float overlap, float strength, float *out, float *nv_out);
+// StreamAudioProcessor step 4-5 for `n_frames` frames (host in / host out)
+void denoise_frames(State &s, const float *frames, int n_frames, int frame_size, float strength, float noise_gate, float *out);
 void run_log_mel(State &s, const float *pcm, size_t n);   // pcm == nullptr: use the resident PCM
 float bench_decode_steps(State &s, int n_steps, int n_past0);
 void run_encode(State &s, int seek);

@@ -23,6 +23,10 @@ size_t denoise_scratch_floats(size_t n, int frame_size, float overlap);
 int denoise_enqueue(const float *d_in, size_t n, int frame_size, float overlap, float strength, float *d_out, float *scratch,
                     cudaStream_t st, int *launches, float *nv_out);
 
+// n_frames independent StreamAudioProcessor frames of frame_size samples each: denoise + noise gate (audio/mod.rs:131-139)
+void denoise_frames_enqueue(const float *d_in, int n_frames, int frame_size, float strength, float noise_gate, float *d_out,
+                            cudaStream_t st, int *launches);
+
 // ---------------------------------------------------------------- tcgen05 GEMM (gemm_sm100.cu)
 struct GemmOperand {        // a K-major (or, for B, MN-major) f16 operand described as up to 4-D strided view
     const __half *ptr = nullptr;
