@@ -64,6 +64,10 @@ SHAPES = {
     "micro-v3": HParams(51866, 1500, 256, 4, 2, 448, 256, 4, 2, 128),
     # large-v3 width with 2+2 layers: exercises every large-v3 kernel shape in seconds on CPU
     "large-v3-l2": HParams(51866, 1500, 1280, 20, 2, 448, 1280, 20, 2, 128),
+    # large-v3-turbo (script/download-ggml-model.sh:49): the large-v3 encoder with a 4-layer decoder
+    "large-v3-turbo": HParams(51866, 1500, 1280, 20, 32, 448, 1280, 20, 4, 128),
+    # turbo-like asymmetry (more encoder than decoder layers) at toy width
+    "micro-turbo": HParams(51866, 1500, 256, 4, 3, 448, 256, 4, 1, 128),
 }
 
 

@@ -166,3 +166,21 @@ def test_beam_size_above_limit_is_rejected(tiny_en_peaked, audio30):
     with pytest.raises(NativeError):
         eng.transcribe(audio30, AsrParams(beam_size=9))
     eng.close()
+
+
+@pytest.mark.gpu
+def test_turbo_like_asymmetric_layers(oracle_mod, audio30):
+    """large-v3-turbo layout (script/download-ggml-model.sh:49): fewer decoder than encoder layers"""
+    from speaksense_b200 import AsrParams, WhisperAsr
+    from tests.conftest import model_path
+    path = model_path("micro-turbo", "peaked", 2)
+    eng = WhisperAsr(path)
+    st = eng.create_state()
+    eng.transcribe_with_state(st, audio30, AsrParams(language="en", stream_mode=True, debug_keep_logits=True))
+    toks, _ = st.result_tokens()
+    om = oracle_mod.OracleModel(path)
+    ost = om.new_state()
+    ref = ost.full(audio30, language="en", stream_mode=True, keep_logits=True)
+    assert toks == ref["tokens"] and len(toks) > 10
+    assert float(np.abs(st.debug_logits() - ost.kept_logits()).max()) < 1e-2
+    ost.close(); om.close(); st.close(); eng.close()
