@@ -8,9 +8,12 @@
 //   warp 1     : TMEM allocator + single-thread MMA issuer
 //                  S_j  = Q . K_j^T         (M128 x N128 x K64,  A,B K-major)   -> TMEM S[j & 1]
 //                  PV_j = P_j . V_j         (M128 x N64  x K128, B = V MN-major) -> TMEM O[j & 1]
-//   warps 2..5 : softmax / correction, one query row per thread: tcgen05.ld S_j, running max and sum
-//                (exp2), P_j (f16) written into shared memory in the 128-byte-swizzled K-major layout the
-//                MMA reads, and the rescaled accumulation of PV_{j-1} in registers.
+//   warps 2..9 : softmax / correction, TWO threads per query row (warps w and w + 4 share a TMEM lane quarter: one takes
+//                keys 0..63 and output channels 0..31 of every block, the other keys 64..127 and channels 32..63; the
+//                block maximum is exchanged through shared memory + a 64-thread named barrier): tcgen05.ld S_j, running
+//                max and sum (exp2), P_j (f16) written into shared memory in the 128-byte-swizzled K-major layout the
+//                MMA reads, and the rescaled accumulation of PV_{j-1} in registers.  (One thread per row - 4 softmax
+//                warps, one per scheduler - left the kernel exp / issue bound at 7 % tensor-pipe activity.)
 // S and P never leave the SM: per layer this removes 0.27 GB of HBM traffic and three launches per head
 // batch compared with the unfused path of round-1 v0 (S GEMM + softmax + PV GEMM = 340 us per layer).
 //
@@ -28,7 +31,7 @@ using namespace ptx;
 constexpr int kBQ = 128;          // queries per CTA
 constexpr int kBK = 128;          // keys per block
 constexpr int kD = 64;            // head dim
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
 constexpr uint32_t kQBytes = kBQ * kD * 2;        // 16 KB
 constexpr uint32_t kKBytes = kBK * kD * 2;        // 16 KB
 constexpr uint32_t kVBytes = kBK * kD * 2;        // 16 KB
@@ -55,6 +58,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
     uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
     uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *p_full = bars + 7, *o_full = bars + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+    float *xmax = reinterpret_cast<float *>(bars + 16);      // [2 blocks in flight][2 halves][128 rows] block maxima
+    float *xsum = xmax + 2 * 2 * kBQ;                        // [2 halves][128 rows] final partial row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBQ, h = blockIdx.y, clip = blockIdx.z;
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&o_full[s], 1); }
-        mbar_init(p_full, 128);
+        mbar_init(p_full, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -127,48 +132,50 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             }
         }
     } else {
-        // ---------------- softmax / correction: thread = query row ----------------
-        const int q = warp & 3;
-        const int row = q * 32 + lane;                  // row inside the tile == TMEM lane
+        // ---------------- softmax / correction: two threads per query row ----------------
+        const int q = warp & 3, half = (warp - 2) >> 2;     // TMEM lane quarter; which 64 keys / 32 channels of the row
+        const int row = q * 32 + lane;                      // row inside the tile == TMEM lane
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t pair_bar = 1u + (uint32_t)q;         // named barrier of the two warps of this lane quarter
+        const int k0 = half * 64;
         float m = -INFINITY, l = 0.f;
-        float acc[kD];
+        float acc[kD / 2];
 #pragma unroll
-        for (int c = 0; c < kD; c++) acc[c] = 0.f;
+        for (int c = 0; c < kD / 2; c++) acc[c] = 0.f;
         for (int j = 0; j < nb; j++) {
             const int s = j & 1;
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tcgen05_fence_after();
-            // pass 1: row maximum of this block (scores scaled into the exp2 domain)
+            // pass 1: maximum of this thread's 64 keys (scores scaled into the exp2 domain), then the partner's
             float mj = -INFINITY;
             const int kvalid = min(kBK, p.T - j * kBK);
 #pragma unroll 1
-            for (int c = 0; c < kBK; c += 32) {
+            for (int c = k0; c < k0 + 64; c += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + c), r);
 #pragma unroll
                 for (int i = 0; i < 32; i++) if (c + i < kvalid) mj = fmaxf(mj, __uint_as_float(r[i]) * p.scale_log2);
             }
+            xmax[(s * 2 + half) * kBQ + row] = mj;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mj = fmaxf(mj, xmax[(s * 2 + (half ^ 1)) * kBQ + row]);
             const float m_new = fmaxf(m, mj);
             const float alpha = exp2f(m - m_new);          // 0 on the first block (m = -inf)
-            // fold the previous block's P.V into the accumulator, then rescale to the new maximum
+            // fold the previous block's P.V (this thread's 32 channels) into the accumulator, then rescale to the new maximum
             if (j > 0) {
                 mbar_wait(&o_full[s ^ 1], ((j - 1) >> 1) & 1);
                 tcgen05_fence_after();
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(lane_base + 256u + (uint32_t)((s ^ 1) * 64 + half * 32), r);
 #pragma unroll
-                for (int c = 0; c < kD; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(lane_base + 256u + (uint32_t)((s ^ 1) * 64 + c), r);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) acc[c + i] += __uint_as_float(r[i]);
-                }
+                for (int i = 0; i < 32; i++) acc[i] += __uint_as_float(r[i]);
             }
 #pragma unroll
-            for (int c = 0; c < kD; c++) acc[c] *= alpha;
-            // pass 2: probabilities -> shared memory (f16, swizzled K-major A operand), row sum
+            for (int c = 0; c < kD / 2; c++) acc[c] *= alpha;
+            // pass 2: probabilities -> shared memory (f16, swizzled K-major A operand), partial row sum
             float lsum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < kBK; c += 32) {
+            for (int c = k0; c < k0 + 64; c += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + c), r);
                 uint32_t pk[16];
@@ -197,20 +204,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             const int s = (nb - 1) & 1;
             mbar_wait(&o_full[s], ((nb - 1) >> 1) & 1);
             tcgen05_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(lane_base + 256u + (uint32_t)(s * 64 + half * 32), r);
 #pragma unroll
-            for (int c = 0; c < kD; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(lane_base + 256u + (uint32_t)(s * 64 + c), r);
-#pragma unroll
-                for (int i = 0; i < 32; i++) acc[c + i] += __uint_as_float(r[i]);
-            }
+            for (int i = 0; i < 32; i++) acc[i] += __uint_as_float(r[i]);
         }
+        xsum[half * kBQ + row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        l += xsum[(half ^ 1) * kBQ + row];
         const int t = q0 + row;
         if (t < p.T) {
             const float inv = 1.0f / l;
-            __half *o = p.out + (size_t)clip * p.out_clip_stride + (size_t)t * p.out_ld + h * kD;
+            __half *o = p.out + (size_t)clip * p.out_clip_stride + (size_t)t * p.out_ld + h * kD + half * (kD / 2);
 #pragma unroll
-            for (int c = 0; c < kD; c += 8) {
+            for (int c = 0; c < kD / 2; c += 8) {
                 __half2 h0 = __floats2half2_rn(acc[c] * inv, acc[c + 1] * inv), h1 = __floats2half2_rn(acc[c + 2] * inv, acc[c + 3] * inv);
                 __half2 h2 = __floats2half2_rn(acc[c + 4] * inv, acc[c + 5] * inv), h3 = __floats2half2_rn(acc[c + 6] * inv, acc[c + 7] * inv);
                 uint4 u;
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
     }
 }
 
-constexpr size_t kAttnSmem = 1024 + kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 16 * 8;
+constexpr size_t kAttnSmem = 1024 + kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 16 * 8 + (2 * 2 + 2) * kBQ * 4;
 
 }  // namespace
 
