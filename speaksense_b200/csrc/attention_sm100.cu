@@ -146,15 +146,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             const int s = j & 1;
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tcgen05_fence_after();
-            // pass 1: maximum of this thread's 64 keys (scores scaled into the exp2 domain), then the partner's
+            // pass 1: maximum of this thread's 64 keys (scores scaled into the exp2 domain), then the partner's.
+            // The 64 scores stay in registers for pass 2 (one TMEM read per block instead of two).
             float mj = -INFINITY;
             const int kvalid = min(kBK, p.T - j * kBK);
-#pragma unroll 1
-            for (int c = k0; c < k0 + 64; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + c), r);
+            uint32_t sr[2][32];
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + k0), sr[0]);
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + k0 + 32), sr[1]);
 #pragma unroll
-                for (int i = 0; i < 32; i++) if (c + i < kvalid) mj = fmaxf(mj, __uint_as_float(r[i]) * p.scale_log2);
+            for (int u = 0; u < 2; u++) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) if (k0 + 32 * u + i < kvalid) mj = fmaxf(mj, __uint_as_float(sr[u][i]) * p.scale_log2);
             }
             xmax[(s * 2 + half) * kBQ + row] = mj;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -174,15 +176,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             for (int c = 0; c < kD / 2; c++) acc[c] *= alpha;
             // pass 2: probabilities -> shared memory (f16, swizzled K-major A operand), partial row sum
             float lsum = 0.f;
-#pragma unroll 1
-            for (int c = k0; c < k0 + 64; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + c), r);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int c = k0 + 32 * u;
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c + i < kvalid) ? exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new) : 0.f;
-                    float p1 = (c + i + 1 < kvalid) ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2 - m_new) : 0.f;
+                    float p0 = (c + i < kvalid) ? exp2f(__uint_as_float(sr[u][i]) * p.scale_log2 - m_new) : 0.f;
+                    float p1 = (c + i + 1 < kvalid) ? exp2f(__uint_as_float(sr[u][i + 1]) * p.scale_log2 - m_new) : 0.f;
                     __half2 hp = __floats2half2_rn(p0, p1);
                     lsum += __low2float(hp) + __high2float(hp);      // sum what the MMA will actually see
                     pk[i >> 1] = *reinterpret_cast<uint32_t *>(&hp);
