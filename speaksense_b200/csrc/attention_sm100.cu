@@ -38,6 +38,8 @@ constexpr uint32_t kVBytes = kBK * kD * 2;        // 16 KB
 constexpr uint32_t kPBytes = kBQ * kBK * 2;       // 32 KB (two 64-wide K halves)
 constexpr uint32_t kTmemCols = 512;               // S[2] at 0 / 128, O[2] at 256 / 320
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 struct AttnDev {
     int T;                 // keys == queries per (clip, head)
     int H;
@@ -153,10 +155,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             uint32_t sr[2][32];
             tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + k0), sr[0]);
             tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + k0 + 32), sr[1]);
+            const bool full = kvalid == kBK;      // every block but the last: no per-key predicates (the softmax warps are issue-bound)
+            if (full) {
+                float mr = -INFINITY;             // maximum of the raw scores; the (positive) scale is applied once
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < 2; u++) {
 #pragma unroll
-                for (int i = 0; i < 32; i++) if (k0 + 32 * u + i < kvalid) mj = fmaxf(mj, __uint_as_float(sr[u][i]) * p.scale_log2);
+                    for (int i = 0; i < 32; i++) mr = fmaxf(mr, __uint_as_float(sr[u][i]));
+                }
+                mj = mr * p.scale_log2;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) if (k0 + 32 * u + i < kvalid) mj = fmaxf(mj, __uint_as_float(sr[u][i]) * p.scale_log2);
+                }
             }
             xmax[(s * 2 + half) * kBQ + row] = mj;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -176,23 +189,43 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             for (int c = 0; c < kD / 2; c++) acc[c] *= alpha;
             // pass 2: probabilities -> shared memory (f16, swizzled K-major A operand), partial row sum
             float lsum = 0.f;
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int c = k0 + 32 * u;
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c + i < kvalid) ? exp2f(__uint_as_float(sr[u][i]) * p.scale_log2 - m_new) : 0.f;
-                    float p1 = (c + i + 1 < kvalid) ? exp2f(__uint_as_float(sr[u][i + 1]) * p.scale_log2 - m_new) : 0.f;
-                    __half2 hp = __floats2half2_rn(p0, p1);
-                    lsum += __low2float(hp) + __high2float(hp);      // sum what the MMA will actually see
-                    pk[i >> 1] = *reinterpret_cast<uint32_t *>(&hp);
-                }
+            auto store_p = [&](int c, const uint32_t (&pk)[16]) {
 #pragma unroll
                 for (int g = 0; g < 4; g++) {          // four 16-byte chunks of 8 keys
                     const int cc = (c >> 3) + g;       // chunk index 0..15 inside the 128-key row
                     uint8_t *dst = sP + (cc >> 3) * 16384 + row * 128 + (((cc & 7) ^ (row & 7)) << 4);
                     *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                }
+            };
+            if (full) {
+                const float nm = -m_new;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[u][i]), p.scale_log2, nm));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(sr[u][i + 1]), p.scale_log2, nm));
+                        __half2 hp = __floats2half2_rn(p0, p1);
+                        lsum += __low2float(hp) + __high2float(hp);      // sum what the MMA will actually see
+                        pk[i >> 1] = *reinterpret_cast<uint32_t *>(&hp);
+                    }
+                    store_p(k0 + 32 * u, pk);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int c = k0 + 32 * u;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = (c + i < kvalid) ? exp2f(__uint_as_float(sr[u][i]) * p.scale_log2 - m_new) : 0.f;
+                        const float p1 = (c + i + 1 < kvalid) ? exp2f(__uint_as_float(sr[u][i + 1]) * p.scale_log2 - m_new) : 0.f;
+                        __half2 hp = __floats2half2_rn(p0, p1);
+                        lsum += __low2float(hp) + __high2float(hp);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t *>(&hp);
+                    }
+                    store_p(c, pk);
                 }
             }
             l = l * alpha + lsum;
