@@ -7,16 +7,17 @@
 // in round-1 v0 = 16 % of the HBM roofline).  Here one CTA per SM stays resident for the whole
 // decode loop:
 //   * warp 8 (producer) streams this CTA's static slice of the weights and of the cross-attention K/V
-//     cache through a 7 x 22.5 KB shared-memory ring with cp.async.bulk + mbarriers.  Its schedule does
-//     not depend on activations, so it runs ahead across phase, layer and token boundaries and keeps
-//     the HBM pipe busy while the consumers wait for each other's activations.
-//   * warps 0..7 (consumers) compute dot products straight out of the ring against an activation
-//     vector held in registers.
+//     cache through a 4 x 40 KB shared-memory ring with cp.async.bulk + mbarriers (one bulk copy per
+//     16-row chunk).  Its schedule does not depend on activations, so it runs ahead across phase, layer
+//     and token boundaries and keeps the HBM pipe busy while the consumers wait for each other.
+//   * warps 0..7 (consumers) run the mat-vecs on the tensor cores (ldmatrix + mma.m16n8k16): a weight
+//     row is 8 interleaved K slices riding the 8 MMA columns, so a warp owns its row pairs outright -
+//     no K split across warps, no cross-warp fold; the finishing lanes publish the rows themselves.
+//     The first chunk's A fragments are fetched before the phase's input vector has arrived.
 //   * CTAs exchange activations (a few KB per phase) through L2 with a flag-in-data protocol: every
-//     float travels as one 64-bit word {epoch, bits}, written with a single 8-byte store and polled
-//     by the readers until the epoch matches.  There are no grid barriers, fences or atomics on the
-//     critical path: a phase boundary costs one L2 store-to-load latency instead of
-//     fence + atomic + poll (measured 3.2 k cycles per barrier before this change).
+//     value travels in a 64-bit word {epoch, f32} or {epoch, 2 x f16}, written with a single 8-byte
+//     store and polled by the readers until the epoch matches.  There are no grid barriers, fences or
+//     atomics on the critical path (an all-to-all exchange still costs ~1.5 us on 148 SMs: DESIGN.md §5).
 //   * logits filter, greedy sampling and the decoder-state update (whisper_process_logits /
 //     whisper_sample_token / whisper_full bookkeeping) are folded in: every CTA
 //     reduces its slice of the vocabulary, all CTAs combine the per-CTA records redundantly, so the
@@ -123,12 +124,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ float2 h2f(uint32_t u) { return __half22float2(*reinterpret_cast<__half2 *>(&u)); }
 __device__ __forceinline__ float dot8(const uint4 &w, const float4 &a, const float4 &b, float acc) {
     float2 f;
@@ -188,8 +183,7 @@ __device__ __noinline__ void poll_packed(const u64 *buf, int n_words, uint32_t e
     }
     if (prof_on) SM.prof[0] += clock64() - t0;
 }
-// poll n (even) flagged floats into dst (shared; f32, or f16 when TO_HALF - the values of the non-LayerNorm
-// phases are f16-representable by construction); every thread spins only on its own words.
+// poll n (even) flagged f32 words into dst (shared; TO_HALF: rounded to f16); every thread spins only on its own words.
 // Returns this thread's {sum, sum of squares} of what it fetched (LayerNorm statistics for free).
 template <bool TO_HALF>
 __device__ __noinline__ float2 poll_vec(const u64 *buf, int n, uint32_t epoch, void *dst) {

@@ -175,7 +175,6 @@ static Decoder *new_decoder(State &s, bool with_keep) {
     b.eot = v.eot; b.sot = v.sot; b.translate = v.translate; b.transcribe = v.transcribe; b.solm = v.solm; b.prev = v.prev;
     b.nosp = v.nosp; b.not_ = v.not_; b.beg = v.beg; b.blank = v.blank;
     b.suppress_blank = 1; b.tdrz = 0; b.tid0_init = -1;
-    b.dbg = getenv("SS_MEGA_DBG") ? atoi(getenv("SS_MEGA_DBG")) : 0;
     d->d_mp = dmalloc<MegaParams>(1); d->mp_dirty = true;
     d->h_ctl = hmalloc<DecCtl>(1); d->h_tok = hmalloc<TokData>(hp.n_text_ctx);
     memset(d->h_ctl, 0, sizeof(DecCtl));

@@ -109,7 +109,6 @@ struct MegaParams {   // device-resident descriptor of one decoder sequence (dec
     long long *prof;             // optional [grid][8] cycle counters (SS_MEGA_PROF=1), else null
     int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
     int suppress_blank, tdrz, tid0_init;
-    int dbg;                     // experiment knob (SS_MEGA_DBG), 0 in production
 };
 size_t decode_mega_smem_bytes();
 void decode_mega_configure();
