@@ -259,3 +259,41 @@ def debug_gemm(a: np.ndarray, b: np.ndarray, b_mn_major: bool = False, device: i
     d = np.empty((M, N), np.float32)
     _native.check(_native.lib().ss_debug_gemm(device, a.ctypes.data, b.ctypes.data, d.ctypes.data, M, N, K, int(b_mn_major)))
     return d
+
+
+# ---- whisper.rs:225-234: calculate_checksum (evaluated only inside a debug! at whisper.rs:56) ----
+_M64 = (1 << 64) - 1
+
+
+def _rotl(x: int, b: int) -> int:
+    return ((x << b) | (x >> (64 - b))) & _M64
+
+
+def siphash(data: bytes, k0: int = 0, k1: int = 0, c_rounds: int = 1, d_rounds: int = 3) -> int:
+    """SipHash-c-d of `data`.  Rust's std DefaultHasher is SipHash-1-3 with the key (0, 0)."""
+    v0, v1 = k0 ^ 0x736f6d6570736575, k1 ^ 0x646f72616e646f6d
+    v2, v3 = k0 ^ 0x6c7967656e657261, k1 ^ 0x7465646279746573
+
+    def rounds(n):
+        nonlocal v0, v1, v2, v3
+        for _ in range(n):
+            v0 = (v0 + v1) & _M64; v1 = _rotl(v1, 13); v1 ^= v0; v0 = _rotl(v0, 32)
+            v2 = (v2 + v3) & _M64; v3 = _rotl(v3, 16); v3 ^= v2
+            v0 = (v0 + v3) & _M64; v3 = _rotl(v3, 21); v3 ^= v0
+            v2 = (v2 + v1) & _M64; v1 = _rotl(v1, 17); v1 ^= v2; v2 = _rotl(v2, 32)
+
+    n = len(data)
+    words = np.frombuffer(data[:n - n % 8], dtype="<u8")
+    for m in words.tolist():
+        v3 ^= m; rounds(c_rounds); v0 ^= m
+    tail = data[n - n % 8:] + b"\x00" * (7 - n % 8) + bytes([n & 0xFF])
+    m = int.from_bytes(tail, "little")
+    v3 ^= m; rounds(c_rounds); v0 ^= m
+    v2 ^= 0xFF
+    rounds(d_rounds)
+    return (v0 ^ v1 ^ v2 ^ v3) & _M64
+
+
+def calculate_checksum(audio) -> int:
+    """u64 the reference logs for an audio buffer: DefaultHasher over sample.to_bits() of every f32 (whisper.rs:225-234)"""
+    return siphash(np.ascontiguousarray(audio, dtype="<f4").tobytes())

@@ -38,3 +38,17 @@ def test_audio_is_seeded_and_bounded():
     a, b, c = synth.synth_audio(16000, 1), synth.synth_audio(16000, 1), synth.synth_audio(16000, 2)
     assert a.dtype == np.float32 and np.array_equal(a, b) and not np.array_equal(a, c)
     assert np.abs(a).max() <= 1.0 and a.std() > 0.05
+
+
+def test_calculate_checksum_is_rust_default_hasher():
+    """whisper.rs:225-234 (row a13): DefaultHasher = SipHash-1-3, key (0, 0), over the f32 bit patterns.  The generic
+    SipHash routine is pinned by the reference vector of the SipHash paper (2-4 rounds, key 00..0f, message 00..0e)."""
+    import numpy as np
+    from speaksense_b200.asr import calculate_checksum, siphash
+    k0, k1 = int.from_bytes(bytes(range(8)), "little"), int.from_bytes(bytes(range(8, 16)), "little")
+    assert siphash(bytes(range(15)), k0, k1, 2, 4) == 0xa129ca6149be45e5
+    assert siphash(b"", k0, k1, 2, 4) == 0x726fdb47dd0e0e31
+    x = np.array([0.0, 1.0, -1.0, 0.5], np.float32)
+    assert calculate_checksum(x) == siphash(x.tobytes(), 0, 0, 1, 3)
+    assert calculate_checksum(x) != calculate_checksum(x[::-1].copy())
+    assert calculate_checksum(np.zeros(0, np.float32)) == siphash(b"", 0, 0, 1, 3)
