@@ -44,3 +44,38 @@ def test_stream_session_matches_chunkwise_recomputation(micro_v3_peaked, oracle_
         if w[2] is not None:
             assert (g.segments[-1].start, g.segments[-1].end) == tuple(w[2])
     st.close(); ses.close(); eng.close()
+
+
+def test_grpc_server_two_concurrent_streams(micro_v3_peaked, audio30):
+    """the real engine behind the gRPC transport (proto/asr.proto), two streams at once on one GPU: every stream has its own
+    ss_state and CUDA stream; the responses equal those of a session driven directly"""
+    import threading
+    from speaksense_b200 import WhisperAsr, grpc_server, stream
+    eng = WhisperAsr(micro_v3_peaked, device=0)
+    pcms = [audio30[:16000 * 11], audio30[16000 * 5:16000 * 17]]
+    want = []
+    for pcm in pcms:
+        ses = stream.AsrStreamSession(eng)
+        w = []
+        for m, e in stream.encode_messages(pcm):
+            w += ses.feed(m, e, "x")
+        ses.close()
+        want.append([(r.end, r.text, [(s.start, s.end, s.text) for s in r.segments]) for r in w])
+    server = grpc_server.serve(eng, "127.0.0.1:0")
+    got = [None, None]
+
+    def run(i):
+        addr = "127.0.0.1:%d" % server.bound_port
+        got[i] = [(r.end, r.text, [(s.start, s.end, s.text) for s in r.segments])
+                  for r in grpc_server.transcribe_stream(addr, stream.encode_messages(pcms[i]), "x")]
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    try:
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=120)
+    finally:
+        server.stop(0)
+    assert got[0] == want[0] and got[1] == want[1] and len(want[0]) >= 1
+    eng.close()

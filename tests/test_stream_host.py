@@ -96,3 +96,25 @@ def test_chunk_accounting_with_stub_engine(monkeypatch):
     assert (out[2].segments[0].start, out[2].segments[0].end) == (600000, 650000)
     # a message that is not base64 is skipped (asr.rs:176-183)
     assert ses.feed(b"!!!not base64!!!", 0) == []
+
+
+def test_grpc_transport_speaks_asr_proto(monkeypatch):
+    """service asr.Asr / Transcribe over a real localhost gRPC channel, stub engine behind AsrStreamSession"""
+    from speaksense_b200 import grpc_server
+    monkeypatch.setattr(stream, "denoise_audio", lambda eng, st, x, cfg, fetch=True: (None, "Stationary", 0.0))
+    # wire format: field numbers / types of proto/asr.proto
+    req = grpc_server.TranscribeRequest(type=7, end=1, audio=b"QUJD", device_id="d")
+    assert req.SerializeToString() == b"\x08\x07\x10\x01\x1a\x04QUJD\x22\x01d"
+    seg_pb = grpc_server.Segment(start=3, end=300000, text="块".encode())
+    assert grpc_server.Segment.FromString(seg_pb.SerializeToString()).end == 300000
+    eng = _StubEngine()
+    server = grpc_server.serve(eng, "127.0.0.1:0")
+    try:
+        pcm = (np.sin(np.arange(16000 * 12) * 0.01) * 0.5).astype(np.float32)
+        out = list(grpc_server.transcribe_stream("127.0.0.1:%d" % server.bound_port, stream.encode_messages(pcm), "dev-9"))
+    finally:
+        server.stop(0)
+    assert [c[0] for c in eng.calls] == ["chunk", "chunk", "tail"]
+    assert [r.end for r in out] == [0, 0, 1] and all(r.device_id == "dev-9" for r in out)
+    assert out[0].text.decode() == "块0。" and out[2].text.decode() == "尾。"
+    assert (out[1].segments[0].start, out[1].segments[0].end) == (300000, 600000)
