@@ -1,6 +1,9 @@
 """Streaming caller benchmark (BASELINE config 5 shape on ONE GPU): one 5-minute synthetic stream, PCM16LE -> base64 ->
 32 KiB messages, through AsrStreamSession (gRPC handler semantics: 5 s chunks, 0.5 s overlap, denoise + transcribe per
-chunk on one state).  Prints one JSON line.   python tools/stream_bench.py [shape] [seconds] [beam_size]"""
+chunk on one state).  Prints one JSON line.   python tools/stream_bench.py [shape] [seconds] [beam_size] [grpc_streams]
+With grpc_streams > 0 the same messages go through the gRPC server (proto/asr.proto, speaksense_b200/grpc_server.py) as that
+many concurrent client streams against ONE GPU (each stream = its own ss_state; the decode kernels of different streams
+take turns on the device)."""
 import json
 import os
 import sys
@@ -15,6 +18,7 @@ from speaksense_b200 import WhisperAsr, stream, synth  # noqa: E402
 shape = sys.argv[1] if len(sys.argv) > 1 else "large-v3"
 seconds = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 beam = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+n_grpc = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 path = os.path.join(os.environ.get("SS_MODEL_DIR", "/tmp/ss_models"), "ggml-%s-peaked-s0.bin" % shape)
 synth.ensure_model(path, shape=shape, family="peaked", seed=0)
 eng = WhisperAsr(path)
@@ -32,6 +36,32 @@ for rep in range(2):      # first pass warms up (allocations, first launches)
     dt = time.perf_counter() - t0
     n_chunks = ses.n_chunks
     ses.close()
+if n_grpc > 0:
+    import threading
+    from speaksense_b200 import grpc_server
+
+    def factory():
+        ses = stream.AsrStreamSession(eng)
+        if beam > 1:
+            ses.params.beam_size = beam
+        return ses
+    server = grpc_server.serve(eng, "127.0.0.1:0", max_workers=2 * n_grpc, session_factory=factory)
+    addr = "127.0.0.1:%d" % server.bound_port
+    counts = [0] * n_grpc
+
+    def run(i):
+        counts[i] = sum(1 for _ in grpc_server.transcribe_stream(addr, msgs, "bench-%d" % i))
+    th = [threading.Thread(target=run, args=(i,)) for i in range(n_grpc)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt_g = time.perf_counter() - t0
+    server.stop(0)
+    print(json.dumps({"workload": "%d concurrent gRPC streams (asr.Asr/Transcribe over localhost) of %d s each on ONE GPU, ggml-%s synthetic, "
+                                  "beam_size=%d" % (n_grpc, seconds, shape, beam),
+                      "aggregate_stream_rtf": n_grpc * seconds / dt_g, "wall_s": dt_g, "responses": counts}))
 print(json.dumps({"workload": "one %d s stream, ggml-%s synthetic, 32 KiB base64 PCM16 messages, gRPC handler semantics "
                               "(5 s chunks, 4.5 s advance, denoise + transcribe per chunk), beam_size=%d" % (seconds, shape, beam),
                   "stream_rtf": seconds / dt, "wall_s": dt, "chunks": n_chunks, "ms_per_chunk": dt / max(n_chunks, 1) * 1e3,
