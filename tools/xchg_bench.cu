@@ -158,9 +158,9 @@ int main(int argc, char **argv) {
             cudaMemset(buf, 0, 4096);
         }
     }
-    const int modes[] = {0, 20};
-    const int grids[] = {2, 4, 8, 16, 32, 64, 100, 148};
-    for (int gi = 0; gi < 8; gi++) { sms = grids[gi];
+    const int modes[] = {0, 1, 2, 3, 4, 21, 30, 31, 32, 33, 34};      // (mode 20 polls only a prefix of the vector: late CTAs can run ahead and deadlock - never in a default run)
+    // the scaling with the number of CTAs is measured by tools/xchg_bench2.cu (bounded spins); here: the full grid only
+    for (int rep = 0; rep < 2; rep++) {
         for (int mi = 0; mi < (int)(sizeof(modes) / sizeof(int)); mi++) {
             const int mode = modes[mi];
             for (int work = 0; work <= (mode == 4 ? 2000 : 0); work += 1000) {
