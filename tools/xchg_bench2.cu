@@ -75,10 +75,11 @@ int main() {
         printf("ld=%d grid=%3d d=%4d pollers=%3d: %6.0f cycles per exchange%s%s\n", fl, grid, d, pollers, (double)mx / iters, he ? "  [SPIN LIMIT HIT]" : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
         fflush(stdout);
     };
-    for (int rep = 0; rep < 2; rep++) {
-        run(0, 148, 1280, 256);
-        run(0, 148, 1280, -256);      // pairs: 74 CTAs poll the vector, 74 wait for their partner's flag
-        run(0, 74, 1280, 256);
-    }
+    for (int grid : {2, 4, 8, 16, 32, 64, 100, 148}) run(0, grid, 1280, 256);      // cost vs number of participating CTAs
+    for (int fl : {1, 2, 3}) run(fl, 148, 1280, 256);                              // load flavours (volatile / .cg / .cv)
+    for (int d : {256, 512, 2560, 5120}) run(0, 148, d, 256);                      // vector length (d = 256: surplus threads all re-read one word)
+    for (int pollers : {32, 64, 128}) run(0, 148, 1280, pollers);                  // fewer polling threads, more sequential batches
+    run(0, 148, 1280, -256);                                                       // pairs: 74 CTAs poll, 74 wait for their partner's flag
+    run(0, 74, 1280, 256);
     return 0;
 }
