@@ -109,3 +109,19 @@ class TranscribeProcessor:
             flush()
         state.close()
         return res
+
+
+# ---- callback JSON of a finished task (src/schedule/callback/mod.rs:28-33,80-97; src/schedule/types.rs:87-95,118-138) ----
+def callback_payload(task_id: str, result: RestTranscribeResult) -> dict:
+    """what HttpCallback::on_complete POSTs: CallbackPayload{task_id, status: Completed, data: TaskResult::Transcribe(..)}
+    (TaskResult is #[serde(tag = "type", content = "result")]; speaker_id is Option<usize>)"""
+    return {"task_id": task_id, "status": "Completed",
+            "data": {"type": "Transcribe",
+                     "result": {"text": result.text,
+                                "segments": [{"text": s.text, "speaker_id": s.speaker_id, "start_time": s.start_time, "end_time": s.end_time}
+                                             for s in result.segments]}}}
+
+
+def callback_error_payload(task_id: str, error: str) -> dict:
+    """HttpCallback::on_error: status = TaskStatus::Failed(msg) (an externally tagged newtype variant), data = the message"""
+    return {"task_id": task_id, "status": {"Failed": error}, "data": error}

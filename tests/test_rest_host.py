@@ -70,3 +70,15 @@ def test_rest_stereo_and_validation(tmp_path, monkeypatch):
     write_wav(p8, left, rate=8000)
     with pytest.raises(ValueError):
         rest.TranscribeProcessor(eng).process_audio(str(p8))
+
+
+def test_callback_payload_shape():
+    """callback/mod.rs:28-33,80-97 + types.rs serde attributes, by hand"""
+    import json
+    r = rest.RestTranscribeResult(text="你好", segments=[rest.RestSegment("你好", 1, 0.0, 296.0)])
+    p = rest.callback_payload("task-1", r)
+    assert json.loads(json.dumps(p, ensure_ascii=False)) == {
+        "task_id": "task-1", "status": "Completed",
+        "data": {"type": "Transcribe", "result": {"text": "你好", "segments": [
+            {"text": "你好", "speaker_id": 1, "start_time": 0.0, "end_time": 296.0}]}}}
+    assert rest.callback_error_payload("t", "boom") == {"task_id": "t", "status": {"Failed": "boom"}, "data": "boom"}
