@@ -188,6 +188,23 @@ class OracleState:
         return dict(segments=segs, tokens=toks, plogs=plogs, n_fallbacks=self.L.wo_n_fallbacks(self.h),
                     n_decoded=self.L.wo_n_decoded(self.h), n_windows=self.L.wo_n_windows(self.h))
 
+    def process_logits(self, ids, raw, has_ts=False, seek_delta=0, temperature=0.0, **over) -> np.ndarray:
+        """whisper_process_logits probe: filtered logits (-inf = masked) for the history `ids` of sampled tokens"""
+        P = WoParams()
+        self.L.wo_default_params(C.byref(P))
+        for k, v in over.items():
+            setattr(P, k, v)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        out = np.empty_like(raw)
+        self.L.wo_probe_process_logits.argtypes = [C.c_void_p, C.POINTER(WoParams), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                   C.c_void_p, C.c_float, C.c_void_p]
+        rc = self.L.wo_probe_process_logits(self.h, C.byref(P), ids.ctypes.data, ids.size, int(has_ts), int(seek_delta),
+                                            raw.ctypes.data, temperature, out.ctypes.data)
+        if rc:
+            raise OracleError("wo_probe_process_logits rc=%d" % rc)
+        return out
+
     def kept_logits(self) -> np.ndarray:
         n = self.L.wo_n_kept_logits(self.h)
         nv = self.m.hparams["n_vocab"]

@@ -913,6 +913,24 @@ static void process_logits(wo_state *s, const wo_params *P, decoder_t *dc, const
     for (int i = 0; i < nv; i++) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
 }
 
+/* test probe: whisper_process_logits on a given token history (ids of the tokens sampled so far in this window),
+ * decoder timestamp state {has_ts, seek_delta} and raw logits; writes the filtered logits (-inf = masked).
+ * Used by tests/test_oracle_golden.py to hold the timestamp grammar against HuggingFace's independent
+ * WhisperTimeStampLogitsProcessor (tests/golden/logits_filter.npz). */
+int wo_probe_process_logits(wo_state *s, const wo_params *P, const int *ids, int n_ids, int has_ts, int seek_delta,
+                            const float *raw, float temperature, float *logits_out) {
+    decoder_t *dc = &s->dec[0];
+    if (n_ids < 0) return -1;
+    if (n_ids > dc->seq.cap) { dc->seq.cap = n_ids + 16; dc->seq.tokens = (tokdata_t *)realloc(dc->seq.tokens, (size_t)dc->seq.cap * sizeof(tokdata_t)); }
+    dc->seq.n = n_ids;
+    for (int i = 0; i < n_ids; i++) { memset(&dc->seq.tokens[i], 0, sizeof dc->seq.tokens[i]); dc->seq.tokens[i].id = ids[i]; }
+    dc->has_ts = has_ts; dc->seek_delta = seek_delta;
+    process_logits(s, P, dc, raw, temperature);
+    memcpy(logits_out, dc->logits, (size_t)s->m->hp.n_vocab * sizeof(float));
+    dc->seq.n = 0; dc->has_ts = 0;
+    return 0;
+}
+
 /* libstdc++ std::discrete_distribution<>(probs) driven by std::mt19937 via generate_canonical<double,53> */
 static int sample_discrete(decoder_t *dc, const float *probs, int n) {
     double sum = 0.0; for (int i = 0; i < n; i++) sum += (double)probs[i];

@@ -89,6 +89,11 @@ int  wo_n_windows(const wo_state *s);
 int  wo_n_kept_logits(const wo_state *s);
 const float *wo_kept_logits(const wo_state *s, int step); /* raw logits [n_vocab] */
 
+/* test probe: the logits filter (whisper_process_logits) on a given history of sampled token ids and decoder timestamp
+ * state; logits_out [n_vocab], -inf = masked */
+int  wo_probe_process_logits(wo_state *s, const wo_params *p, const int *ids, int n_ids, int has_ts, int seek_delta,
+                             const float *raw, float temperature, float *logits_out);
+
 #ifdef __cplusplus
 }
 #endif
