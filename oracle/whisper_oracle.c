@@ -942,6 +942,16 @@ static int sample_discrete(decoder_t *dc, const float *probs, int n) {
     return n - 1;
 }
 
+/* test probe: `count` draws of std::discrete_distribution<>(probs) from a std::mt19937 seeded with `seed`, as restated above;
+ * tests/test_oracle_full.py compares them with the real libstdc++ classes (a C++ snippet compiled at test time). */
+int wo_probe_sample(wo_state *s, uint32_t seed, const float *probs, int n, int count, int *out) {
+    decoder_t *dc = &s->dec[0];
+    mt_seed(dc, seed);
+    for (int i = 0; i < count; i++) out[i] = sample_discrete(dc, probs, n);
+    mt_seed(dc, 0);
+    return 0;
+}
+
 static tokdata_t sample_token(wo_state *s, decoder_t *dc, int best) {
     const wo_model *m = s->m; const int nv = m->hp.n_vocab;
     tokdata_t r = {0, 0, 0.f, 0.f, 0.f, 0.f};

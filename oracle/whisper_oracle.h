@@ -94,6 +94,9 @@ const float *wo_kept_logits(const wo_state *s, int step); /* raw logits [n_vocab
 int  wo_probe_process_logits(wo_state *s, const wo_params *p, const int *ids, int n_ids, int has_ts, int seek_delta,
                              const float *raw, float temperature, float *logits_out);
 
+/* test probe: draws of the restated std::mt19937 + std::discrete_distribution<> pair */
+int  wo_probe_sample(wo_state *s, uint32_t seed, const float *probs, int n, int count, int *out);
+
 #ifdef __cplusplus
 }
 #endif

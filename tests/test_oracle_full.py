@@ -96,3 +96,43 @@ def test_rust_text_rules():
     assert add_punctuation("今天下雨") == "今天下雨 "
     assert add_punctuation("已经有了。") == "已经有了。"
     assert is_promotional_text("欢迎订阅我的频道") and not is_promotional_text("hello")
+
+
+def test_sampler_matches_real_libstdcxx(oracle_mod, micro_v3_random, tmp_path):
+    """whisper_sample_token at temperature > 0 draws from std::discrete_distribution<> driven by std::mt19937
+    (SURVEY App. A.5).  The oracle restates both in C; here they are held to the real libstdc++ classes."""
+    import ctypes as C
+    import subprocess
+    src = tmp_path / "sampler.cpp"
+    src.write_text('''
+#include <random>
+#include <vector>
+#include <cstdio>
+int main(int argc, char **argv) {
+    unsigned seed = 0; int n = 0, count = 0;
+    if (scanf("%u %d %d", &seed, &n, &count) != 3) return 1;
+    std::vector<float> p(n);
+    for (int i = 0; i < n; i++) if (scanf("%f", &p[i]) != 1) return 1;
+    std::mt19937 rng(seed);
+    std::discrete_distribution<> dist(p.begin(), p.end());
+    for (int i = 0; i < count; i++) printf("%d\\n", dist(rng));
+    return 0;
+}
+''')
+    exe = tmp_path / "sampler"
+    subprocess.check_call(["g++", "-O1", "-o", str(exe), str(src)])
+    m = oracle_mod.OracleModel(micro_v3_random)
+    st = m.new_state()
+    L = oracle_mod.lib()
+    L.wo_probe_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for seed, n in ((0, 7), (1, 1000), (12345, 51866)):
+        p = rng.random(n).astype(np.float32) ** 8          # peaky, unnormalised (discrete_distribution normalises)
+        p[rng.integers(0, n, size=max(1, n // 10))] = 0.0
+        count = 200
+        out = np.zeros(count, np.int32)
+        L.wo_probe_sample(st.h, seed, p.ctypes.data, n, count, out.ctypes.data)
+        text = "%d %d %d\n" % (seed, n, count) + " ".join("%.9g" % v for v in p) + "\n"
+        ref = subprocess.run([str(exe)], input=text, capture_output=True, text=True, check=True).stdout.split()
+        assert out.tolist() == [int(x) for x in ref], (seed, n)
+    st.close(); m.close()
