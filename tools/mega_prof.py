@@ -1,4 +1,7 @@
-"""Decode-kernel cycle breakdown (SS_MEGA_PROF=1): python tools/mega_prof.py [shape] [steps]"""
+"""Decode-kernel timing / cycle breakdown: python tools/mega_prof.py [shape] [steps]
+Prints ms per decode step; the per-phase / per-stage cycle counters additionally need a profiling build of the library
+(`SS_MEGA_PROFILE=1 python -m speaksense_b200.build --force`; the counters cost ~13 % and are compiled out by default).
+SS_NO_PROF=1: plain timing (tools/ab.sh)."""
 import os, sys
 if not os.environ.get("SS_NO_PROF"):
     os.environ["SS_MEGA_PROF"] = "1"
