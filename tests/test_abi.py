@@ -90,3 +90,30 @@ def test_model_probe(L, tiny_en_peaked, micro_v3_random, tmp_path):
     trunc.write_bytes(open(tiny_en_peaked, "rb").read(3_000_000))
     assert L.ss_model_probe(str(trunc).encode(), None, None, None, None, None, None) == -2
     assert L.ss_model_probe(b"/nonexistent/model.bin", None, None, None, None, None, None) == -2
+
+
+def test_header_is_plain_c_and_links(tmp_path, L):
+    """the drop-in boundary is a C ABI: include/speaksense_whisper.h compiles as C99 (and C++), and a C program that only
+    includes it links against the library and gets the documented no-device error without a GPU"""
+    import shutil
+    import subprocess
+    from speaksense_b200 import build
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "speaksense_whisper.h"\n'
+                   'int main(void) { ss_params p; ss_denoise_config c; ss_engine *e = 0; int rc;\n'
+                   '  ss_params_default(&p); ss_denoise_config_default(&c);\n'
+                   '  rc = ss_engine_open("/nonexistent/model.bin", 0, &e);\n'
+                   '  printf("%d %d %d %s\\n", ss_abi_version(), c.frame_size, rc, ss_last_error());\n'
+                   '  return rc == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)])
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(build.LIB)
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, "-o", str(exe), str(src), "-L", libdir, "-lspeaksense_whisper",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    ver, fs, rc, msg = out.stdout.strip().split(" ", 3)
+    assert int(ver) == 1 and int(fs) == 2048 and int(rc) < 0 and len(msg) > 0
