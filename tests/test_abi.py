@@ -117,3 +117,29 @@ def test_header_is_plain_c_and_links(tmp_path, L):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     ver, fs, rc, msg = out.stdout.strip().split(" ", 3)
     assert int(ver) == 1 and int(fs) == 2048 and int(rc) < 0 and len(msg) > 0
+
+
+def test_loader_survives_corrupt_files(L, micro_v3_random, tmp_path):
+    """truncations at every structural boundary and corrupted tensor headers come back as SS_ERR_MODEL (-2), never a crash"""
+    import struct
+    blob = open(micro_v3_random, "rb").read()
+    probe = lambda b: (open(tmp_path / "m.bin", "wb").write(b), L.ss_model_probe(str(tmp_path / "m.bin").encode(), None, None, None, None, None, None))[1]  # noqa: E731
+    assert probe(blob) == 0
+    # header | mel filters | vocabulary | first tensor header | inside tensor data | last byte
+    meta = 4 + 44 + 8 + 128 * 201 * 4
+    cuts = [0, 3, 4, 20, 47, 52, 56, meta - 1, meta + 2, meta + 1000, meta + 400000, len(blob) // 2, len(blob) - 1]
+    for c in cuts:
+        assert probe(blob[:c]) == -2, c
+    # find the first tensor header (after the vocabulary) and corrupt its fields one at a time
+    o = meta
+    n_tok, = struct.unpack_from("<i", blob, o); o += 4
+    for _ in range(n_tok):
+        ln, = struct.unpack_from("<I", blob, o); o += 4 + ln
+    for field, value in ((0, 9), (0, -1), (1, -5), (1, 100000), (2, 99), (2, -3)):      # n_dims, name length, type
+        b = bytearray(blob)
+        struct.pack_into("<i", b, o + 4 * field, value)
+        assert probe(bytes(b)) == -2, (field, value)
+    b = bytearray(blob)
+    struct.pack_into("<i", b, o + 12, 0x7fffffff)            # absurd first dimension
+    assert probe(bytes(b)) == -2
+    assert b"" != L.ss_last_error()

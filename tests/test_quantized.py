@@ -71,3 +71,30 @@ def test_gpu_loader_dequantises_bit_exactly_and_matches_oracle(oracle_mod, micro
     assert res[0][0] == ref["tokens"]
     assert float(np.abs(res[0][1] - ost.kept_logits()).max()) < 1e-2
     ost.close(); m.close()
+
+
+@pytest.mark.parametrize("qtype", QT)
+def test_cxx_loader_arena_is_bit_identical_to_the_f16_twin(micro_v3_peaked, qtype):
+    """CPU-only check of csrc/model.cc's dequantiser: the packed weight arena (what would be uploaded to HBM) of the
+    quantised file hashes to the same FNV-1a value as the arena of the numpy-dequantised f16 twin... except for the raw
+    file prefix both arenas embed (hparams.ftype differs), so the hash is taken over the tensors only via identical
+    metadata: the twin is written with the same ftype field for this comparison."""
+    import ctypes as C
+    import struct
+    from speaksense_b200 import _native, build
+    build.build()
+    L = _native.lib()
+    q, twin = quant_pair(micro_v3_peaked, qtype)
+    # give the twin the quantised file's ftype so that the embedded prefix is byte-identical
+    raw = bytearray(open(twin, "rb").read())
+    ftype_q = struct.unpack_from("<i", open(q, "rb").read(48), 4 + 40)[0]
+    struct.pack_into("<i", raw, 4 + 40, ftype_q)
+    twin2 = twin[:-4] + "-ftype.bin"
+    open(twin2, "wb").write(raw)
+    hs = []
+    for path in (q, twin2):
+        h, ab = C.c_uint64(), C.c_int64()
+        assert L.ss_model_probe(path.encode(), None, C.byref(ab), C.byref(h), None, None, None) == 0, L.ss_last_error()
+        hs.append((h.value, ab.value))
+    assert hs[0] == hs[1]
+    os.remove(twin2)
