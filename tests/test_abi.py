@@ -143,3 +143,26 @@ def test_loader_survives_corrupt_files(L, micro_v3_random, tmp_path):
     struct.pack_into("<i", b, o + 12, 0x7fffffff)            # absurd first dimension
     assert probe(bytes(b)) == -2
     assert b"" != L.ss_last_error()
+
+
+def test_text_rules_literal_cases(L):
+    """expected values written down by hand from whisper.rs:9-14 (promo list), :41-43 (contains any), :175-201 (punctuation) -
+    independent of tests/rust_post.py"""
+    buf = C.create_string_buffer(1024)
+
+    def punct(s):
+        assert L.ss_add_punctuation(s.encode(), buf, len(buf)) >= 0
+        return buf.value.decode()
+    assert punct("你好吗") == "你好吗？"            # 吗 -> question
+    assert punct("这是什么好东西") == "这是什么好东西？"  # question wins over exclamation (checked first)
+    assert punct("太棒了") == "太棒了！"            # 太 -> exclamation
+    assert punct("今天开会") == "今天开会 "          # neither -> a single space
+    assert punct("hello") == "hello "
+    assert punct("") == " "
+    for tail in "。！？，":
+        assert punct("已有标点" + tail) == "已有标点" + tail      # already punctuated: unchanged
+    assert punct("英文标点.") == "英文标点. "       # ASCII '.' is not in the ends_with list
+    assert L.ss_is_promotional_text("欢迎订阅我们的频道".encode()) == 1        # contains 订阅
+    assert L.ss_is_promotional_text("感谢收看 請按讚、訂閱、分享!".encode()) == 1
+    assert L.ss_is_promotional_text("订 阅".encode()) == 0                     # substring match, not fuzzy
+    assert L.ss_is_promotional_text("今天天气不错".encode()) == 0
