@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libspeaksense_whisper.so")
-SOURCES = ["api.cc", "engine.cc", "model.cc", "mel.cu", "denoise.cu", "gemm_sm100.cu", "attention_sm100.cu", "encoder.cu", "decoder_mega.cu"]
+SOURCES = ["api.cc", "engine.cc", "engine_batch.cc", "model.cc", "mel.cu", "denoise.cu", "gemm_sm100.cu", "attention_sm100.cu", "encoder.cu", "decoder_mega.cu", "decoder_batch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--cudart", "static", "-x", "cu"]
 

@@ -150,9 +150,15 @@ int ss_bench_decode_steps(ss_engine *e, ss_state *s, int n_steps, int n_past0, f
 int ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *const *pcm, const size_t *n, int batch, const ss_params *p) {
     return guard([&]() -> int {
         if (!e || !states || !pcm || !n || batch < 0) SS_THROW(SS_ERR_INVALID, "null argument");
+        for (int i = 0; i < batch; i++)
+            if (!states[i] || states[i]->s->engine.get() != e->e.get() || (!pcm[i] && n[i])) SS_THROW(SS_ERR_INVALID, "bad state / clip %d", i);
+        if (batch_decode_enabled()) {      // SS_BATCH_DECODE=1: one batched decoder step per token for all clips (engine_batch.cc)
+            std::vector<State *> st(batch);
+            for (int i = 0; i < batch; i++) st[i] = states[i]->s;
+            return transcribe_batch(st.data(), pcm, n, batch, make_params(p), p && p->stream_mode);
+        }
         int rc = 0;
         for (int i = 0; i < batch; i++) {
-            if (!states[i] || states[i]->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "bad state %d", i);
             const int r = transcribe(*states[i]->s, pcm[i], n[i], make_params(p), p && p->stream_mode);
             if (r && !rc) rc = r;
         }

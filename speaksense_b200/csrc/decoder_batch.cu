@@ -1,0 +1,514 @@
+// decoder_batch.cu - one decode step for a BATCH of independent sequences (ss_transcribe_batch; BASELINE.json
+// configs 3/4: 32 clips per GPU).  SURVEY.md §8d "decoder step, batch B": 1.6008 GB of weights + B x 0.24576 GB of
+// cross-KV per step, so the weights must be streamed ONCE per step for the whole batch - the batch-1 persistent kernel
+// (decoder_mega.cu) streams them once per sequence.
+//
+// Shape of the work: M = B <= 32 tokens against [N][K] f16 weight matrices.  That is far too skinny for the 128-row
+// tcgen05 tiles of gemm_sm100.cu (10 CTAs for N = 1280), and it is HBM-bound anyway, so the mat-muls run on
+// mma.m16n8k16 with the WEIGHTS as the A operand (16 output features per warp tile) and the sequences on the 8-wide N
+// dimension (1, 2 or 4 n-tiles).  Fragments are loaded straight from global memory as 16-byte vectors: thread (g, t) of
+// a warp reads halves [8t, 8t+8) of a 32-wide K block of weight rows g and g+8 and of x rows g (+8 per n-tile).  The MMA
+// then sees K in a permuted order - the same permutation on both operands, so every product is still formed exactly
+// once - and each row's 64 bytes per K block are read by 4 adjacent lanes (whole 32-byte sectors, no shared-memory
+// staging, no ldmatrix).  Warps of a CTA split N (WR row tiles) and K (WK slices, folded through shared memory).
+//
+// Arithmetic is the oracle's and decoder_mega.cu's: f16 weights, activations rounded to f16 in front of every mat-mul,
+// f32 accumulation, f32 LayerNorm / softmax, ggml's f16 GELU; Q and K carry head_dim^-1/4 each.  The logits filter,
+// greedy sampling and whisper_full's per-token bookkeeping are restated per sequence in bd_sample_kernel
+// (== lm_epilogue + sample_and_update of decoder_mega.cu).
+//
+// STATUS: written at the end of round 1 without GPU time left - compiled for sm_100a, NOT yet run.  It is therefore
+// opt-in (SS_BATCH_DECODE=1, see engine_batch.cc); the default ss_transcribe_batch still decodes clip by clip.
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace ss {
+
+namespace {
+
+enum : int { EPI_QKV = 0, EPI_RES, EPI_Q, EPI_GELU, EPI_LOGITS };
+
+__device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ float gelu16(float x) {
+    const float xh = r16(x);
+    return r16(0.5f * xh * (1.0f + tanhf(0.79788456080286535587989211986876f * xh * (1.0f + 0.044715f * xh * xh))));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide reductions over NW warps; `scratch` holds NW floats and must not be in use (callers alternate two rows)
+template <int NW>
+__device__ __forceinline__ float block_sum(float v, float *scratch) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; i++) t += scratch[i];
+    return t;
+}
+template <int NW>
+__device__ __forceinline__ float block_max(float v, float *scratch) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = scratch[0];
+#pragma unroll
+    for (int i = 1; i < NW; i++) t = fmaxf(t, scratch[i]);
+    return t;
+}
+__device__ __forceinline__ float2 h2f(uint32_t u) { return __half22float2(*reinterpret_cast<__half2 *>(&u)); }
+__device__ __forceinline__ float dot8(const uint4 &w, const float4 &a, const float4 &b) {
+    float acc = 0.f;
+    float2 f;
+    f = h2f(w.x); acc = fmaf(f.x, a.x, acc); acc = fmaf(f.y, a.y, acc);
+    f = h2f(w.y); acc = fmaf(f.x, a.z, acc); acc = fmaf(f.y, a.w, acc);
+    f = h2f(w.z); acc = fmaf(f.x, b.x, acc); acc = fmaf(f.y, b.y, acc);
+    f = h2f(w.w); acc = fmaf(f.x, b.z, acc); acc = fmaf(f.y, b.w, acc);
+    return acc;
+}
+__device__ __forceinline__ void axpy8(const uint4 &v, float p, float (&acc)[8]) {
+    float2 f;
+    f = h2f(v.x); acc[0] = fmaf(p, f.x, acc[0]); acc[1] = fmaf(p, f.y, acc[1]);
+    f = h2f(v.y); acc[2] = fmaf(p, f.x, acc[2]); acc[3] = fmaf(p, f.y, acc[3]);
+    f = h2f(v.z); acc[4] = fmaf(p, f.x, acc[4]); acc[5] = fmaf(p, f.y, acc[5]);
+    f = h2f(v.w); acc[6] = fmaf(p, f.x, acc[6]); acc[7] = fmaf(p, f.y, acc[7]);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm of every live sequence's residual row -> f16 operand (ggml_norm: mean, then the variance of the centred
+// values).  embed: the row is first formed as token embedding + positional embedding (start of a step).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnThreads = 256;
+constexpr int kLnPer = 5;     // d <= 1280
+__global__ void __launch_bounds__(kLnThreads) bd_ln_kernel(const __grid_constant__ BatchParams P, const float *__restrict__ lw,
+                                                           const float *__restrict__ lb, int embed) {
+    __shared__ float red[2][8];
+    const int b = blockIdx.x, tid = threadIdx.x, d = P.d;
+    const DecCtl *ctl = P.seq[b].ctl;
+    if (ctl->done) return;
+    float *x = P.x + (size_t)b * d;
+    float v[kLnPer];
+    float s = 0.f;
+    const int tok = ctl->token, pos = ctl->pos;
+#pragma unroll
+    for (int k = 0; k < kLnPer; k++) {
+        const int i = tid + k * kLnThreads;
+        v[k] = 0.f;
+        if (i < d) {
+            if (embed) { v[k] = __half2float(P.tok_emb[(size_t)tok * d + i]) + P.d_pos[(size_t)pos * d + i]; x[i] = v[k]; }
+            else v[k] = x[i];
+            s += v[k];
+        }
+    }
+    const float mean = block_sum<8>(s, red[0]) / (float)d;
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnPer; k++) if (tid + k * kLnThreads < d) { const float c = v[k] - mean; s2 += c * c; }
+    const float var = block_sum<8>(s2, red[1]) / (float)d;
+    const float scale = 1.0f / sqrtf(var + 1e-5f);
+    __half *y = P.xn + (size_t)b * d;
+#pragma unroll
+    for (int k = 0; k < kLnPer; k++) {
+        const int i = tid + k * kLnThreads;
+        if (i < d) y[i] = __float2half_rn((v[k] - mean) * scale * lw[i] + lb[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// skinny GEMM: out[b][n] = sum_k W[n][k] * X[b][k]  (+ epilogue), b < 8 * NT
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void bd_epilogue(const BatchParams &P, const float *__restrict__ bias, int il, int row, int b, float v) {
+    if (EPI == EPI_LOGITS) { P.logits[(size_t)b * P.n_vocab + row] = v; return; }
+    const DecCtl *ctl = P.seq[b].ctl;
+    if (ctl->done) return;
+    v += bias[row];
+    const int d = P.d;
+    if (EPI == EPI_QKV) {
+        if (row < d) P.q[(size_t)b * d + row] = __float2half_rn(v * P.s4);
+        else {
+            const bool is_k = row < 2 * d;
+            const int n = row - (is_k ? d : 2 * d), pos = ctl->pos;
+            __half *cache = (is_k ? P.seq[b].self_k : P.seq[b].self_v) + (size_t)il * P.ctx * d;
+            cache[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = __float2half_rn(is_k ? v * P.s4 : v);
+        }
+    } else if (EPI == EPI_RES) {
+        P.x[(size_t)b * d + row] += v;
+    } else if (EPI == EPI_Q) {
+        P.q[(size_t)b * d + row] = __float2half_rn(v * P.s4);
+    } else if (EPI == EPI_GELU) {
+        P.hid[(size_t)b * 4 * d + row] = __float2half_rn(gelu16(v));
+    }
+}
+
+constexpr int kGemmThreads = 256;
+template <int WR, int WK, int NT, int EPI>
+__global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_constant__ BatchParams P, const __half *__restrict__ W,
+                                                               const float *__restrict__ bias, const __half *__restrict__ X, int N, int K, int il) {
+    static_assert(WR * WK == 8, "8 warps per CTA");
+    if (*P.n_done >= P.B) return;
+    __shared__ float red[WR][WK][8 * NT][17];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wr = warp / WK, wk = warp % WK;
+    const int row_base = (blockIdx.x * WR + wr) * 16;
+    const int nblk = K >> 5, blk0 = wk * nblk / WK, blk1 = (wk + 1) * nblk / WK;      // 32-wide K blocks of this warp
+    const int ra = min(row_base + g, N - 1), rb = min(row_base + g + 8, N - 1);       // clamped: rows past N are computed, not stored
+    const uint4 *wa = reinterpret_cast<const uint4 *>(W + (size_t)ra * K) + t;
+    const uint4 *wb = reinterpret_cast<const uint4 *>(W + (size_t)rb * K) + t;
+    const uint4 *xp = reinterpret_cast<const uint4 *>(X + (size_t)g * K) + t;         // n-tile nt: + nt * K (8 rows of K / 8 vectors)
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+    constexpr int U = 4;      // K blocks in flight per warp: 4 KB of weights
+    for (int blk = blk0; blk < blk1; blk += U) {
+        uint4 a[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int bi = min(blk + u, blk1 - 1);      // the tail re-reads the last block; its products are skipped below
+            a[u] = __ldcs(wa + bi * 4); c[u] = __ldcs(wb + bi * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (blk + u < blk1) {      // warp-uniform
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+                    const uint4 xv = __ldg(xp + (size_t)nt * K + (blk + u) * 4);
+                    mma16816(acc[nt], a[u].x, c[u].x, a[u].y, c[u].y, xv.x, xv.y);
+                    mma16816(acc[nt], a[u].z, c[u].z, a[u].w, c[u].w, xv.z, xv.w);
+                }
+            }
+        }
+    }
+    // C fragment: c0/c1 = (row g, sequences 2t, 2t+1), c2/c3 = (row g + 8, ...)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        red[wr][wk][nt * 8 + 2 * t][g] = acc[nt][0]; red[wr][wk][nt * 8 + 2 * t + 1][g] = acc[nt][1];
+        red[wr][wk][nt * 8 + 2 * t][g + 8] = acc[nt][2]; red[wr][wk][nt * 8 + 2 * t + 1][g + 8] = acc[nt][3];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < WR * 16 * 8 * NT; idx += kGemmThreads) {
+        const int r = idx & 15, b = (idx >> 4) % (8 * NT), w2 = idx / (16 * 8 * NT);
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < WK; k++) v += red[w2][k][b][r];
+        const int row = (blockIdx.x * WR + w2) * 16 + r;
+        if (row < N && b < P.B) bd_epilogue<EPI>(P, bias, il, row, b, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention of one query (64 channels) over keys [0, n) of a head-major f16 cache: scores -> softmax statistics -> P.V
+// 8 lanes per key row (16 bytes each), 4 keys per warp and step, 4 steps in flight.
+// Returns in thread c < 64 the UNNORMALISED output channel c; m / l are the softmax maximum and sum.
+// ------------------------------------------------------------------------------------------------
+template <int NW, bool STREAM>
+__device__ __forceinline__ float attend(const __half *__restrict__ Kh, const __half *__restrict__ Vh, int n, const float *q, float *sc,
+                                        float (*red)[64], float *red1, float &m_out, float &l_out) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
+    const float4 qa = *reinterpret_cast<const float4 *>(q + l8 * 8), qb = *reinterpret_cast<const float4 *>(q + l8 * 8 + 4);
+    constexpr int STEP = NW * 4, U = 4;
+    float lmax = -INFINITY;
+    for (int jb = 0; jb < n; jb += STEP * U) {
+        uint4 kv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = min(jb + u * STEP + warp * 4 + sub, n - 1);
+            const uint4 *p = reinterpret_cast<const uint4 *>(Kh + (size_t)j * 64) + l8;
+            kv[u] = STREAM ? __ldcs(p) : __ldcg(p);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + u * STEP + warp * 4 + sub;
+            float ds = dot8(kv[u], qa, qb);
+            ds += __shfl_xor_sync(0xffffffffu, ds, 1);
+            ds += __shfl_xor_sync(0xffffffffu, ds, 2);
+            ds += __shfl_xor_sync(0xffffffffu, ds, 4);
+            if (j < n) { if (l8 == 0) sc[j] = ds; lmax = fmaxf(lmax, ds); }
+        }
+    }
+    const float m = block_max<NW>(lmax, red1);          // (its barrier also publishes the scores)
+    float lsum = 0.f;
+    for (int j = tid; j < n; j += NW * 32) { const float e = __expf(sc[j] - m); sc[j] = e; lsum += e; }
+    const float l = block_sum<NW>(lsum, red1 + NW);     // (its barrier also publishes the probabilities)
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int jb = 0; jb < n; jb += STEP * U) {
+        uint4 vv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = min(jb + u * STEP + warp * 4 + sub, n - 1);
+            const uint4 *p = reinterpret_cast<const uint4 *>(Vh + (size_t)j * 64) + l8;
+            vv[u] = STREAM ? __ldcs(p) : __ldcg(p);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + u * STEP + warp * 4 + sub;
+            if (j < n) axpy8(vv[u], sc[j], acc);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8); acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16); }
+    if (sub == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) red[warp][l8 * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    float o = 0.f;
+    if (tid < 64) for (int w = 0; w < NW; w++) o += red[w][tid];
+    m_out = m; l_out = l;
+    return o;
+}
+
+// self-attention: grid (H, B); the current token's K / V are already in the cache (QKV epilogue), so n = pos + 1
+constexpr int kSelfWarps = 4;
+__global__ void __launch_bounds__(kSelfWarps * 32) bd_self_attn_kernel(const __grid_constant__ BatchParams P, int il) {
+    __shared__ __align__(16) float q[64];
+    __shared__ float sc[512];
+    __shared__ float red[kSelfWarps][64];
+    __shared__ float red1[2 * kSelfWarps];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, d = P.d;
+    const DecCtl *ctl = P.seq[b].ctl;
+    if (ctl->done) return;
+    const int n = ctl->pos + 1;
+    if (tid < 64) q[tid] = __half2float(P.q[(size_t)b * d + h * 64 + tid]);
+    __syncthreads();
+    const size_t off = (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64;
+    float m, l;
+    const float o = attend<kSelfWarps, false>(P.seq[b].self_k + off, P.seq[b].self_v + off, n, q, sc, red, red1, m, l);
+    if (tid < 64) P.att[(size_t)b * d + h * 64 + tid] = __float2half_rn(o / l);
+}
+
+// cross-attention over the T encoder positions: grid (H, B, S); S > 1 splits the keys and leaves {m, l, o[64]} records
+constexpr int kCrossWarps = 8;
+__global__ void __launch_bounds__(kCrossWarps * 32) bd_cross_attn_kernel(const __grid_constant__ BatchParams P, int il, int S) {
+    __shared__ __align__(16) float q[64];
+    __shared__ float sc[1536];
+    __shared__ float red[kCrossWarps][64];
+    __shared__ float red1[2 * kCrossWarps];
+    const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x, d = P.d, T = P.T;
+    const DecCtl *ctl = P.seq[b].ctl;
+    if (ctl->done) return;
+    if (tid < 64) q[tid] = __half2float(P.q[(size_t)b * d + h * 64 + tid]);
+    __syncthreads();
+    const int per = (T + S - 1) / S, j0 = min(T, sp * per), n = min(T, j0 + per) - j0;
+    const size_t off = (size_t)il * 2 * T * d + ((size_t)h * T + j0) * 64;
+    float m = -INFINITY, l = 0.f, o = 0.f;
+    if (n > 0) o = attend<kCrossWarps, true>(P.seq[b].cross_k + off, P.seq[b].cross_v + off, n, q, sc, red, red1, m, l);
+    if (S == 1) {
+        if (tid < 64) P.att[(size_t)b * d + h * 64 + tid] = __float2half_rn(o / l);
+    } else {
+        float *rec = P.part + (((size_t)b * P.H + h) * S + sp) * 66;
+        if (tid < 64) rec[2 + tid] = o;
+        if (tid == 0) { rec[0] = m; rec[1] = l; }
+    }
+}
+__global__ void __launch_bounds__(64) bd_cross_fold_kernel(const __grid_constant__ BatchParams P, int S) {
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (P.seq[b].ctl->done) return;
+    const float *rec = P.part + ((size_t)b * P.H + h) * S * 66;
+    float M = -INFINITY;
+    for (int s = 0; s < S; s++) M = fmaxf(M, rec[s * 66]);
+    float L = 0.f, o = 0.f;
+    for (int s = 0; s < S; s++) {
+        const float pm = rec[s * 66];
+        if (pm > -INFINITY) { const float e = __expf(pm - M); L += rec[s * 66 + 1] * e; o += rec[s * 66 + 2 + tid] * e; }
+    }
+    P.att[(size_t)b * P.d + h * 64 + tid] = __float2half_rn(o / L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// end of a step, one CTA per sequence: feed the next prompt token, or filter the logits (whisper_process_logits), take
+// the greedy token (whisper_sample_token, best = true) and apply whisper_full's per-token bookkeeping
+// ------------------------------------------------------------------------------------------------
+struct MaxIdx { float v; int i; };
+__device__ __forceinline__ MaxIdx better(MaxIdx a, MaxIdx b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+
+struct SeqState { int pos, pos0, token, done, n_sampled, has_ts, seek_delta, result_len, last_id, penult_id, n_prompt, seek, seek_end, n_max, sample; };
+
+__device__ __forceinline__ bool token_masked(const BatchParams &P, const SeqState &st, int i) {
+    const bool is_initial = st.n_sampled == 0;
+    if (is_initial && P.suppress_blank && (i == P.eot || i == P.blank)) return true;
+    if (i == P.not_ || i == P.sot || i == P.nosp || i == P.translate || i == P.transcribe || i == P.prev) return true;
+    if (!P.tdrz && i == P.solm) return true;
+    if (i > P.sot && i <= P.sot + kNumLangSuppress) return true;
+    const bool last_ts = st.n_sampled > 0 && st.last_id >= P.beg;
+    const bool penult_ts = st.n_sampled < 2 || st.penult_id >= P.beg;
+    if (last_ts) { if (penult_ts) { if (i >= P.beg) return true; } else { if (i < P.eot) return true; } }
+    if (is_initial && P.tid0_init >= 0 && i >= P.beg + P.tid0_init + 1) return true;
+    if (st.has_ts && i >= P.beg && i < P.beg + st.seek_delta / 2) return true;
+    return false;
+}
+
+constexpr int kSampleWarps = 32;
+__global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __grid_constant__ BatchParams P) {
+    __shared__ SeqState S;
+    __shared__ float rv[2][kSampleWarps];
+    __shared__ int ri[2][kSampleWarps];
+    __shared__ float rs[2][kSampleWarps];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DecCtl *ctl = P.seq[b].ctl;
+    if (tid == 0) {
+        SeqState s;
+        s.pos = ctl->pos; s.pos0 = ctl->pos0; s.token = ctl->token; s.done = ctl->done; s.n_sampled = ctl->n_sampled; s.has_ts = ctl->has_ts;
+        s.seek_delta = ctl->seek_delta; s.result_len = ctl->result_len; s.last_id = ctl->last_id; s.penult_id = ctl->penult_id;
+        s.n_prompt = ctl->n_prompt; s.seek = ctl->seek; s.seek_end = ctl->seek_end; s.n_max = ctl->n_max; s.sample = ctl->sample;
+        S = s;
+    }
+    __syncthreads();
+    const SeqState st = S;
+    if (st.done) return;
+    const int jrel = st.pos - st.pos0;
+    if (jrel < st.n_prompt - 1) {      // prompt token: feed the next one
+        if (tid == 0) { ctl->token = ctl->prompt[jrel + 1]; ctl->pos = st.pos + 1; }
+        return;
+    }
+    if (!st.sample) {                  // teacher-forced run: the logits of the last token are the result
+        if (tid == 0) { ctl->done = 1; atomicAdd(P.n_done, 1); }
+        return;
+    }
+    const float *logits = P.logits + (size_t)b * P.n_vocab;
+    MaxIdx mt{-INFINITY, 0x7fffffff}, ms{-INFINITY, 0x7fffffff};      // best text token / best timestamp token
+    for (int i = tid; i < P.n_vocab; i += kSampleWarps * 32) {
+        const float x = token_masked(P, st, i) ? -INFINITY : logits[i];
+        if (i < P.beg) { if (x > mt.v) mt = MaxIdx{x, i}; } else { if (x > ms.v) ms = MaxIdx{x, i}; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxIdx a{__shfl_xor_sync(0xffffffffu, mt.v, o), __shfl_xor_sync(0xffffffffu, mt.i, o)}; mt = better(mt, a);
+        MaxIdx c{__shfl_xor_sync(0xffffffffu, ms.v, o), __shfl_xor_sync(0xffffffffu, ms.i, o)}; ms = better(ms, c);
+    }
+    if (lane == 0) { rv[0][warp] = mt.v; ri[0][warp] = mt.i; rv[1][warp] = ms.v; ri[1][warp] = ms.i; }
+    __syncthreads();
+    mt = MaxIdx{rv[0][0], ri[0][0]}; ms = MaxIdx{rv[1][0], ri[1][0]};
+    for (int w = 1; w < kSampleWarps; w++) { mt = better(mt, MaxIdx{rv[0][w], ri[0][w]}); ms = better(ms, MaxIdx{rv[1][w], ri[1][w]}); }
+    const float m_all = fmaxf(mt.v, ms.v);
+    float sa = 0.f, sb = 0.f;      // sum exp over everything (relative to m_all) / over the timestamps (relative to their maximum)
+    for (int i = tid; i < P.n_vocab; i += kSampleWarps * 32) {
+        const float x = token_masked(P, st, i) ? -INFINITY : logits[i];
+        if (x > -INFINITY) { sa += expf(x - m_all); if (i >= P.beg) sb += expf(x - ms.v); }
+    }
+    sa = warp_sum(sa); sb = warp_sum(sb);
+    if (lane == 0) { rs[0][warp] = sa; rs[1][warp] = sb; }
+    __syncthreads();
+    if (tid != 0) return;
+    sa = 0.f; sb = 0.f;
+    for (int w = 0; w < kSampleWarps; w++) { sa += rs[0][w]; sb += rs[1][w]; }
+    SeqState s = st;
+    const float max_text = mt.v, max_ts = ms.v;
+    const float lse = logf(sa) + m_all;
+    const float ts_lp = sb > 0.f ? logf(sb) + (max_ts - lse) : -INFINITY;      // logsumexp of the timestamp log-probs
+    const float text_lp = max_text - lse;
+    TokData tk;
+    if (ts_lp > text_lp) { tk.id = ms.i; tk.plog = max_ts - lse; }              // timestamps outweigh every text token
+    else if (max_text >= max_ts) { tk.id = mt.i; tk.plog = text_lp; }
+    else { tk.id = ms.i; tk.plog = max_ts - lse; }
+    if (tk.id == 0x7fffffff) { tk.id = 0; tk.plog = -INFINITY; }
+    tk.p = expf(tk.plog);
+    const float p_ts_max = max_ts > -INFINITY ? expf(max_ts - lse) : 0.f;
+    const float p_ts_sum = sb * p_ts_max;
+    tk.tid = (max_ts > -INFINITY && p_ts_max > 0.f) ? ms.i : 0;
+    tk.pt = p_ts_max / (p_ts_sum + 1e-10f); tk.ptsum = p_ts_sum;
+    if (tk.id >= P.beg) { tk.tid = tk.id; tk.pt = tk.p; }
+    const int i = s.n_sampled;
+    P.seq[b].tok_out[i] = tk;
+    int f = 0, cpl = 0;
+    if (tk.id > P.beg) {
+        const int sd_new = 2 * (tk.id - P.beg);
+        if (s.has_ts && s.seek_delta > sd_new && s.result_len < i) f = 1;
+        else { s.seek_delta = sd_new; s.result_len = i + 1; s.has_ts = 1; }
+    }
+    if (!f) {
+        if (tk.id == P.eot || (s.has_ts && s.seek + s.seek_delta + 100 >= s.seek_end)) {
+            if (s.result_len == 0) { if (s.seek + s.seek_delta + 100 >= s.seek_end) s.result_len = i + 1; else f = 1; }
+            if (!f) cpl = 1;
+        }
+    }
+    if (!f && !cpl && i == s.n_max - 1 && (s.result_len == 0 || s.seek_delta < 100 * kChunkSec / 2)) f = 1;
+    s.penult_id = s.last_id; s.last_id = tk.id; s.n_sampled = i + 1;
+    const int done = (f || cpl || s.n_sampled >= s.n_max) ? 1 : 0;
+    if (!done) { s.token = tk.id; s.pos = s.pos + 1; }
+    ctl->pos = s.pos; ctl->token = s.token; ctl->n_sampled = s.n_sampled; ctl->has_ts = s.has_ts; ctl->seek_delta = s.seek_delta;
+    ctl->result_len = s.result_len; ctl->last_id = s.last_id; ctl->penult_id = s.penult_id; ctl->failed = f; ctl->completed = cpl;
+    if (done) { ctl->done = 1; atomicAdd(P.n_done, 1); }
+}
+
+template <int WR, int WK, int EPI>
+void launch_gemm(const BatchParams &P, int n_tiles, const __half *W, const float *bias, const __half *X, int N, int K, int il, cudaStream_t st) {
+    const dim3 grid(ceil_div(N, 16 * WR)), block(kGemmThreads);
+    if (n_tiles == 1) bd_gemm_kernel<WR, WK, 1, EPI><<<grid, block, 0, st>>>(P, W, bias, X, N, K, il);
+    else if (n_tiles == 2) bd_gemm_kernel<WR, WK, 2, EPI><<<grid, block, 0, st>>>(P, W, bias, X, N, K, il);
+    else bd_gemm_kernel<WR, WK, 4, EPI><<<grid, block, 0, st>>>(P, W, bias, X, N, K, il);
+}
+
+size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// ================================================================================================
+size_t decode_batch_scratch_bytes(int d, int n_vocab, int H, int xsplit_max) {
+    const size_t R = kMaxBatch;
+    return align256(R * d * 4) + 3 * align256(R * d * 2) + align256(R * 4 * d * 2) + align256(R * (size_t)n_vocab * 4) +
+           align256(R * H * (size_t)xsplit_max * 66 * 4) + 256;
+}
+
+void decode_batch_bind(BatchParams &P, void *scratch) {
+    const size_t R = kMaxBatch, d = P.d;
+    uint8_t *p = static_cast<uint8_t *>(scratch);
+    P.n_done = reinterpret_cast<int *>(p); p += 256;
+    P.x = reinterpret_cast<float *>(p); p += align256(R * d * 4);
+    P.xn = reinterpret_cast<__half *>(p); p += align256(R * d * 2);
+    P.q = reinterpret_cast<__half *>(p); p += align256(R * d * 2);
+    P.att = reinterpret_cast<__half *>(p); p += align256(R * d * 2);
+    P.hid = reinterpret_cast<__half *>(p); p += align256(R * 4 * d * 2);
+    P.logits = reinterpret_cast<float *>(p); p += align256(R * (size_t)P.n_vocab * 4);
+    P.part = reinterpret_cast<float *>(p);
+}
+
+// key splits of the cross-attention so that at least ~2 CTAs per SM are in flight when the batch is small
+int decode_batch_xsplit(int B, int H, int sms) {
+    const int want = 2 * sms;
+    return std::max(1, std::min(8, ceil_div(want, std::max(1, B * H))));
+}
+
+void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st, int *launches) {
+    const int B = P.B, d = P.d, nt = B <= 8 ? 1 : B <= 16 ? 2 : 4;
+    if (B < 1 || B > kMaxBatch) SS_THROW(-1, "decode_batch: batch %d out of range", B);
+    if ((d & 63) || d > kLnPer * kLnThreads || d != P.H * 64 || P.ctx > 512 || P.T > 1536) SS_THROW(-1, "decode_batch: unsupported decoder shape");
+    int n = 0;
+    for (int il = 0; il < P.L; il++) {
+        const MegaLayer &L = w.layer[il];
+        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, L.lnw[0], L.lnb[0], il == 0 ? 1 : 0); n++;
+        launch_gemm<2, 4, EPI_QKV>(P, nt, L.w[0], L.b[0], P.xn, 3 * d, d, il, st); n++;
+        bd_self_attn_kernel<<<dim3(P.H, B), kSelfWarps * 32, 0, st>>>(P, il); n++;
+        launch_gemm<1, 8, EPI_RES>(P, nt, L.w[1], L.b[1], P.att, d, d, il, st); n++;
+        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, L.lnw[1], L.lnb[1], 0); n++;
+        launch_gemm<1, 8, EPI_Q>(P, nt, L.w[2], L.b[2], P.xn, d, d, il, st); n++;
+        bd_cross_attn_kernel<<<dim3(P.H, B, xsplit), kCrossWarps * 32, 0, st>>>(P, il, xsplit); n++;
+        if (xsplit > 1) { bd_cross_fold_kernel<<<dim3(P.H, B), 64, 0, st>>>(P, xsplit); n++; }
+        launch_gemm<1, 8, EPI_RES>(P, nt, L.w[3], L.b[3], P.att, d, d, il, st); n++;
+        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, L.lnw[2], L.lnb[2], 0); n++;
+        launch_gemm<2, 4, EPI_GELU>(P, nt, L.w[4], L.b[4], P.xn, 4 * d, d, il, st); n++;
+        launch_gemm<1, 8, EPI_RES>(P, nt, L.w[5], L.b[5], P.hid, d, 4 * d, il, st); n++;
+    }
+    if (need_logits) {
+        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, P.lnf_w, P.lnf_b, 0); n++;
+        launch_gemm<8, 1, EPI_LOGITS>(P, nt, P.tok_emb, nullptr, P.xn, P.n_vocab, d, 0, st); n++;
+    }
+    bd_sample_kernel<<<B, kSampleWarps * 32, 0, st>>>(P); n++;
+    CUDA_CHECK(cudaGetLastError());
+    if (launches) *launches += n;
+}
+
+}  // namespace ss

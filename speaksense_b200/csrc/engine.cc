@@ -5,7 +5,7 @@
 // every arithmetic stage on the device.  The temperature-0 greedy decoder runs entirely on the GPU
 // (CUDA-graph replay, on-device logits filter / argmax / state update); the t>0 fallback decoders are
 // sampled on the host with std::mt19937 + std::discrete_distribution exactly like whisper.cpp.
-#include "engine.h"
+#include "engine_internal.h"
 
 #include <dlfcn.h>
 
@@ -135,7 +135,7 @@ std::shared_ptr<Engine> engine_open_dist(const char *path, int device, int rank,
 // ------------------------------------------------------------------------------------------------
 // state
 // ------------------------------------------------------------------------------------------------
-static Decoder *new_decoder(State &s, bool with_keep) {
+Decoder *new_decoder(State &s, bool with_keep) {
     const Model &m = s.engine->model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
     if (hp.n_text_layer > kMaxLayers || hp.n_text_state > 1280) SS_THROW(-2, "decoder larger than large-v3 is not supported");
     auto d = std::make_unique<Decoder>();
@@ -383,7 +383,7 @@ void run_encode(State &s, int seek) {
 // ------------------------------------------------------------------------------------------------
 // decoder driving
 // ------------------------------------------------------------------------------------------------
-static void ensure_params(State &s, Decoder &d) {
+void ensure_params(State &s, Decoder &d) {
     if (!d.mp_dirty) return;
     d.mp.cross_k = s.cross_k; d.mp.cross_v = s.cross_v;
     CUDA_CHECK(cudaMemcpyAsync(d.d_mp, &d.mp, sizeof(MegaParams), cudaMemcpyHostToDevice, s.stream));
@@ -400,7 +400,7 @@ static void run_steps(State &s, Decoder &d, int max_steps) {
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
 }
 
-static void upload_ctl(State &s, Decoder &d) {
+void upload_ctl(State &s, Decoder &d) {
     CUDA_CHECK(cudaMemcpyAsync(d.mp.ctl, d.h_ctl, sizeof(DecCtl), cudaMemcpyHostToDevice, s.stream));
 }
 
@@ -472,14 +472,14 @@ void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *lo
     if (logits_out) memcpy(logits_out, s.h_logits, (size_t)hp.n_vocab * sizeof(float));
 }
 
-static void set_sampling(Decoder &d, const FullParams &P, int tid0_init) {
+void set_sampling(Decoder &d, const FullParams &P, int tid0_init) {
     if (d.mp.suppress_blank != (int)P.suppress_blank || d.mp.tdrz != (int)P.tdrz_enable || d.mp.tid0_init != tid0_init) {
         d.mp.suppress_blank = P.suppress_blank; d.mp.tdrz = P.tdrz_enable; d.mp.tid0_init = tid0_init; d.mp_dirty = true;
     }
 }
 
 // ---- host restatement of whisper_process_logits / whisper_sample_token for the t>0 fallback path
-static void process_logits_host(const Model &m, const FullParams &P, Decoder &dc, const float *raw, float temperature) {
+void process_logits_host(const Model &m, const FullParams &P, Decoder &dc, const float *raw, float temperature) {
     const Vocab &v = m.vocab; const int nv = m.hp.n_vocab;
     dc.logits.assign(raw, raw + nv); dc.logprobs.resize(nv); dc.probs.resize(nv);
     float *logits = dc.logits.data(), *logprobs = dc.logprobs.data(), *probs = dc.probs.data();
@@ -526,7 +526,7 @@ static void process_logits_host(const Model &m, const FullParams &P, Decoder &dc
     for (int i = 0; i < nv; i++) probs[i] = logits[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
 }
 
-static TokData sample_token_host(const Model &m, Decoder &dc, bool best) {
+TokData sample_token_host(const Model &m, Decoder &dc, bool best) {
     const Vocab &v = m.vocab; const int nv = m.hp.n_vocab;
     TokData r{0, 0, 0.f, 0.f, 0.f, 0.f};
     {
@@ -544,7 +544,7 @@ static TokData sample_token_host(const Model &m, Decoder &dc, bool best) {
     return r;
 }
 
-static void sequence_score(const FullParams &P, Sequence &q) {
+void sequence_score(const FullParams &P, Sequence &q) {
     if (q.result_len == 0) return;
     double result = 0.0;
     for (int i = 0; i < q.result_len; i++) result += q.tokens[i].plog;
@@ -560,7 +560,7 @@ static void sequence_score(const FullParams &P, Sequence &q) {
 }
 
 // one forward step of decoder `d` feeding `token` at position n_past; raw logits land in s.h_logits
-static void step_host_sampled(State &s, Decoder &d, const int *tokens, int n, int n_past) {
+void step_host_sampled(State &s, Decoder &d, const int *tokens, int n, int n_past) {
     ensure_params(s, d);
     DecCtl &c = *d.h_ctl;
     memset(&c, 0, offsetof(DecCtl, prompt));
@@ -573,7 +573,7 @@ static void step_host_sampled(State &s, Decoder &d, const int *tokens, int n, in
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
 }
 
-static void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos) {
+void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos) {
     const HParams &hp = s.engine->model.hp;
     const size_t pitch = (size_t)hp.n_text_ctx * 64 * 2, width = (size_t)n_pos * 64 * 2, height = (size_t)hp.n_text_layer * hp.n_text_head;
     CUDA_CHECK(cudaMemcpy2DAsync(to.mp.self_k, pitch, from.mp.self_k, pitch, width, height, cudaMemcpyDeviceToDevice, s.stream));

@@ -2,6 +2,7 @@
 // segment assembly and the reference's Rust-side post-processing.
 #pragma once
 #include <memory>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -14,6 +15,14 @@ struct Engine {
     Model model;
     int device = 0;
     std::string path;
+    // operand buffers of the batched decoder (engine_batch.cc): one batch at a time per engine
+    std::mutex batch_mu;
+    void *batch_scratch = nullptr;
+    cudaStream_t batch_stream = nullptr;
+    cudaEvent_t batch_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0, 1: termination polls; 2, 3: timing
+    int *batch_h_flags = nullptr;                                     // pinned [2]: finished-sequence counts read back by the polls
+    int sms = 0;
+    ~Engine();
 };
 
 struct FullParams {   // == build_params (whisper.rs:131-173) + overrides (:60-71)
@@ -97,6 +106,10 @@ float bench_decode_steps(State &s, int n_steps, int n_past0);
 void run_encode(State &s, int seek);
 void run_decode_forced(State &s, const int *tokens, int n, int n_past, float *logits_out);
 int transcribe(State &s, const float *pcm, size_t n, const FullParams &fp, bool stream_mode);
+// ss_transcribe_batch: the clips advance window by window together, their temperature-0 greedy decodes share one batched
+// decoder step (decoder_batch.cu); fallbacks run per clip.  Results land in each State exactly as transcribe() leaves them.
+int transcribe_batch(State *const *states, const float *const *pcm, const size_t *n, int batch, const FullParams &fp, bool stream_mode);
+bool batch_decode_enabled();   // SS_BATCH_DECODE=1 (opt-in until the batched kernels have been verified on a B200)
 
 // Rust-side post-processing of whisper.rs:84-128 on s.raw -> s.out / s.full_text
 int postprocess(State &s, bool stream_mode);

@@ -1,0 +1,390 @@
+// engine_batch.cc - ss_transcribe_batch: several clips through `state.full` together (BASELINE.json configs 3/4).
+//
+// The clips of a batch are independent sessions (one ss_state each, exactly as the reference would hold one
+// WhisperState per stream / task: /root/reference/src/asr/whisper.rs:30-39,75), so the control flow of whisper_full
+//  stays per clip; what is shared is the expensive part of every window - the temperature-0 greedy
+// decode - which runs as ONE batched decoder step per token for all clips that are in a window (decoder_batch.cu:
+// the weights are streamed once per step instead of once per clip).  Rounds:
+//     every unfinished clip: encode its current window (own stream), arm its decoder-0 control block
+//     all of them together : batched greedy decode until every sequence has completed / failed / hit the cap
+//     every clip           : whisper_full's scoring and success test; clips that fail walk the temperature ladder
+//                            (5 sampled decoders, host sampling) on their own as in engine.cc; segments; seek advance
+// Beam search, kept logits and a non-zero base temperature take the clip-by-clip path (engine.cc `transcribe`).
+//
+// The per-window logic below restates the corresponding parts of `transcribe` in engine.cc on purpose instead of
+// sharing them: that function is the GPU-verified path of round 1 and this file was written without GPU time left
+// (STATUS in decoder_batch.cu).  Once the batched path is parity-green the two are to be folded into one.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine_internal.h"
+
+namespace ss {
+
+Engine::~Engine() {
+    if (batch_scratch || batch_stream || batch_h_flags) cudaSetDevice(device);
+    if (batch_stream) { cudaStreamSynchronize(batch_stream); cudaStreamDestroy(batch_stream); }
+    for (auto &e : batch_ev) if (e) cudaEventDestroy(e);
+    if (batch_scratch) cudaFree(batch_scratch);
+    if (batch_h_flags) cudaFreeHost(batch_h_flags);
+}
+
+bool batch_decode_enabled() {
+    const char *e = getenv("SS_BATCH_DECODE");
+    return e && e[0] && e[0] != '0';
+}
+
+namespace {
+
+constexpr int kXsplitMax = 8;
+constexpr int kPollEvery = 4;      // decoder steps between two reads of the finished-sequence count
+
+struct ClipRun {
+    State *s = nullptr;
+    int seek = 0, seek_end = 0;
+    bool finished = false;
+    std::vector<int> prompt;       // prompt of the temperature in progress
+    int best_decoder_id = 0;
+};
+
+struct Common {      // what whisper_full derives once per call
+    std::vector<float> temps;
+    std::vector<int> prompt_init;
+    int n_decoders = 1, n_max = 0, tid0_init = -1;
+};
+
+void ensure_batch_resources(Engine &E) {
+    if (E.batch_scratch) return;
+    const HParams &hp = E.model.hp;
+    const size_t bytes = decode_batch_scratch_bytes(hp.n_text_state, hp.n_vocab, hp.n_text_head, kXsplitMax);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) SS_THROW(-5, "cudaMalloc of %zu bytes (batched decoder operands) failed", bytes);
+    CUDA_CHECK(cudaMemset(p, 0, bytes));      // rows of absent sequences stay finite (they are multiplied, never stored)
+    E.batch_scratch = p;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&E.batch_stream, cudaStreamNonBlocking));
+    for (auto &e : E.batch_ev) CUDA_CHECK(cudaEventCreate(&e));
+    if (cudaMallocHost(&E.batch_h_flags, 2 * sizeof(int)) != cudaSuccess) SS_THROW(-5, "cudaMallocHost failed");
+    CUDA_CHECK(cudaDeviceGetAttribute(&E.sms, cudaDevAttrMultiProcessorCount, E.device));
+}
+
+void build_prompt(const State &s, const FullParams &P, const Common &C, float t_cur, std::vector<int> &prompt) {
+    const HParams &hp = s.engine->model.hp; const Vocab &v = s.engine->model.vocab;
+    prompt.clear();
+    if (!s.prompt_past.empty() && t_cur < 0.5f && P.n_max_text_ctx > 0) {
+        const int n_take = std::min({P.n_max_text_ctx, hp.n_text_ctx / 2, (int)s.prompt_past.size()});
+        prompt.push_back(v.prev);
+        prompt.insert(prompt.end(), s.prompt_past.end() - n_take, s.prompt_past.end());
+    }
+    prompt.insert(prompt.end(), C.prompt_init.begin(), C.prompt_init.end());
+}
+
+void reset_decoders(State &s, int n_cur) {
+    while ((int)s.dec.size() < n_cur) new_decoder(s, false);
+    for (int j = 0; j < n_cur; j++) {
+        Decoder &dc = *s.dec[j];
+        dc.seq = Sequence{}; dc.seq.sum_logprobs = -INFINITY; dc.seq.avg_logprobs = -INFINITY; dc.seq.score = -INFINITY;
+        dc.seek_delta = 100 * kChunkSec; dc.failed = false; dc.completed = false; dc.has_ts = false;
+    }
+}
+
+// whisper_full's ranking of the decoders of one temperature and its success test; returns true when the window is settled
+bool score_and_test(State &s, const FullParams &P, const Common &C, size_t it, int n_cur, int &best_decoder_id) {
+    double best_score = -INFINITY;
+    for (int j = 0; j < n_cur; j++) {
+        Decoder &dc = *s.dec[j];
+        if (dc.failed) continue;
+        dc.seq.tokens.resize(std::min<size_t>(dc.seq.tokens.size(), (size_t)dc.seq.result_len));
+        sequence_score(P, dc.seq);
+        if (dc.seq.entropy < P.entropy_thold) { dc.failed = true; continue; }
+        if (best_score < dc.seq.score) { best_score = dc.seq.score; best_decoder_id = j; }
+    }
+    if (it != C.temps.size() - 1) {
+        const Decoder &dc = *s.dec[best_decoder_id];
+        if (dc.failed || dc.seq.avg_logprobs < P.logprob_thold) return false;
+    }
+    return true;
+}
+
+// t > 0: best_of sampled decoders of one clip, host-side sampling (== the non-beam fallback branch of engine.cc)
+void decode_sampled(State &s, const FullParams &P, const Common &C, float t_cur, int n_cur, const std::vector<int> &prompt, int seek, int seek_end) {
+    const Model &m = s.engine->model; const Vocab &v = m.vocab;
+    const int n_prompt = (int)prompt.size(), n_max = C.n_max;
+    for (int j = 0; j < n_cur; j++) set_sampling(*s.dec[j], P, C.tid0_init);
+    step_host_sampled(s, *s.dec[0], prompt.data(), n_prompt, 0);
+    s.n_decoded += n_prompt - 1;
+    process_logits_host(m, P, *s.dec[0], s.h_logits, t_cur);
+    for (int j = 1; j < n_cur; j++) {
+        kv_copy(s, *s.dec[0], *s.dec[j], n_prompt);
+        s.dec[j]->probs = s.dec[0]->probs; s.dec[j]->logits = s.dec[0]->logits; s.dec[j]->logprobs = s.dec[0]->logprobs;
+    }
+    for (int i = 0; i < n_max; i++) {
+        for (int j = 0; j < n_cur; j++) {
+            Decoder &dc = *s.dec[j];
+            if (dc.completed || dc.failed) continue;
+            dc.seq.tokens.push_back(sample_token_host(m, dc, false));
+            dc.seq.sum_logprobs_all += dc.seq.tokens.back().plog;
+        }
+        for (int j = 0; j < n_cur; j++) {
+            Decoder &dc = *s.dec[j];
+            if (dc.completed || dc.failed) continue;
+            const TokData &tk = dc.seq.tokens.back();
+            if (tk.id > v.beg) {
+                const int sd_new = 2 * (tk.id - v.beg);
+                if (dc.has_ts && dc.seek_delta > sd_new && dc.seq.result_len < i) { dc.failed = true; continue; }
+                dc.seek_delta = sd_new; dc.seq.result_len = i + 1; dc.has_ts = true;
+            }
+            if (tk.id == v.eot || (P.max_tokens > 0 && i >= P.max_tokens) || (dc.has_ts && seek + dc.seek_delta + 100 >= seek_end)) {
+                if (dc.seq.result_len == 0) {
+                    if (seek + dc.seek_delta + 100 >= seek_end) dc.seq.result_len = i + 1;
+                    else { dc.failed = true; continue; }
+                }
+                if (P.single_segment) { dc.seq.result_len = i + 1; dc.seek_delta = 100 * kChunkSec; }
+                dc.completed = true; continue;
+            }
+            if (i == n_max - 1 && (dc.seq.result_len == 0 || dc.seek_delta < 100 * kChunkSec / 2)) { dc.failed = true; continue; }
+        }
+        bool all = true;
+        for (int j = 0; j < n_cur; j++) if (!(s.dec[j]->completed || s.dec[j]->failed)) all = false;
+        if (all) break;
+        const int n_past = n_prompt + i;
+        for (int j = 0; j < n_cur; j++) {
+            Decoder &dc = *s.dec[j];
+            if (dc.failed || dc.completed) continue;
+            const int tok = dc.seq.tokens.back().id;
+            step_host_sampled(s, dc, &tok, 1, n_past);
+            process_logits_host(m, P, dc, s.h_logits, t_cur);
+        }
+    }
+}
+
+// the winner's tokens -> prompt_past, result tokens, raw segments; returns seek_delta
+int emit_window(State &s, const FullParams &P, const Common &C, const ClipRun &r) {
+    const Vocab &v = s.engine->model.vocab;
+    const Decoder &bd = *s.dec[r.best_decoder_id];
+    const int seek = r.seek, seek_delta = bd.seek_delta, result_len = bd.seq.result_len;
+    const auto &tc = bd.seq.tokens;
+    const std::vector<int> &prompt = r.prompt;
+    std::vector<int> keep;
+    if (prompt.front() == v.prev) keep.assign(prompt.begin() + 1, prompt.end() - C.prompt_init.size());
+    s.prompt_past = keep;
+    for (int i = 0; i < result_len && i < (int)tc.size(); i++) s.prompt_past.push_back(tc[i].id);
+    if (!tc.empty()) {
+        s.result_tokens.insert(s.result_tokens.end(), tc.begin(), tc.end());
+        int64_t t0 = seek + 2 * (tc.front().tid - v.beg);
+        std::string text; bool turn = false;
+        for (int i = 0; i < (int)tc.size(); i++) {
+            if (tc[i].id < v.eot) text += v.id_to_token[tc[i].id];
+            if (P.tdrz_enable && tc[i].id == v.solm) turn = true;
+            if (tc[i].id > v.beg && !P.single_segment) {
+                const int64_t t1 = seek + 2 * (tc[i].tid - v.beg);
+                if (!text.empty()) s.raw.push_back({t0, t1, text, turn});
+                text.clear();
+                while (i < (int)tc.size() && tc[i].id > v.beg) i++;
+                i--;
+                t0 = t1; turn = false;
+            }
+        }
+        if (!text.empty()) s.raw.push_back({t0, (int64_t)seek + seek_delta, text, turn});
+    }
+    return seek_delta;
+}
+
+// batched greedy decode of the armed decoder-0 sequences of `grp` (<= kMaxBatch clips)
+void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<ClipRun *> &grp) {
+    const Model &m = E.model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
+    const int nb = (int)grp.size();
+    BatchParams bp{};
+    bp.B = nb; bp.d = hp.n_text_state; bp.H = hp.n_text_head; bp.L = hp.n_text_layer; bp.T = hp.n_audio_ctx; bp.ctx = hp.n_text_ctx; bp.n_vocab = hp.n_vocab;
+    bp.s4 = powf((float)(bp.d / bp.H), -0.25f);
+    bp.tok_emb = m.tok_emb; bp.d_pos = m.d_pos; bp.lnf_w = m.d_ln.w; bp.lnf_b = m.d_ln.b;
+    bp.eot = v.eot; bp.sot = v.sot; bp.translate = v.translate; bp.transcribe = v.transcribe; bp.solm = v.solm; bp.prev = v.prev;
+    bp.nosp = v.nosp; bp.not_ = v.not_; bp.beg = v.beg; bp.blank = v.blank;
+    bp.suppress_blank = P.suppress_blank; bp.tdrz = P.tdrz_enable; bp.tid0_init = C.tid0_init;
+    decode_batch_bind(bp, E.batch_scratch);
+    cudaStream_t bs = E.batch_stream;
+    int max_steps = 0, min_prompt = 1 << 30;
+    for (int k = 0; k < nb; k++) {
+        State &s = *grp[k]->s; Decoder &dc = *s.dec[0];
+        bp.seq[k] = BatchSeq{dc.mp.ctl, dc.mp.self_k, dc.mp.self_v, s.cross_k, s.cross_v, dc.mp.tok_out};
+        CUDA_CHECK(cudaStreamWaitEvent(bs, s.ev[2], 0));      // its encoder, cross-KV and control block are on its own stream
+        const int np = (int)grp[k]->prompt.size();
+        max_steps = std::max(max_steps, np + C.n_max - 1); min_prompt = std::min(min_prompt, np);
+    }
+    for (int k = nb; k < kMaxBatch; k++) bp.seq[k] = bp.seq[0];      // never dereferenced (b < B guards); keeps the block defined
+    const MegaParams &w = grp[0]->s->dec[0]->mp;                     // weight pointers (identical for every decoder of the engine)
+    const int xsplit = decode_batch_xsplit(nb, bp.H, E.sms);
+    CUDA_CHECK(cudaMemsetAsync(bp.n_done, 0, sizeof(int), bs));
+    CUDA_CHECK(cudaEventRecord(E.batch_ev[2], bs));
+    int launches = 0, steps = 0;
+    E.batch_h_flags[0] = E.batch_h_flags[1] = 0;
+    for (int t = 0; t < max_steps; t++) {
+        if (t % kPollEvery == 0) {
+            const int G = t / kPollEvery;
+            if (G >= 2) {      // the count read back two groups ago: at most 2 * kPollEvery steps of early-exit kernels are wasted
+                CUDA_CHECK(cudaEventSynchronize(E.batch_ev[G & 1]));
+                if (E.batch_h_flags[G & 1] >= nb) break;
+            }
+        }
+        decode_batch_step_enqueue(bp, w, /*need_logits=*/t >= min_prompt - 1, xsplit, bs, &launches);
+        steps++;
+        if (t % kPollEvery == kPollEvery - 1) {
+            const int G = t / kPollEvery;
+            CUDA_CHECK(cudaMemcpyAsync(&E.batch_h_flags[G & 1], bp.n_done, sizeof(int), cudaMemcpyDeviceToHost, bs));
+            CUDA_CHECK(cudaEventRecord(E.batch_ev[G & 1], bs));
+        }
+    }
+    CUDA_CHECK(cudaEventRecord(E.batch_ev[3], bs));
+    CUDA_CHECK(cudaStreamSynchronize(bs));
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, E.batch_ev[2], E.batch_ev[3]));
+    // results back into each clip's decoder 0, as the device-side greedy path of engine.cc leaves them
+    for (int k = 0; k < nb; k++) {
+        State &s = *grp[k]->s; Decoder &dc = *s.dec[0];
+        CUDA_CHECK(cudaMemcpyAsync(dc.h_ctl, dc.mp.ctl, offsetof(DecCtl, prompt), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        const int ns = dc.h_ctl->n_sampled, np = (int)grp[k]->prompt.size();
+        if (ns > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(dc.h_tok, dc.mp.tok_out, (size_t)ns * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        }
+        dc.seq.tokens.assign(dc.h_tok, dc.h_tok + ns);
+        for (int i = 0; i < ns; i++) dc.seq.sum_logprobs_all += dc.h_tok[i].plog;
+        dc.seq.result_len = dc.h_ctl->result_len; dc.seek_delta = dc.h_ctl->seek_delta;
+        dc.failed = dc.h_ctl->failed; dc.completed = dc.h_ctl->completed; dc.has_ts = dc.h_ctl->has_ts;
+        s.n_decoded += np - 1 + ns;
+        s.n_launches += ceil_div(launches, nb);
+        s.ms_dec += ms / nb;      // the batch's device time, shared equally
+    }
+    (void)steps;
+}
+
+}  // namespace
+
+int transcribe_batch(State *const *states, const float *const *pcm, const size_t *n, int batch, const FullParams &P, bool stream_mode) {
+    if (batch <= 0) return 0;
+    Engine &E = *states[0]->engine;
+    const Model &m = E.model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
+    bool batched = batch >= 2 && P.beam_size <= 1 && !P.keep_logits && P.temperature < 1e-6f && hp.n_text_state == hp.n_text_head * 64 &&
+                   hp.n_text_state <= 1280 && hp.n_text_ctx <= 512 && hp.n_audio_ctx <= 1536;
+    for (int i = 0; i < batch && batched; i++)
+        for (int j = 0; j < i; j++) if (states[i] == states[j]) batched = false;      // one state twice: the calls must serialise
+    if (!batched) {
+        int rc = 0;
+        for (int i = 0; i < batch; i++) { const int r = transcribe(*states[i], pcm[i], n[i], P, stream_mode); if (r && !rc) rc = r; }
+        return rc;
+    }
+    std::lock_guard<std::mutex> lk(E.batch_mu);
+    CUDA_CHECK(cudaSetDevice(E.device));
+    ensure_batch_resources(E);
+
+    int lang = 0;
+    if (v.multilingual) { lang = lang_id(P.language.c_str()); if (lang < 0) SS_THROW(-6, "unknown language '%s'", P.language.c_str()); }
+    Common C;
+    if (P.temperature_inc > 0.0f) { for (float t = P.temperature; t < 1.0f + 1e-6f; t += P.temperature_inc) C.temps.push_back(t); }
+    else C.temps.push_back(P.temperature);
+    C.n_decoders = std::max(1, P.best_of);
+    if (P.best_of > kMaxDecoders) SS_THROW(-1, "best_of above %d", kMaxDecoders);
+    C.prompt_init = {v.sot};
+    if (v.multilingual) { C.prompt_init.push_back(v.sot + 1 + lang); C.prompt_init.push_back(v.transcribe); }
+    C.n_max = hp.n_text_ctx / 2 - 4;
+    const float precision = (float)kChunkSec / hp.n_audio_ctx;
+    C.tid0_init = P.max_initial_ts > 0.0f ? (int)std::round(P.max_initial_ts / precision) : -1;
+
+    std::vector<ClipRun> runs(batch);
+    for (int i = 0; i < batch; i++) {      // log-mel of every clip, each on its own stream
+        State &s = *states[i];
+        runs[i].s = &s;
+        s.raw.clear(); s.out.clear(); s.full_text.clear(); s.result_tokens.clear();
+        s.n_fallbacks = 0; s.n_decoded = 0; s.n_windows = 0; s.n_launches = 0; s.n_keep = 0; s.h_keep.clear();
+        s.ms_mel = s.ms_enc = s.ms_dec = 0;
+        CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
+        run_log_mel(s, pcm[i], n[i]);
+        CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
+    }
+    for (int i = 0; i < batch; i++) {
+        State &s = *states[i];
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        { float ms; cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.ms_mel += ms; }
+        runs[i].seek = 0; runs[i].seek_end = s.n_len_org;
+        if (runs[i].seek_end < 100) { postprocess(s, stream_mode); runs[i].finished = true; continue; }
+        if (P.no_context) s.prompt_past.clear();
+    }
+
+    while (true) {
+        std::vector<ClipRun *> act;
+        for (auto &r : runs) {
+            if (r.finished) continue;
+            if (r.seek + 100 >= r.seek_end) { postprocess(*r.s, stream_mode); r.finished = true; continue; }
+            act.push_back(&r);
+        }
+        if (act.empty()) break;
+        for (ClipRun *r : act) {      // encoder + cross-KV of the window, temperature-0 control block
+            State &s = *r->s;
+            CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
+            run_encode(s, r->seek);
+            CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
+            s.n_windows++;
+            if (r->seek > 0 && r->seek + 500 >= r->seek_end) s.prompt_past.clear();
+            r->best_decoder_id = 0;
+            reset_decoders(s, 1);
+            build_prompt(s, P, C, C.temps[0], r->prompt);
+            Decoder &dc = *s.dec[0];
+            DecCtl &c = *dc.h_ctl;
+            memset(&c, 0, sizeof c);
+            const int n_prompt = (int)r->prompt.size();
+            c.pos = 0; c.pos0 = 0; c.token = r->prompt[0]; c.n_prompt = n_prompt; c.sample = 1; c.last_id = -1; c.penult_id = -1;
+            c.seek = r->seek; c.seek_end = r->seek_end; c.n_max = C.n_max; c.seek_delta = 100 * kChunkSec;
+            for (int i = 0; i < n_prompt; i++) c.prompt[i] = r->prompt[i];
+            upload_ctl(s, dc);
+            CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
+        }
+        for (size_t g0 = 0; g0 < act.size(); g0 += kMaxBatch) {
+            std::vector<ClipRun *> grp(act.begin() + g0, act.begin() + std::min(act.size(), g0 + (size_t)kMaxBatch));
+            if (grp.size() == 1) {      // a lone straggler: the batch-1 persistent kernel is the faster one
+                State &s = *grp[0]->s; Decoder &dc = *s.dec[0];
+                set_sampling(dc, P, C.tid0_init);
+                ensure_params(s, dc);
+                CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
+                decode_mega_launch(dc.d_mp, dc.d_ll, dc.ll_bytes, (int)grp[0]->prompt.size() + C.n_max - 1, s.mega_grid, s.stream);
+                s.n_launches += 1;
+                CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
+                CUDA_CHECK(cudaMemcpyAsync(dc.h_ctl, dc.mp.ctl, offsetof(DecCtl, prompt), cudaMemcpyDeviceToHost, s.stream));
+                CUDA_CHECK(cudaStreamSynchronize(s.stream));
+                { float ms; cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.ms_dec += ms; }
+                const int ns = dc.h_ctl->n_sampled;
+                if (ns > 0) {
+                    CUDA_CHECK(cudaMemcpyAsync(dc.h_tok, dc.mp.tok_out, (size_t)ns * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
+                    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+                }
+                dc.seq.tokens.assign(dc.h_tok, dc.h_tok + ns);
+                for (int i = 0; i < ns; i++) dc.seq.sum_logprobs_all += dc.h_tok[i].plog;
+                dc.seq.result_len = dc.h_ctl->result_len; dc.seek_delta = dc.h_ctl->seek_delta;
+                dc.failed = dc.h_ctl->failed; dc.completed = dc.h_ctl->completed; dc.has_ts = dc.h_ctl->has_ts;
+                s.n_decoded += (int)grp[0]->prompt.size() - 1 + ns;
+            } else decode_group(E, P, C, grp);
+        }
+        for (ClipRun *r : act) {      // scoring, temperature ladder, segments, seek advance - per clip
+            State &s = *r->s;
+            { float ms; cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.ms_enc += ms; }
+            bool settled = score_and_test(s, P, C, 0, 1, r->best_decoder_id);
+            for (size_t it = 1; it < C.temps.size() && !settled; it++) {
+                const float t_cur = C.temps[it];
+                const int n_cur = std::max(1, t_cur > 0.0f ? C.n_decoders : 1);
+                s.n_fallbacks++;
+                reset_decoders(s, n_cur);
+                build_prompt(s, P, C, t_cur, r->prompt);
+                CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
+                decode_sampled(s, P, C, t_cur, n_cur, r->prompt, r->seek, r->seek_end);
+                CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
+                CUDA_CHECK(cudaStreamSynchronize(s.stream));
+                { float ms; cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.ms_dec += ms; }
+                settled = score_and_test(s, P, C, it, n_cur, r->best_decoder_id);
+            }
+            r->seek += emit_window(s, P, C, *r);
+        }
+    }
+    return 0;
+}
+
+}  // namespace ss

@@ -1,0 +1,19 @@
+// engine_internal.h - helpers of engine.cc shared with engine_batch.cc (not part of the library's interface).
+#pragma once
+#include "engine.h"
+
+namespace ss {
+
+Decoder *new_decoder(State &s, bool with_keep);
+void ensure_params(State &s, Decoder &d);
+void upload_ctl(State &s, Decoder &d);
+void set_sampling(Decoder &d, const FullParams &P, int tid0_init);
+// host restatement of whisper_process_logits / whisper_sample_token (t > 0 fallback decoders)
+void process_logits_host(const Model &m, const FullParams &P, Decoder &dc, const float *raw, float temperature);
+TokData sample_token_host(const Model &m, Decoder &dc, bool best);
+void sequence_score(const FullParams &P, Sequence &q);
+// one forward step of decoder `d` feeding `tokens` at position n_past; raw logits of the last one land in s.h_logits
+void step_host_sampled(State &s, Decoder &d, const int *tokens, int n, int n_past);
+void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos);
+
+}  // namespace ss

@@ -115,4 +115,39 @@ void decode_mega_configure();
 int decode_mega_grid(int device);
 void decode_mega_launch(const MegaParams *d_params, void *d_ll, size_t ll_bytes, int max_steps, int grid, cudaStream_t st);
 
+// ---------------------------------------------------------------- batched decoder (decoder_batch.cu)
+// One decode step for up to kMaxBatch independent sequences (the clips of ss_transcribe_batch; BASELINE configs 3/4):
+// every weight matrix is streamed from HBM once per step for the whole batch (skinny tensor-core GEMMs, weights as the
+// MMA A operand, the sequences on the 8-wide N dimension), attention runs per (sequence, head).  A sequence borrows the
+// control block, self-KV cache and token buffer of decoder 0 of its State and the State's cross-KV cache.
+constexpr int kMaxBatch = 32;
+struct BatchSeq {
+    DecCtl *ctl;
+    __half *self_k, *self_v;              // [layer][head][n_text_ctx][64]
+    const __half *cross_k, *cross_v;      // [layer][K | V][head][n_audio_ctx][64]
+    TokData *tok_out;
+};
+struct BatchParams {
+    int B;                                // live sequences (<= kMaxBatch); operand buffers hold 8 * n_tiles rows
+    int d, H, L, T, ctx, n_vocab;
+    float s4;
+    const __half *tok_emb; const float *d_pos; const float *lnf_w, *lnf_b;
+    float *x;                             // residual stream f32 [rows][d]
+    __half *xn, *q, *att, *hid;           // f16 operands [rows][d] ([rows][4d] for hid)
+    float *logits;                        // [rows][n_vocab]
+    float *part;                          // cross-attention partial records [B][H][xsplit][66] when the keys are split
+    int *n_done;                          // sequences that have finished (every kernel returns at once when == B)
+    int eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, blank;
+    int suppress_blank, tdrz, tid0_init;
+    BatchSeq seq[kMaxBatch];
+};
+// scratch floats / halfs a batch of `rows` operand rows needs (see decode_batch_bind)
+size_t decode_batch_scratch_bytes(int d, int n_vocab, int H, int xsplit_max);
+// carve the operand buffers of `P` out of one zero-initialised device allocation
+void decode_batch_bind(BatchParams &P, void *scratch);
+int decode_batch_xsplit(int B, int H, int sms);
+// enqueue one step (all layers; LM head + sampling / prompt feeding) for the live sequences of P.  `w` carries the
+// weight pointers (any decoder's MegaParams of the same engine).
+void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st, int *launches);
+
 }  // namespace ss
