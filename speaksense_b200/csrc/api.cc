@@ -152,7 +152,7 @@ int ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *cons
         if (!e || !states || !pcm || !n || batch < 0) SS_THROW(SS_ERR_INVALID, "null argument");
         for (int i = 0; i < batch; i++)
             if (!states[i] || states[i]->s->engine.get() != e->e.get() || (!pcm[i] && n[i])) SS_THROW(SS_ERR_INVALID, "bad state / clip %d", i);
-        if (batch_decode_enabled()) {      // SS_BATCH_DECODE=1: one batched decoder step per token for all clips (engine_batch.cc)
+        if (batch_decode_enabled()) {      // one batched decoder step per token for all clips (engine_batch.cc); SS_BATCH_DECODE=0: clip by clip
             std::vector<State *> st(batch);
             for (int i = 0; i < batch; i++) st[i] = states[i]->s;
             return transcribe_batch(st.data(), pcm, n, batch, make_params(p), p && p->stream_mode);

@@ -17,9 +17,10 @@
 // greedy sampling and whisper_full's per-token bookkeeping are restated per sequence in bd_sample_kernel
 // (== lm_epilogue + sample_and_update of decoder_mega.cu).
 //
-// STATUS: written at the end of round 1 without GPU time left - compiled for sm_100a, NOT yet run.  It is therefore
-// opt-in (SS_BATCH_DECODE=1, see engine_batch.cc); the default ss_transcribe_batch still decodes clip by clip.
+// Measured (round 1, tools/batch_bench.py, profiles/r1e_*): 32 x 30 s clips, large-v3, one B200.  SS_BATCH_DECODE=0 gives
+// ss_transcribe_batch the clip-by-clip decode back.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -28,6 +29,13 @@ namespace ss {
 namespace {
 
 enum : int { EPI_QKV = 0, EPI_RES, EPI_Q, EPI_GELU, EPI_LOGITS };
+
+// Programmatic dependent launch: every kernel of a step lets its successor start at once (launch_dependents) and itself
+// waits for its predecessor (wait) only where it first touches something the predecessor wrote.  What a GEMM does before
+// the wait - issuing the loads of its first weight fragments, which are static - overlaps the predecessor's execution, and
+// every kernel's launch latency and ramp-up hide behind the previous one.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 __device__ __forceinline__ float gelu16(float x) {
@@ -97,6 +105,11 @@ __global__ void __launch_bounds__(kLnThreads) bd_ln_kernel(const __grid_constant
                                                            const float *__restrict__ lb, int embed) {
     __shared__ float red[2][8];
     const int b = blockIdx.x, tid = threadIdx.x, d = P.d;
+    pdl_trigger();
+    float w[kLnPer], bb[kLnPer];      // the affine parameters are static: fetched before the wait
+#pragma unroll
+    for (int k = 0; k < kLnPer; k++) { const int i = min(tid + k * kLnThreads, d - 1); w[k] = __ldg(lw + i); bb[k] = __ldg(lb + i); }
+    pdl_wait();
     const DecCtl *ctl = P.seq[b].ctl;
     if (ctl->done) return;
     float *x = P.x + (size_t)b * d;
@@ -123,43 +136,40 @@ __global__ void __launch_bounds__(kLnThreads) bd_ln_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < kLnPer; k++) {
         const int i = tid + k * kLnThreads;
-        if (i < d) y[i] = __float2half_rn((v[k] - mean) * scale * lw[i] + lb[i]);
+        if (i < d) y[i] = __float2half_rn((v[k] - mean) * scale * w[k] + bb[k]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // skinny GEMM: out[b][n] = sum_k W[n][k] * X[b][k]  (+ epilogue), b < 8 * NT
 // ------------------------------------------------------------------------------------------------
+// `bias` already added by the caller where the kind has one; `res` = the prefetched residual (EPI_RES)
 template <int EPI>
-__device__ __forceinline__ void bd_epilogue(const BatchParams &P, const float *__restrict__ bias, int il, int row, int b, float v) {
-    if (EPI == EPI_LOGITS) { P.logits[(size_t)b * P.n_vocab + row] = v; return; }
-    const DecCtl *ctl = P.seq[b].ctl;
-    if (ctl->done) return;
-    v += bias[row];
+__device__ __forceinline__ void bd_epilogue(const BatchParams &P, int il, int row, int b, float v, float res) {
     const int d = P.d;
-    if (EPI == EPI_QKV) {
+    if (EPI == EPI_LOGITS) P.logits[(size_t)b * P.n_vocab + row] = v;
+    else if (EPI == EPI_QKV) {
         if (row < d) P.q[(size_t)b * d + row] = __float2half_rn(v * P.s4);
         else {
             const bool is_k = row < 2 * d;
-            const int n = row - (is_k ? d : 2 * d), pos = ctl->pos;
+            const int n = row - (is_k ? d : 2 * d), pos = P.seq[b].ctl->pos;
             __half *cache = (is_k ? P.seq[b].self_k : P.seq[b].self_v) + (size_t)il * P.ctx * d;
             cache[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = __float2half_rn(is_k ? v * P.s4 : v);
         }
-    } else if (EPI == EPI_RES) {
-        P.x[(size_t)b * d + row] += v;
-    } else if (EPI == EPI_Q) {
-        P.q[(size_t)b * d + row] = __float2half_rn(v * P.s4);
-    } else if (EPI == EPI_GELU) {
-        P.hid[(size_t)b * 4 * d + row] = __float2half_rn(gelu16(v));
-    }
+    } else if (EPI == EPI_RES) P.x[(size_t)b * d + row] = res + v;
+    else if (EPI == EPI_Q) P.q[(size_t)b * d + row] = __float2half_rn(v * P.s4);
+    else if (EPI == EPI_GELU) P.hid[(size_t)b * 4 * d + row] = __float2half_rn(gelu16(v));
 }
 
 constexpr int kGemmThreads = 256;
+constexpr int kGemmU = 5;      // 32-wide K blocks in flight per warp (5 KB of weights): K = 1280 split 8 ways is one round
 template <int WR, int WK, int NT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_constant__ BatchParams P, const __half *__restrict__ W,
                                                                const float *__restrict__ bias, const __half *__restrict__ X, int N, int K, int il) {
     static_assert(WR * WK == 8, "8 warps per CTA");
-    if (*P.n_done >= P.B) return;
+    constexpr int U = kGemmU;
+    constexpr int TOTAL = WR * 16 * 8 * NT;                                   // outputs of the CTA
+    constexpr int NOUT = (TOTAL + kGemmThreads - 1) / kGemmThreads;           // per thread in the epilogue
     __shared__ float red[WR][WK][8 * NT][17];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wr = warp / WK, wk = warp % WK;
@@ -169,16 +179,46 @@ __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_cons
     const uint4 *wa = reinterpret_cast<const uint4 *>(W + (size_t)ra * K) + t;
     const uint4 *wb = reinterpret_cast<const uint4 *>(W + (size_t)rb * K) + t;
     const uint4 *xp = reinterpret_cast<const uint4 *>(X + (size_t)g * K) + t;         // n-tile nt: + nt * K (8 rows of K / 8 vectors)
+    pdl_trigger();
+    uint4 a[U], c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {      // first round of weight fragments: static data, in flight while the predecessor still runs
+        const int bi = min(blk0 + u, blk1 - 1);      // a short tail re-reads the last block; its products are skipped below
+        a[u] = __ldcs(wa + bi * 4); c[u] = __ldcs(wb + bi * 4);
+    }
+    float pb[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+        const int idx = tid + k * kGemmThreads;
+        const int row = (blockIdx.x * WR + idx / (16 * 8 * NT)) * 16 + (idx & 15);
+        pb[k] = (EPI != EPI_LOGITS && idx < TOTAL && row < N) ? __ldg(bias + row) : 0.f;
+    }
+    pdl_wait();
+    if (*P.n_done >= P.B) return;
+    // what the epilogue needs from the predecessor (finished flags, the residual): fetched now, used after the tiles
+    bool live[2];
+    float pr[NOUT];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {      // a thread's outputs alternate between two sequences at most (512 / 16 is a multiple of 8 * NT)
+        const int b = ((tid + k * kGemmThreads) >> 4) % (8 * NT);
+        live[k] = b < P.B && (EPI == EPI_LOGITS || !P.seq[b].ctl->done);
+    }
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+        const int idx = tid + k * kGemmThreads;
+        const int b = (idx >> 4) % (8 * NT), row = (blockIdx.x * WR + idx / (16 * 8 * NT)) * 16 + (idx & 15);
+        pr[k] = (EPI == EPI_RES && idx < TOTAL && row < N && b < P.B) ? P.x[(size_t)b * P.d + row] : 0.f;
+    }
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
-    constexpr int U = 4;      // K blocks in flight per warp: 4 KB of weights
     for (int blk = blk0; blk < blk1; blk += U) {
-        uint4 a[U], c[U];
+        if (blk != blk0) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int bi = min(blk + u, blk1 - 1);      // the tail re-reads the last block; its products are skipped below
-            a[u] = __ldcs(wa + bi * 4); c[u] = __ldcs(wb + bi * 4);
+            for (int u = 0; u < U; u++) {
+                const int bi = min(blk + u, blk1 - 1);
+                a[u] = __ldcs(wa + bi * 4); c[u] = __ldcs(wb + bi * 4);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -199,13 +239,16 @@ __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_cons
         red[wr][wk][nt * 8 + 2 * t][g + 8] = acc[nt][2]; red[wr][wk][nt * 8 + 2 * t + 1][g + 8] = acc[nt][3];
     }
     __syncthreads();
-    for (int idx = tid; idx < WR * 16 * 8 * NT; idx += kGemmThreads) {
+#pragma unroll
+    for (int k = 0; k < NOUT; k++) {
+        const int idx = tid + k * kGemmThreads;
         const int r = idx & 15, b = (idx >> 4) % (8 * NT), w2 = idx / (16 * 8 * NT);
+        if (idx >= TOTAL) break;
         float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < WK; k++) v += red[w2][k][b][r];
+        for (int kk = 0; kk < WK; kk++) v += red[w2][kk][b][r];
         const int row = (blockIdx.x * WR + w2) * 16 + r;
-        if (row < N && b < P.B) bd_epilogue<EPI>(P, bias, il, row, b, v);
+        if (row < N && live[k & 1]) bd_epilogue<EPI>(P, il, row, b, v + pb[k], pr[k]);
     }
 }
 
@@ -279,6 +322,8 @@ __global__ void __launch_bounds__(kSelfWarps * 32) bd_self_attn_kernel(const __g
     __shared__ float red[kSelfWarps][64];
     __shared__ float red1[2 * kSelfWarps];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, d = P.d;
+    pdl_trigger();
+    pdl_wait();
     const DecCtl *ctl = P.seq[b].ctl;
     if (ctl->done) return;
     const int n = ctl->pos + 1;
@@ -298,6 +343,8 @@ __global__ void __launch_bounds__(kCrossWarps * 32) bd_cross_attn_kernel(const _
     __shared__ float red[kCrossWarps][64];
     __shared__ float red1[2 * kCrossWarps];
     const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x, d = P.d, T = P.T;
+    pdl_trigger();
+    pdl_wait();
     const DecCtl *ctl = P.seq[b].ctl;
     if (ctl->done) return;
     if (tid < 64) q[tid] = __half2float(P.q[(size_t)b * d + h * 64 + tid]);
@@ -316,6 +363,8 @@ __global__ void __launch_bounds__(kCrossWarps * 32) bd_cross_attn_kernel(const _
 }
 __global__ void __launch_bounds__(64) bd_cross_fold_kernel(const __grid_constant__ BatchParams P, int S) {
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (P.seq[b].ctl->done) return;
     const float *rec = P.part + ((size_t)b * P.H + h) * S * 66;
     float M = -INFINITY;
@@ -359,6 +408,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __gr
     __shared__ float rs[2][kSampleWarps];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DecCtl *ctl = P.seq[b].ctl;
+    pdl_trigger();
+    pdl_wait();
     if (tid == 0) {
         SeqState s;
         s.pos = ctl->pos; s.pos0 = ctl->pos0; s.token = ctl->token; s.done = ctl->done; s.n_sampled = ctl->n_sampled; s.has_ts = ctl->has_ts;
@@ -444,12 +495,27 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __gr
     if (done) { ctl->done = 1; atomicAdd(P.n_done, 1); }
 }
 
+bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("SS_BATCH_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 template <int WR, int WK, int EPI>
 void launch_gemm(const BatchParams &P, int n_tiles, const __half *W, const float *bias, const __half *X, int N, int K, int il, cudaStream_t st) {
     const dim3 grid(ceil_div(N, 16 * WR)), block(kGemmThreads);
-    if (n_tiles == 1) bd_gemm_kernel<WR, WK, 1, EPI><<<grid, block, 0, st>>>(P, W, bias, X, N, K, il);
-    else if (n_tiles == 2) bd_gemm_kernel<WR, WK, 2, EPI><<<grid, block, 0, st>>>(P, W, bias, X, N, K, il);
-    else bd_gemm_kernel<WR, WK, 4, EPI><<<grid, block, 0, st>>>(P, W, bias, X, N, K, il);
+    if (n_tiles == 1) launch(bd_gemm_kernel<WR, WK, 1, EPI>, grid, block, st, P, W, bias, X, N, K, il);
+    else if (n_tiles == 2) launch(bd_gemm_kernel<WR, WK, 2, EPI>, grid, block, st, P, W, bias, X, N, K, il);
+    else launch(bd_gemm_kernel<WR, WK, 4, EPI>, grid, block, st, P, W, bias, X, N, K, il);
 }
 
 size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -487,26 +553,27 @@ void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool n
     if (B < 1 || B > kMaxBatch) SS_THROW(-1, "decode_batch: batch %d out of range", B);
     if ((d & 63) || d > kLnPer * kLnThreads || d != P.H * 64 || P.ctx > 512 || P.T > 1536) SS_THROW(-1, "decode_batch: unsupported decoder shape");
     int n = 0;
+    const dim3 ln_block(kLnThreads);
     for (int il = 0; il < P.L; il++) {
         const MegaLayer &L = w.layer[il];
-        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, L.lnw[0], L.lnb[0], il == 0 ? 1 : 0); n++;
+        launch(bd_ln_kernel, dim3(B), ln_block, st, P, L.lnw[0], L.lnb[0], il == 0 ? 1 : 0); n++;
         launch_gemm<2, 4, EPI_QKV>(P, nt, L.w[0], L.b[0], P.xn, 3 * d, d, il, st); n++;
-        bd_self_attn_kernel<<<dim3(P.H, B), kSelfWarps * 32, 0, st>>>(P, il); n++;
+        launch(bd_self_attn_kernel, dim3(P.H, B), dim3(kSelfWarps * 32), st, P, il); n++;
         launch_gemm<1, 8, EPI_RES>(P, nt, L.w[1], L.b[1], P.att, d, d, il, st); n++;
-        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, L.lnw[1], L.lnb[1], 0); n++;
+        launch(bd_ln_kernel, dim3(B), ln_block, st, P, L.lnw[1], L.lnb[1], 0); n++;
         launch_gemm<1, 8, EPI_Q>(P, nt, L.w[2], L.b[2], P.xn, d, d, il, st); n++;
-        bd_cross_attn_kernel<<<dim3(P.H, B, xsplit), kCrossWarps * 32, 0, st>>>(P, il, xsplit); n++;
-        if (xsplit > 1) { bd_cross_fold_kernel<<<dim3(P.H, B), 64, 0, st>>>(P, xsplit); n++; }
+        launch(bd_cross_attn_kernel, dim3(P.H, B, xsplit), dim3(kCrossWarps * 32), st, P, il, xsplit); n++;
+        if (xsplit > 1) { launch(bd_cross_fold_kernel, dim3(P.H, B), dim3(64), st, P, xsplit); n++; }
         launch_gemm<1, 8, EPI_RES>(P, nt, L.w[3], L.b[3], P.att, d, d, il, st); n++;
-        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, L.lnw[2], L.lnb[2], 0); n++;
+        launch(bd_ln_kernel, dim3(B), ln_block, st, P, L.lnw[2], L.lnb[2], 0); n++;
         launch_gemm<2, 4, EPI_GELU>(P, nt, L.w[4], L.b[4], P.xn, 4 * d, d, il, st); n++;
         launch_gemm<1, 8, EPI_RES>(P, nt, L.w[5], L.b[5], P.hid, d, 4 * d, il, st); n++;
     }
     if (need_logits) {
-        bd_ln_kernel<<<B, kLnThreads, 0, st>>>(P, P.lnf_w, P.lnf_b, 0); n++;
-        launch_gemm<8, 1, EPI_LOGITS>(P, nt, P.tok_emb, nullptr, P.xn, P.n_vocab, d, 0, st); n++;
+        launch(bd_ln_kernel, dim3(B), ln_block, st, P, P.lnf_w, P.lnf_b, 0); n++;
+        launch_gemm<8, 1, EPI_LOGITS>(P, nt, P.tok_emb, (const float *)nullptr, P.xn, P.n_vocab, d, 0, st); n++;
     }
-    bd_sample_kernel<<<B, kSampleWarps * 32, 0, st>>>(P); n++;
+    launch(bd_sample_kernel, dim3(B), dim3(kSampleWarps * 32), st, P); n++;
     CUDA_CHECK(cudaGetLastError());
     if (launches) *launches += n;
 }

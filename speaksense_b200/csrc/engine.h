@@ -109,7 +109,7 @@ int transcribe(State &s, const float *pcm, size_t n, const FullParams &fp, bool 
 // ss_transcribe_batch: the clips advance window by window together, their temperature-0 greedy decodes share one batched
 // decoder step (decoder_batch.cu); fallbacks run per clip.  Results land in each State exactly as transcribe() leaves them.
 int transcribe_batch(State *const *states, const float *const *pcm, const size_t *n, int batch, const FullParams &fp, bool stream_mode);
-bool batch_decode_enabled();   // SS_BATCH_DECODE=1 (opt-in until the batched kernels have been verified on a B200)
+bool batch_decode_enabled();   // default on; SS_BATCH_DECODE=0 disables
 
 // Rust-side post-processing of whisper.rs:84-128 on s.raw -> s.out / s.full_text
 int postprocess(State &s, bool stream_mode);

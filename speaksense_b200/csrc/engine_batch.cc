@@ -11,9 +11,9 @@
 //                            (5 sampled decoders, host sampling) on their own as in engine.cc; segments; seek advance
 // Beam search, kept logits and a non-zero base temperature take the clip-by-clip path (engine.cc `transcribe`).
 //
-// The per-window logic below restates the corresponding parts of `transcribe` in engine.cc on purpose instead of
-// sharing them: that function is the GPU-verified path of round 1 and this file was written without GPU time left
-// (STATUS in decoder_batch.cu).  Once the batched path is parity-green the two are to be folded into one.
+// The per-window logic below restates the corresponding parts of `transcribe` in engine.cc instead of sharing them: this
+// file was written at the very end of round 1 and `transcribe` was left untouched as the verified single-clip path.  The
+// batched path is parity-green against it (tests/test_gpu_batch.py); folding the two into one is round-2 housekeeping.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -31,9 +31,9 @@ Engine::~Engine() {
     if (batch_h_flags) cudaFreeHost(batch_h_flags);
 }
 
-bool batch_decode_enabled() {
+bool batch_decode_enabled() {      // on by default; SS_BATCH_DECODE=0 gives ss_transcribe_batch the clip-by-clip decode back
     const char *e = getenv("SS_BATCH_DECODE");
-    return e && e[0] && e[0] != '0';
+    return !(e && e[0] == '0');
 }
 
 namespace {

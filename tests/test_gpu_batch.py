@@ -1,16 +1,12 @@
-"""Batched decoder (csrc/decoder_batch.cu + engine_batch.cc, opt-in through SS_BATCH_DECODE=1): `ss_transcribe_batch`
-must give, clip by clip, exactly what the verified clip-by-clip path gives (tokens, raw segments, post-processed result) -
-the two paths share the oracle-checked arithmetic (f16 operands, f32 accumulate), so greedy tokens have to be identical.
-
-The batched kernels were written after the round's GPU budget was spent: until they have been run once on a B200 these
-tests are skipped unless SS_TEST_BATCH=1 is set (the default `ss_transcribe_batch` does not use them either)."""
+"""Batched decoder (csrc/decoder_batch.cu + engine_batch.cc): `ss_transcribe_batch` must give, clip by clip, exactly what
+the oracle-checked single-clip path gives (tokens, raw segments, post-processed result) - the two paths share the
+arithmetic (f16 operands, f32 accumulate), so greedy tokens have to be identical."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SS_TEST_BATCH") != "1", reason="batched decoder not yet verified on a GPU: set SS_TEST_BATCH=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture()
