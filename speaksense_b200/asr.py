@@ -217,16 +217,24 @@ class WhisperAsr(AsrEngine):          # whisper.rs:16-129
         _native.check(_native.lib().ss_bench_decode_steps(self._h, state._h, n_steps, n_past0, C.byref(ms)))
         return ms.value
 
-    def transcribe_batch(self, states: Sequence[WhisperState], audios: Sequence[np.ndarray], params: AsrParams):
-        """Data-parallel batch inside one GPU (BASELINE configs 3/4): result i belongs to audios[i]."""
+    def transcribe_batch(self, states: Sequence[WhisperState], audios: Sequence[Optional[np.ndarray]], params: AsrParams):
+        """Data-parallel batch inside one GPU (BASELINE configs 3/4): result i belongs to audios[i].  audios[i] = None
+        takes the PCM resident on states[i] (upload_pcm / denoise_audio), like transcribe_resident."""
         n = len(states)
-        pcms = [np.ascontiguousarray(a, dtype=np.float32) for a in audios]
+        pcms = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in audios]
         sp = (C.c_void_p * n)(*[s._h for s in states])
-        pp = (C.c_void_p * n)(*[a.ctypes.data for a in pcms])
-        ns = (C.c_size_t * n)(*[a.size for a in pcms])
+        pp = (C.c_void_p * n)(*[None if a is None else a.ctypes.data for a in pcms])
+        ns = (C.c_size_t * n)(*[0 if a is None else a.size for a in pcms])
         p = params._native()
-        _native.check(_native.lib().ss_transcribe_batch(self._h, sp, pp, ns, n, C.byref(p)))
-        return [self._read_result(s) for s in states]
+        locks = sorted({id(s): s._lock for s in states}.items())      # one order for everybody: no lock cycles between batches
+        for _, lk in locks:
+            lk.acquire()
+        try:
+            _native.check(_native.lib().ss_transcribe_batch(self._h, sp, pp, ns, n, C.byref(p)))
+            return [self._read_result(s) for s in states]
+        finally:
+            for _, lk in reversed(locks):
+                lk.release()
 
     # ---- stage-level entry points (parity tests / roofline measurement)
     def log_mel(self, state: WhisperState, audio):

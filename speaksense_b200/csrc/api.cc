@@ -1,6 +1,7 @@
 // api.cc - the C ABI declared in include/speaksense_whisper.h.
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/speaksense_whisper.h"
 #include "engine.h"
@@ -150,16 +151,23 @@ int ss_bench_decode_steps(ss_engine *e, ss_state *s, int n_steps, int n_past0, f
 int ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *const *pcm, const size_t *n, int batch, const ss_params *p) {
     return guard([&]() -> int {
         if (!e || !states || !pcm || !n || batch < 0) SS_THROW(SS_ERR_INVALID, "null argument");
-        for (int i = 0; i < batch; i++)
-            if (!states[i] || states[i]->s->engine.get() != e->e.get() || (!pcm[i] && n[i])) SS_THROW(SS_ERR_INVALID, "bad state / clip %d", i);
+        std::vector<size_t> len(batch);
+        for (int i = 0; i < batch; i++) {
+            if (!states[i] || states[i]->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "bad state %d", i);
+            len[i] = n[i];
+            if (!pcm[i]) {      // NULL clip: the state's resident PCM (ss_upload_pcm / ss_denoise_audio), as ss_transcribe_resident
+                if (!states[i]->s->d_pcm) SS_THROW(SS_ERR_INVALID, "clip %d: no resident PCM: call ss_upload_pcm / ss_denoise_audio first", i);
+                len[i] = states[i]->s->n_resident;
+            }
+        }
         if (batch_decode_enabled()) {      // one batched decoder step per token for all clips (engine_batch.cc); SS_BATCH_DECODE=0: clip by clip
             std::vector<State *> st(batch);
             for (int i = 0; i < batch; i++) st[i] = states[i]->s;
-            return transcribe_batch(st.data(), pcm, n, batch, make_params(p), p && p->stream_mode);
+            return transcribe_batch(st.data(), pcm, len.data(), batch, make_params(p), p && p->stream_mode);
         }
         int rc = 0;
         for (int i = 0; i < batch; i++) {
-            const int r = transcribe(*states[i]->s, pcm[i], n[i], make_params(p), p && p->stream_mode);
+            const int r = transcribe(*states[i]->s, pcm[i], len[i], make_params(p), p && p->stream_mode);
             if (r && !rc) rc = r;
         }
         return rc;

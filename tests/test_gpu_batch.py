@@ -113,3 +113,33 @@ def test_batch_teacher_forced_logits_match_batch1(batch_on, tiny_en_peaked, audi
     lg = eng.decode(sts[0], np.array([50257], np.int32), 0)
     assert np.isfinite(lg).all()
     eng.close()
+
+
+def test_batch_resident_clips_and_front_end(batch_on, tiny_en_peaked):
+    """pcm[i] == NULL takes the state's resident PCM (the stream path: denoise leaves the chunk resident); the micro-batching
+    front end (speaksense_b200/batching.py) merges concurrent calls and hands every caller its own result."""
+    import threading
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    from speaksense_b200.batching import BatchingEngine
+    eng = WhisperAsr(tiny_en_peaked)
+    clips = [synth.synth_audio(seed=300 + i) for i in range(3)]
+    p = AsrParams(stream_mode=True)
+    ref = [eng.transcribe(c, p) for c in clips]
+    sts = [eng.create_state() for _ in clips]
+    for s, c in zip(sts, clips):
+        eng.upload_pcm(s, c)
+    assert eng.transcribe_batch(sts, [None, None, None], p) == ref
+    assert eng.transcribe_batch(sts, [clips[0], None, clips[2]], p) == ref
+    be = BatchingEngine(eng, linger_s=0.2)
+    out = [None] * 3
+
+    def call(i):
+        out[i] = be.transcribe_resident(sts[i], p) if i == 1 else be.transcribe_with_state(sts[i], clips[i], p)
+    th = [threading.Thread(target=call, args=(i,)) for i in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out == ref and be.max_seen >= 2
+    be.close()
+    eng.close()
