@@ -92,7 +92,9 @@ class AsrService:
 
 
 def serve(engine, address: str = "127.0.0.1:7300", max_workers: int = 8, session_factory: Optional[Callable] = None):
-    """start a grpc.Server speaking proto/asr.proto on `address` (the reference listens on GRPC_ADDR, src/main.rs)"""
+    """start a grpc.Server speaking proto/asr.proto on `address` (the reference listens on GRPC_ADDR, src/main.rs).
+    `engine` may be a BatchingEngine (speaksense_b200/batching.py): chunks of concurrent streams that are ready together then
+    share one batched decoder step per token."""
     service = AsrService(engine, session_factory)
     handler = grpc.method_handlers_generic_handler(SERVICE, {
         "Transcribe": grpc.stream_stream_rpc_method_handler(
