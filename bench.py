@@ -319,6 +319,19 @@ def main():
             except Exception:   # noqa: BLE001
                 pass
         line["next_rows"] = {"f1_denoise": f1}
+        if world == 1 and not os.environ.get("SS_BENCH_NO_BATCH"):
+            # BASELINE configs[2] beside the headline (informational; the headline stays configs[1]): 32 x 30 s clips through
+            # ss_transcribe_batch (batched decoder step, csrc/decoder_batch.cu) in a child process - a failure there cannot
+            # take this line down.  Same tool and arguments as profiles/r1f_batch_bench_pdl.json.
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "batch_bench.py"), args.shape, "32", "2", "1"],
+                                     capture_output=True, text=True, timeout=300)
+                b = json.loads(out.stdout.strip().splitlines()[-1])
+                line["next_rows"]["batch32"] = {"workload": b["workload"], "rtf_host_buffers": b["batched"]["rtf"],
+                                                "wall_s": b["batched"]["wall_s"], "tokens": b["batched"]["tokens"],
+                                                "decode_ms": b["batched"]["decode_ms"], "gpu_launches": b["batched"]["launches"]}
+            except Exception as ex:   # noqa: BLE001
+                line["next_rows"]["batch32"] = {"error": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     state.close()
     eng.close()
