@@ -102,7 +102,9 @@ class BatchingEngine(AsrEngine):
                 for r, res in zip(group, results):
                     r.future.set_result(res)
                 return
-            except Exception:      # noqa: BLE001  one clip failed the batch call: find out which, the others must not suffer
+            except Exception:      # noqa: BLE001
+                # One clip failed the batch call; the others must not suffer.  Run the clips again one by one: a call starts
+                # from its clip, not from what an earlier call left in the state (stream mode sets no_context, whisper.rs:67).
                 pass
         for r in group:
             try:

@@ -217,7 +217,7 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
     const int xsplit = decode_batch_xsplit(nb, bp.H, E.sms);
     CUDA_CHECK(cudaMemsetAsync(bp.n_done, 0, sizeof(int), bs));
     CUDA_CHECK(cudaEventRecord(E.batch_ev[2], bs));
-    int launches = 0, steps = 0;
+    int launches = 0;
     E.batch_h_flags[0] = E.batch_h_flags[1] = 0;
     for (int t = 0; t < max_steps; t++) {
         if (t % kPollEvery == 0) {
@@ -228,7 +228,6 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
             }
         }
         decode_batch_step_enqueue(bp, w, /*need_logits=*/t >= min_prompt - 1, xsplit, bs, &launches);
-        steps++;
         if (t % kPollEvery == kPollEvery - 1) {
             const int G = t / kPollEvery;
             CUDA_CHECK(cudaMemcpyAsync(&E.batch_h_flags[G & 1], bp.n_done, sizeof(int), cudaMemcpyDeviceToHost, bs));
@@ -256,7 +255,6 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
         s.n_launches += ceil_div(launches, nb);
         s.ms_dec += ms / nb;      // the batch's device time, shared equally
     }
-    (void)steps;
 }
 
 }  // namespace
