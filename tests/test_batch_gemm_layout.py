@@ -1,0 +1,74 @@
+"""CPU: the fragment addressing of the batched decoder's skinny GEMM (csrc/decoder_batch.cu `bd_gemm_kernel`), emulated in
+numpy with the PTX fragment layout of mma.m16n8k16 (row-major A 16x16, column-major B 16x8, C 16x8):
+
+    a0 = A[g][2t, 2t+1]   a1 = A[g+8][2t, 2t+1]   a2 = A[g][2t+8, 2t+9]   a3 = A[g+8][2t+8, 2t+9]
+    b0 = B[2t, 2t+1][g]   b1 = B[2t+8, 2t+9][g]
+    c0 = C[g][2t]   c1 = C[g][2t+1]   c2 = C[g+8][2t]   c3 = C[g+8][2t+1]          (g = lane / 4, t = lane % 4)
+
+The kernel loads, per 32-wide K block, the 8 halves [8t, 8t+8) of weight rows g / g+8 and of x row g as ONE 16-byte vector each
+and feeds register pairs (x, y) and (z, w) to two MMAs.  The MMA therefore sees K in a permuted order - the same permutation on
+both operands - and this test checks that every product is still formed exactly once for all warp tilings the kernel is
+instantiated with, including the clamped rows past N, the K split across warps and the shared-memory fold's index math."""
+import numpy as np
+import pytest
+
+
+def _emulate(WR, WK, NT, N, K, B, rng):
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    X = np.zeros((8 * NT, K), np.float32)
+    X[:B] = rng.standard_normal((B, K))
+    out = np.full((B, N), np.nan, np.float32)
+    lanes = [(lane >> 2, lane & 3) for lane in range(32)]
+    for cta in range((N + 16 * WR - 1) // (16 * WR)):
+        red = np.zeros((WR, WK, 8 * NT, 17), np.float32)
+        for warp in range(8):
+            wr, wk = warp // WK, warp % WK
+            row_base = (cta * WR + wr) * 16
+            nblk = K >> 5
+            blk0, blk1 = wk * nblk // WK, (wk + 1) * nblk // WK
+            C = np.zeros((NT, 16, 8), np.float32)
+            for blk in range(blk0, blk1):
+                for half in range(2):                      # the two MMAs of a block: vector components (x, y) then (z, w)
+                    A = np.zeros((16, 16), np.float32)
+                    Bm = np.zeros((NT, 16, 8), np.float32)
+                    o = 4 * half
+                    for g, t in lanes:
+                        ra, rb = min(row_base + g, N - 1), min(row_base + g + 8, N - 1)
+                        a = W[ra, blk * 32 + t * 8: blk * 32 + t * 8 + 8]
+                        c = W[rb, blk * 32 + t * 8: blk * 32 + t * 8 + 8]
+                        A[g, 2 * t:2 * t + 2] = a[o:o + 2]; A[g + 8, 2 * t:2 * t + 2] = c[o:o + 2]
+                        A[g, 2 * t + 8:2 * t + 10] = a[o + 2:o + 4]; A[g + 8, 2 * t + 8:2 * t + 10] = c[o + 2:o + 4]
+                        for nt in range(NT):
+                            xv = X[nt * 8 + g, blk * 32 + t * 8: blk * 32 + t * 8 + 8]
+                            Bm[nt, 2 * t:2 * t + 2, g] = xv[o:o + 2]; Bm[nt, 2 * t + 8:2 * t + 10, g] = xv[o + 2:o + 4]
+                    for nt in range(NT):
+                        C[nt] += A @ Bm[nt]
+            for g, t in lanes:
+                for nt in range(NT):
+                    red[wr, wk, nt * 8 + 2 * t, g] = C[nt, g, 2 * t]; red[wr, wk, nt * 8 + 2 * t + 1, g] = C[nt, g, 2 * t + 1]
+                    red[wr, wk, nt * 8 + 2 * t, g + 8] = C[nt, g + 8, 2 * t]; red[wr, wk, nt * 8 + 2 * t + 1, g + 8] = C[nt, g + 8, 2 * t + 1]
+        total = WR * 16 * 8 * NT
+        for tid in range(256):
+            for k in range((total + 255) // 256):
+                idx = tid + k * 256
+                if idx >= total:
+                    break
+                r, b, w2 = idx & 15, (idx >> 4) % (8 * NT), idx // (16 * 8 * NT)
+                row = (cta * WR + w2) * 16 + r
+                if row < N and b < B:
+                    assert np.isnan(out[b, row])           # every output is written by exactly one thread
+                    out[b, row] = red[w2, :, b, r].sum()
+    return out, X[:B] @ W.T
+
+
+@pytest.mark.parametrize("WR,WK,NT,N,K,B", [
+    (1, 8, 1, 100, 256, 5),      # N = d tilings, one n-tile, ragged N
+    (1, 8, 4, 64, 1024, 32),     # full batch
+    (2, 4, 2, 200, 384, 11),     # QKV / FC1 tiling, K blocks that do not divide evenly among the K splits (12 over 4)
+    (8, 1, 4, 300, 128, 29),     # LM-head tiling: no K split, N not a multiple of 128
+    (1, 8, 2, 48, 384, 16),      # 12 K blocks over 8 splits: some warps get one block, some two
+])
+def test_permuted_k_fragments_form_every_product_once(WR, WK, NT, N, K, B):
+    out, ref = _emulate(WR, WK, NT, N, K, B, np.random.default_rng(N + K))
+    assert not np.isnan(out).any()
+    np.testing.assert_allclose(out, ref, rtol=0, atol=2e-4)
