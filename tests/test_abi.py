@@ -166,3 +166,22 @@ def test_text_rules_literal_cases(L):
     assert L.ss_is_promotional_text("感谢收看 請按讚、訂閱、分享!".encode()) == 1
     assert L.ss_is_promotional_text("订 阅".encode()) == 0                     # substring match, not fuzzy
     assert L.ss_is_promotional_text("今天天气不错".encode()) == 0
+
+
+def test_cpp_trait_mirror_compiles_and_reports_errors(tmp_path):
+    """include/speaksense_asr.hpp (C++ mirror of mod.rs:9-73 / whisper.rs:16-129 above the C ABI) builds warning-free and the
+    example host program runs its host-only part: text rules through the library, and WhisperAsr::new failing with the
+    reference's message prefix (whisper.rs:24) - here because the model file does not exist / there is no GPU."""
+    import shutil
+    import subprocess
+    from speaksense_b200 import build
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    inc, libdir = os.path.join(ROOT, "include"), os.path.dirname(build.LIB)
+    exe = tmp_path / "asr_host"
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, os.path.join(ROOT, "examples", "asr_host.cpp"),
+                           "-o", str(exe), "-L", libdir, "-lspeaksense_whisper", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout.splitlines()
+    assert out[0] == "promo 1 0"
+    assert out[1] == "punct [hello ]"
+    assert out[2].startswith("error -") and "failed to open whisper model: " in out[2]
