@@ -143,3 +143,22 @@ def test_batch_resident_clips_and_front_end(batch_on, tiny_en_peaked):
     assert out == ref and be.max_seen >= 2
     be.close()
     eng.close()
+
+
+def test_batch_matches_oracle_directly(batch_on, oracle_mod, tiny_en_peaked, audio30):
+    """the batched path against the CPU oracle itself (not only through the single-clip path): tokens and raw segments of every
+    sequence of a batch, token for token"""
+    from speaksense_b200 import AsrParams, WhisperAsr
+    om = oracle_mod.OracleModel(tiny_en_peaked)
+    ost = om.new_state()
+    ref = ost.full(audio30, stream_mode=True)
+    ost.close(); om.close()
+    eng = WhisperAsr(tiny_en_peaked)
+    sts = [eng.create_state() for _ in range(3)]
+    eng.transcribe_batch(sts, [audio30] * 3, AsrParams(stream_mode=True))
+    for st in sts:
+        assert st.result_tokens()[0] == ref["tokens"]
+        assert [(s["t0"], s["t1"], s["text"]) for s in st.raw_segments()] == [(s["t0"], s["t1"], s["text"]) for s in ref["segments"]]
+        assert st.stats()["n_fallbacks"] == ref["n_fallbacks"] == 0
+        st.close()
+    eng.close()
