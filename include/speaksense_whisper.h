@@ -84,7 +84,8 @@ int  ss_transcribe(ss_engine *e, ss_state *s, const float *pcm, size_t n_samples
 /* Batched form (data-parallel inside one GPU; BASELINE configs 3/4): states[i] receives the result for pcm[i], exactly
  * what ss_transcribe(states[i], pcm[i]) would leave there.  The clips' temperature-0 greedy decodes share one batched
  * decoder step per token (the weights are streamed once per step for the whole batch); fallbacks run per clip.  The states
- * must be distinct for that; beam_size > 1 / debug_keep_logits / SS_BATCH_DECODE=0 in the environment decode clip by clip.
+ * must be distinct for that; beam_size > 1 / debug_keep_logits / batches below SS_BATCH_MIN (default 4) clips / SS_BATCH_DECODE=0 in
+ * the environment decode clip by clip.
  * pcm[i] == NULL: clip i is the resident PCM of states[i] (ss_upload_pcm / ss_denoise_audio), n_samples[i] is ignored. */
 int  ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *const *pcm,
                          const size_t *n_samples, int batch, const ss_params *p);

@@ -36,6 +36,15 @@ bool batch_decode_enabled() {      // on by default; SS_BATCH_DECODE=0 gives ss_
     return !(e && e[0] == '0');
 }
 
+// Smallest batch that takes the batched decoder.  A batched step is a chain of ~390 short kernels (~2 ms per step at large-v3
+// whatever the batch), the batch-1 persistent kernel needs 0.71 ms per token and clip: below ~3 clips clip-by-clip is the
+// faster way (estimate from profiles/r1e_batch_launches_summary.txt; to be re-measured: tools/gpu_round_check.sh).
+static int batch_decode_min() {
+    const char *e = getenv("SS_BATCH_MIN");
+    const int v = e ? atoi(e) : 4;
+    return std::max(2, v);
+}
+
 namespace {
 
 constexpr int kXsplitMax = 8;
@@ -263,7 +272,7 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
     if (batch <= 0) return 0;
     Engine &E = *states[0]->engine;
     const Model &m = E.model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
-    bool batched = batch >= 2 && P.beam_size <= 1 && !P.keep_logits && P.temperature < 1e-6f && hp.n_text_state == hp.n_text_head * 64 &&
+    bool batched = batch >= batch_decode_min() && P.beam_size <= 1 && !P.keep_logits && P.temperature < 1e-6f && hp.n_text_state == hp.n_text_head * 64 &&
                    hp.n_text_state <= 1280 && hp.n_text_ctx <= 512 && hp.n_audio_ctx <= 1536;
     for (int i = 0; i < batch && batched; i++)
         for (int j = 0; j < i; j++) if (states[i] == states[j]) batched = false;      // one state twice: the calls must serialise

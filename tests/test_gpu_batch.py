@@ -11,13 +11,16 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture()
 def batch_on():
-    old = os.environ.get("SS_BATCH_DECODE")
+    """batched decoder on, for every batch of two or more clips (by default batches below 4 decode clip by clip)"""
+    old = {k: os.environ.get(k) for k in ("SS_BATCH_DECODE", "SS_BATCH_MIN")}
     os.environ["SS_BATCH_DECODE"] = "1"
+    os.environ["SS_BATCH_MIN"] = "2"
     yield
-    if old is None:
-        os.environ.pop("SS_BATCH_DECODE", None)
-    else:
-        os.environ["SS_BATCH_DECODE"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def _single(eng, clips, params):
