@@ -22,6 +22,9 @@ struct Engine {
     cudaEvent_t batch_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0, 1: termination polls; 2, 3: timing
     int *batch_h_flags = nullptr;                                     // pinned [2]: finished-sequence counts read back by the polls
     int sms = 0;
+    // activations of the batched encoder pass (opt-in, SS_BATCH_ENCODER=1): [clips * n_audio_ctx] rows
+    void *enc_scratch = nullptr;
+    cudaEvent_t enc_ev[3] = {nullptr, nullptr, nullptr};              // start / end of the pass (timing), done (other streams wait on it)
     ~Engine();
 };
 

@@ -29,6 +29,8 @@ Engine::~Engine() {
     for (auto &e : batch_ev) if (e) cudaEventDestroy(e);
     if (batch_scratch) cudaFree(batch_scratch);
     if (batch_h_flags) cudaFreeHost(batch_h_flags);
+    if (enc_scratch) { cudaSetDevice(device); cudaFree(enc_scratch); }
+    for (auto &e : enc_ev) if (e) cudaEventDestroy(e);
 }
 
 bool batch_decode_enabled() {      // on by default; SS_BATCH_DECODE=0 gives ss_transcribe_batch the clip-by-clip decode back
@@ -200,6 +202,127 @@ int emit_window(State &s, const FullParams &P, const Common &C, const ClipRun &r
     return seek_delta;
 }
 
+// ---- batched encoder pass (opt-in: SS_BATCH_ENCODER=1; written after the round's GPU budget was spent, NOT yet run) ----
+// The windows of all clips of a round as ONE pass over [clips * 1500] rows: the conv stem and the cross-KV projection stay
+// per clip (their operands live in each State), the 32 layers run once with M = clips * 1500 - the N = 1280 GEMMs, 120 tiles
+// on 148 SMs for one clip, become 375 * clips tiles - and the fused attention kernel takes the clip as its outer batch.
+// By default the clips' encoders run concurrently on their own streams (run_encode), which is what round 1 measured.
+bool batch_encoder_enabled() {
+    const char *e = getenv("SS_BATCH_ENCODER");
+    return e && e[0] == '1';
+}
+
+struct EncBuf { float *x, *enc_out; __half *xn, *qkv, *att, *ff, *enc16; };
+
+size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+EncBuf bind_enc_scratch(Engine &E) {
+    const HParams &hp = E.model.hp;
+    const size_t rows = (size_t)kMaxBatch * hp.n_audio_ctx, d = hp.n_audio_state;
+    const size_t sz[7] = {a256(rows * d * 4), a256(rows * d * 4), a256(rows * d * 2), a256(rows * 3 * d * 2), a256(rows * d * 2),
+                          a256(rows * 4 * d * 2), a256(rows * d * 2)};
+    if (!E.enc_scratch) {
+        size_t total = 0;
+        for (size_t b : sz) total += b;
+        if (cudaMalloc(&E.enc_scratch, total) != cudaSuccess) SS_THROW(-5, "cudaMalloc of %zu bytes (batched encoder activations) failed", total);
+        for (auto &e : E.enc_ev) CUDA_CHECK(cudaEventCreate(&e));
+    }
+    uint8_t *p = static_cast<uint8_t *>(E.enc_scratch);
+    EncBuf b;
+    b.x = reinterpret_cast<float *>(p); p += sz[0];
+    b.enc_out = reinterpret_cast<float *>(p); p += sz[1];
+    b.xn = reinterpret_cast<__half *>(p); p += sz[2];
+    b.qkv = reinterpret_cast<__half *>(p); p += sz[3];
+    b.att = reinterpret_cast<__half *>(p); p += sz[4];
+    b.ff = reinterpret_cast<__half *>(p); p += sz[5];
+    b.enc16 = reinterpret_cast<__half *>(p);
+    return b;
+}
+
+// encoder + cross-KV of the current window of every clip of `grp` (<= kMaxBatch) on the engine's batch stream; every clip's
+// own stream is made to wait for the pass.  Same arithmetic, kernels and epilogues as run_encode (engine.cc).
+void run_encode_batch(Engine &E, std::vector<ClipRun *> &grp) {
+    const Model &m = E.model; const HParams &hp = m.hp;
+    const int R = (int)grp.size(), T = hp.n_audio_ctx, d = hp.n_audio_state, H = hp.n_audio_head, C = hp.n_mels;
+    const EncBuf B = bind_enc_scratch(E);
+    cudaStream_t st = E.batch_stream;
+    int launches = 0; int *nl = &launches;
+    CUDA_CHECK(cudaEventRecord(E.enc_ev[0], st));
+    for (int b = 0; b < R; b++) {      // conv stem per clip -> rows [b * T, (b + 1) * T) of the residual stream
+        State &s = *grp[b]->s;
+        mel_window_enqueue(m, s.d_mel, s.n_len, grp[b]->seek, s.win, st, nl);
+        {
+            GemmOperand A; A.ptr = s.win; A.rows = 2 * T; A.ld = C;
+            GemmOperand W; W.ptr = m.conv1.w; W.rows = d; W.ld = 3 * C;
+            GemmEpilogue ep; ep.bias = m.conv1.b; ep.gelu = 1; ep.out = s.x1; ep.out_type = GEMM_OUT_F16; ep.out_ld = d; ep.out_row_offset = 1;
+            gemm_enqueue(A, W, 2 * T, d, 3 * C, false, ep, st, nl);
+        }
+        {
+            GemmOperand A; A.ptr = s.x1; A.rows = T; A.ld = 2 * d;
+            GemmOperand W; W.ptr = m.conv2.w; W.rows = d; W.ld = 3 * d;
+            GemmEpilogue ep; ep.bias = m.conv2.b; ep.gelu = 1; ep.pos = m.e_pos; ep.pos_rows = T; ep.out = B.x + (size_t)b * T * d; ep.out_type = GEMM_OUT_F32; ep.out_ld = d;
+            gemm_enqueue(A, W, T, d, 3 * d, false, ep, st, nl);
+        }
+    }
+    const int M = R * T;
+    for (int il = 0; il < hp.n_audio_layer; il++) {
+        const EncLayer &L = m.enc[il];
+        layernorm_f16_enqueue(B.x, B.xn, M, d, L.attn_ln, st, nl);
+        {
+            GemmOperand A; A.ptr = B.xn; A.rows = M; A.ld = d;
+            GemmOperand W; W.ptr = L.qkv.w; W.rows = 3 * d; W.ld = d;
+            GemmEpilogue ep; ep.bias = L.qkv.b; ep.out = B.qkv; ep.out_ld = 3 * d;
+            gemm_enqueue(A, W, M, 3 * d, d, false, ep, st, nl);
+        }
+        attention_enqueue(B.qkv, B.att, R, T, H, 1.0f / sqrtf(64.0f), st, nl);
+        {
+            GemmOperand A; A.ptr = B.att; A.rows = M; A.ld = d;
+            GemmOperand W; W.ptr = L.o.w; W.rows = d; W.ld = d;
+            GemmEpilogue ep; ep.bias = L.o.b; ep.residual = 1; ep.out = B.x; ep.out_type = GEMM_OUT_F32; ep.out_ld = d;
+            gemm_enqueue(A, W, M, d, d, false, ep, st, nl);
+        }
+        layernorm_f16_enqueue(B.x, B.xn, M, d, L.mlp_ln, st, nl);
+        {
+            GemmOperand A; A.ptr = B.xn; A.rows = M; A.ld = d;
+            GemmOperand W; W.ptr = L.fc1.w; W.rows = 4 * d; W.ld = d;
+            GemmEpilogue ep; ep.bias = L.fc1.b; ep.gelu = 1; ep.out = B.ff; ep.out_ld = 4 * d;
+            gemm_enqueue(A, W, M, 4 * d, d, false, ep, st, nl);
+        }
+        {
+            GemmOperand A; A.ptr = B.ff; A.rows = M; A.ld = 4 * d;
+            GemmOperand W; W.ptr = L.fc2.w; W.rows = d; W.ld = 4 * d;
+            GemmEpilogue ep; ep.bias = L.fc2.b; ep.residual = 1; ep.out = B.x; ep.out_type = GEMM_OUT_F32; ep.out_ld = d;
+            gemm_enqueue(A, W, M, d, 4 * d, false, ep, st, nl);
+        }
+    }
+    layernorm_f32_enqueue(B.x, B.enc_out, M, d, m.ln_post, st, nl);
+    f32_to_f16_enqueue(B.enc_out, B.enc16, (size_t)M * d, st, nl);
+    const int dd = hp.n_text_state, Ld = hp.n_text_layer;
+    const float s4 = powf((float)(dd / hp.n_text_head), -0.25f);
+    const long wstride = Ld > 1 ? (long)(m.dec[1].ckv.w - m.dec[0].ckv.w) : (long)2 * dd * d;
+    const long bstride = Ld > 1 ? (long)(m.dec[1].ckv.b - m.dec[0].ckv.b) : (long)2 * dd;
+    for (int il = 0; il < Ld; il++)
+        if (m.dec[il].ckv.w != m.dec[0].ckv.w + (long)il * wstride || m.dec[il].ckv.b != m.dec[0].ckv.b + (long)il * bstride)
+            SS_THROW(-9, "decoder layers are not equally spaced in the weight arena");
+    for (int b = 0; b < R; b++) {      // cross-attention K / V of every decoder layer into the clip's own cache
+        State &s = *grp[b]->s;
+        GemmOperand A; A.ptr = B.enc16 + (size_t)b * T * d; A.rows = T; A.ld = d;
+        GemmOperand W; W.ptr = m.dec[0].ckv.w; W.rows = 2 * dd; W.ld = d; W.batch0 = Ld; W.stride0 = wstride;
+        GemmEpilogue ep; ep.a_broadcast = 1; ep.bias = m.dec[0].ckv.b; ep.bias_stride0 = bstride;
+        ep.alpha = s4; ep.alpha_cols = dd;
+        ep.out = s.cross_k; ep.head_major = 1; ep.head_rows = T; ep.out_stride0 = (long)2 * T * dd;
+        gemm_enqueue(A, W, T, 2 * dd, d, false, ep, st, nl);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(E.enc_ev[1], st));
+    CUDA_CHECK(cudaEventRecord(E.enc_ev[2], st));
+    for (int b = 0; b < R; b++) {
+        State &s = *grp[b]->s;
+        CUDA_CHECK(cudaStreamWaitEvent(s.stream, E.enc_ev[2], 0));
+        s.n_launches += ceil_div(launches, R);
+    }
+}
+
 // batched greedy decode of the armed decoder-0 sequences of `grp` (<= kMaxBatch clips)
 void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<ClipRun *> &grp) {
     const Model &m = E.model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
@@ -326,10 +449,18 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
             act.push_back(&r);
         }
         if (act.empty()) break;
+        const bool enc_batched = batch_encoder_enabled() && act.size() >= 2;
+        for (size_t g0 = 0; enc_batched && g0 < act.size(); g0 += kMaxBatch) {
+            std::vector<ClipRun *> grp(act.begin() + g0, act.begin() + std::min(act.size(), g0 + (size_t)kMaxBatch));
+            run_encode_batch(E, grp);
+            CUDA_CHECK(cudaStreamSynchronize(E.batch_stream));      // the activations are reused by the next group
+            float ms = 0.f; cudaEventElapsedTime(&ms, E.enc_ev[0], E.enc_ev[1]);
+            for (ClipRun *r : grp) r->s->ms_enc += ms / (float)grp.size();
+        }
         for (ClipRun *r : act) {      // encoder + cross-KV of the window, temperature-0 control block
             State &s = *r->s;
             CUDA_CHECK(cudaEventRecord(s.ev[0], s.stream));
-            run_encode(s, r->seek);
+            if (!enc_batched) run_encode(s, r->seek);
             CUDA_CHECK(cudaEventRecord(s.ev[1], s.stream));
             s.n_windows++;
             if (r->seek > 0 && r->seek + 500 >= r->seek_end) s.prompt_past.clear();
@@ -373,7 +504,7 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
         }
         for (ClipRun *r : act) {      // scoring, temperature ladder, segments, seek advance - per clip
             State &s = *r->s;
-            { float ms; cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.ms_enc += ms; }
+            if (!enc_batched) { float ms; cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.ms_enc += ms; }
             bool settled = score_and_test(s, P, C, 0, 1, r->best_decoder_id);
             for (size_t it = 1; it < C.temps.size() && !settled; it++) {
                 const float t_cur = C.temps[it];

@@ -165,3 +165,25 @@ def test_batch_matches_oracle_directly(batch_on, oracle_mod, tiny_en_peaked, aud
         assert st.stats()["n_fallbacks"] == ref["n_fallbacks"] == 0
         st.close()
     eng.close()
+
+
+@pytest.mark.skipif(os.environ.get("SS_TEST_BATCH_ENCODER") != "1",
+                    reason="batched encoder pass (SS_BATCH_ENCODER=1) was written after the round's GPU budget was spent and is off by "
+                           "default: set SS_TEST_BATCH_ENCODER=1 to run it")
+@pytest.mark.parametrize("shape,lang,n_clips", [("tiny.en", None, 5), ("large-v3-l2", "en", 3)])
+def test_batched_encoder_pass_equals_per_clip_encoders(batch_on, shape, lang, n_clips):
+    """SS_BATCH_ENCODER=1: the windows of all clips as one encoder pass over [clips * 1500] rows - same tokens and segments"""
+    from tests.conftest import model_path
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    eng = WhisperAsr(model_path(shape, "peaked", 0))
+    clips = [synth.synth_audio(seed=1234 + i) for i in range(n_clips)] + [synth.synth_audio(45 * 16000, seed=11)]
+    p = AsrParams(language=lang, stream_mode=True)
+    ref = _single(eng, clips, p)
+    os.environ["SS_BATCH_ENCODER"] = "1"
+    try:
+        got, _ = _batched(eng, clips, p)
+    finally:
+        os.environ.pop("SS_BATCH_ENCODER", None)
+    for g, r in zip(got, ref):
+        assert g[1] == r[1] and g[2] == r[2] and g[0] == r[0]
+    eng.close()
