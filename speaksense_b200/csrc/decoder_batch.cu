@@ -497,6 +497,109 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __gr
     if (done) { ctl->done = 1; atomicAdd(P.n_done, 1); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// beam search (opt-in, SS_BATCH_BEAM=1; written after round 1's GPU budget was spent, NOT yet run): end of a step whose
+// sequences are the live beams of one window.  Same filter and statistics as bd_sample_kernel (whisper_process_logits, with
+// the temperature division of the t > 0 rungs), then whisper_sample_token_topk: the k most likely tokens in (log-prob
+// descending, id ascending) order - masked tokens stay at -inf, so a list that runs out of allowed tokens fills up with the
+// lowest ids exactly like the host's partial sort (engine.cc sample_topk_host).  k <= 8 candidates per sequence are left in
+// `cand`; the host does the beam bookkeeping and re-arms the control blocks for the next step.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSampleWarps * 32) bd_topk_kernel(const __grid_constant__ BatchParams P, float temperature, int K, TokData *cand) {
+    __shared__ SeqState S;
+    __shared__ float rv[2][kSampleWarps];
+    __shared__ int ri[2][kSampleWarps];
+    __shared__ float rs[2][kSampleWarps];
+    __shared__ MaxIdx pick;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DecCtl *ctl = P.seq[b].ctl;
+    pdl_trigger();
+    pdl_wait();
+    if (tid == 0) {
+        SeqState s;
+        s.pos = ctl->pos; s.pos0 = ctl->pos0; s.token = ctl->token; s.done = ctl->done; s.n_sampled = ctl->n_sampled; s.has_ts = ctl->has_ts;
+        s.seek_delta = ctl->seek_delta; s.result_len = ctl->result_len; s.last_id = ctl->last_id; s.penult_id = ctl->penult_id;
+        s.n_prompt = ctl->n_prompt; s.seek = ctl->seek; s.seek_end = ctl->seek_end; s.n_max = ctl->n_max; s.sample = ctl->sample;
+        S = s;
+    }
+    __syncthreads();
+    const SeqState st = S;
+    if (st.done) return;
+    const float *logits = P.logits + (size_t)b * P.n_vocab;
+    const bool scaled = temperature > 0.0f;
+    auto value = [&](int i) -> float {
+        if (token_masked(P, st, i)) return -INFINITY;
+        return scaled ? logits[i] / temperature : logits[i];
+    };
+    MaxIdx mt{-INFINITY, 0x7fffffff}, ms{-INFINITY, 0x7fffffff};
+    for (int i = tid; i < P.n_vocab; i += kSampleWarps * 32) {
+        const float x = value(i);
+        if (i < P.beg) { if (x > mt.v) mt = MaxIdx{x, i}; } else { if (x > ms.v) ms = MaxIdx{x, i}; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxIdx a{__shfl_xor_sync(0xffffffffu, mt.v, o), __shfl_xor_sync(0xffffffffu, mt.i, o)}; mt = better(mt, a);
+        MaxIdx c{__shfl_xor_sync(0xffffffffu, ms.v, o), __shfl_xor_sync(0xffffffffu, ms.i, o)}; ms = better(ms, c);
+    }
+    if (lane == 0) { rv[0][warp] = mt.v; ri[0][warp] = mt.i; rv[1][warp] = ms.v; ri[1][warp] = ms.i; }
+    __syncthreads();
+    mt = MaxIdx{rv[0][0], ri[0][0]}; ms = MaxIdx{rv[1][0], ri[1][0]};
+    for (int w = 1; w < kSampleWarps; w++) { mt = better(mt, MaxIdx{rv[0][w], ri[0][w]}); ms = better(ms, MaxIdx{rv[1][w], ri[1][w]}); }
+    const float m_all = fmaxf(mt.v, ms.v);
+    float sa = 0.f, sb = 0.f;
+    for (int i = tid; i < P.n_vocab; i += kSampleWarps * 32) {
+        const float x = value(i);
+        if (x > -INFINITY) { sa += expf(x - m_all); if (i >= P.beg) sb += expf(x - ms.v); }
+    }
+    sa = warp_sum(sa); sb = warp_sum(sb);
+    if (lane == 0) { rs[0][warp] = sa; rs[1][warp] = sb; }
+    __syncthreads();
+    sa = 0.f; sb = 0.f;
+    for (int w = 0; w < kSampleWarps; w++) { sa += rs[0][w]; sb += rs[1][w]; }
+    const float max_text = mt.v, max_ts = ms.v;
+    const float lse = logf(sa) + m_all;
+    const float ts_lp = sb > 0.f ? logf(sb) + (max_ts - lse) : -INFINITY;
+    const bool text_off = ts_lp > max_text - lse;                  // the timestamps outweigh every text token: text is suppressed
+    const float p_ts_max = max_ts > -INFINITY ? expf(max_ts - lse) : 0.f;
+    const float p_ts_sum = sb * p_ts_max;
+    const int tid_best = (max_ts > -INFINITY && p_ts_max > 0.f) ? ms.i : 0;
+    // k selection passes: the best (value, id) strictly after the previous pick in (value descending, id ascending) order
+    float prev_v = INFINITY; int prev_i = -1;
+    for (int k = 0; k < K; k++) {
+        MaxIdx best{-INFINITY, 0x7fffffff};
+        bool have = false;
+        for (int i = tid; i < P.n_vocab; i += kSampleWarps * 32) {
+            float x = value(i);
+            if (text_off && i < P.beg) x = -INFINITY;
+            const bool after = x < prev_v || (x == prev_v && i > prev_i);
+            if (after && (!have || x > best.v || (x == best.v && i < best.i))) { best = MaxIdx{x, i}; have = true; }
+        }
+        // reduce (a thread without a candidate carries id 0x7fffffff, which loses every tie)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MaxIdx a{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)}; best = better(best, a);
+        }
+        __syncthreads();                                            // rv / ri of the previous pass have been read by everybody
+        if (lane == 0) { rv[0][warp] = best.v; ri[0][warp] = best.i; }
+        __syncthreads();
+        if (tid == 0) {
+            MaxIdx t{rv[0][0], ri[0][0]};
+            for (int w = 1; w < kSampleWarps; w++) t = better(t, MaxIdx{rv[0][w], ri[0][w]});
+            pick = t;
+            TokData tk;
+            tk.id = t.i == 0x7fffffff ? 0 : t.i;
+            tk.plog = t.i == 0x7fffffff ? -INFINITY : t.v - lse;
+            tk.p = tk.plog > -INFINITY ? expf(tk.plog) : 0.f;
+            tk.tid = tid_best; tk.pt = p_ts_max / (p_ts_sum + 1e-10f); tk.ptsum = p_ts_sum;
+            if (tk.id >= P.beg) { tk.tid = tk.id; tk.pt = tk.p; }
+            cand[(size_t)b * 8 + k] = tk;
+        }
+        __syncthreads();
+        prev_v = pick.v; prev_i = pick.i;
+    }
+    if (tid == 0) { ctl->done = 1; atomicAdd(P.n_done, 1); }
+}
+
 bool pdl_enabled() {
     static const bool on = [] { const char *e = getenv("SS_BATCH_PDL"); return !(e && e[0] == '0'); }();
     return on;
@@ -550,7 +653,8 @@ int decode_batch_xsplit(int B, int H, int sms) {
     return std::max(1, std::min(8, ceil_div(want, std::max(1, B * H))));
 }
 
-void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st, int *launches) {
+void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st, int *launches,
+                               const BeamStep *beam) {
     const int B = P.B, d = P.d, nt = B <= 8 ? 1 : B <= 16 ? 2 : 4;
     if (B < 1 || B > kMaxBatch) SS_THROW(-1, "decode_batch: batch %d out of range", B);
     if ((d & 63) || d > kLnPer * kLnThreads || d != P.H * 64 || P.ctx > 512 || P.T > 1536) SS_THROW(-1, "decode_batch: unsupported decoder shape");
@@ -575,7 +679,12 @@ void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool n
         launch(bd_ln_kernel, dim3(B), ln_block, st, P, P.lnf_w, P.lnf_b, 0); n++;
         launch_gemm<8, 1, EPI_LOGITS>(P, nt, P.tok_emb, (const float *)nullptr, P.xn, P.n_vocab, d, 0, st); n++;
     }
-    launch(bd_sample_kernel, dim3(B), dim3(kSampleWarps * 32), st, P); n++;
+    if (beam) {      // beam search: k candidates per live beam instead of one greedy token
+        if (beam->k < 1 || beam->k > 8 || !beam->cand) SS_THROW(-1, "decode_batch: bad beam step");
+        launch(bd_topk_kernel, dim3(B), dim3(kSampleWarps * 32), st, P, beam->temperature, beam->k, beam->cand); n++;
+    } else {
+        launch(bd_sample_kernel, dim3(B), dim3(kSampleWarps * 32), st, P); n++;
+    }
     CUDA_CHECK(cudaGetLastError());
     if (launches) *launches += n;
 }

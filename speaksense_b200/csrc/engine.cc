@@ -582,11 +582,10 @@ void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos) {
 
 // ---- beam search (whisper_full's BEAM_SEARCH strategy; the reference itself always asks for Greedy{best_of:5},
 // whisper.rs:132 - this is the beam_size>1 extension BASELINE config 5 names)
-struct BeamCandidate { int decoder_idx, seek_delta; bool has_ts; Sequence seq; };
 
 // whisper_sample_token_topk: the k most likely tokens (log-prob descending, id ascending on ties), each carrying the
 // same timestamp summary (tid / pt / ptsum) sample_token_host computes
-static std::vector<TokData> sample_topk_host(const Model &m, const Decoder &dc, int k) {
+std::vector<TokData> sample_topk_host(const Model &m, const Decoder &dc, int k) {
     const Vocab &v = m.vocab; const int nv = m.hp.n_vocab;
     std::vector<int> ids(nv);
     for (int i = 0; i < nv; i++) ids[i] = i;
@@ -614,7 +613,7 @@ static bool same_tokens(const Sequence &a, const Sequence &b) {
 // hand the best candidates to the live decoders (skipping duplicates of the one just taken) and move each decoder's
 // self-attention cache to follow its new sequence. The shuffle is two-phase like whisper.cpp's temporary sequence ids:
 // every moved cache is first copied into the destination decoder's second buffer, then the buffers are swapped.
-static void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i, int n_past) {
+void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i, int n_past) {
     std::stable_sort(cands.begin(), cands.end(), [](const BeamCandidate &a, const BeamCandidate &b) {
         return a.seq.sum_logprobs_all > b.seq.sum_logprobs_all;
     });
@@ -754,6 +753,9 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
                     CUDA_CHECK(cudaMemcpy(s.h_keep.data() + old, s.keep, (size_t)nk * hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost));
                     s.n_keep += nk;
                 }
+            } else if (beam && batch_beam_enabled() && batch_beam_supported(s)) {
+                // ------- opt-in (SS_BATCH_BEAM=1): the live beams as sequences of one batched decoder step (engine_batch.cc) -------
+                decode_beam_batched(s, P, t_cur, n_cur, prompt, seek, seek_end, n_max, tid0_init);
             } else {
                 // ------- t > 0: best_of sampled decoders; beam search at any temperature: host-side sampling -------
                 for (int j = 0; j < n_cur; j++) set_sampling(*s.dec[j], P, tid0_init);

@@ -25,6 +25,8 @@ struct Engine {
     // activations of the batched encoder pass (opt-in, SS_BATCH_ENCODER=1): [clips * n_audio_ctx] rows
     void *enc_scratch = nullptr;
     cudaEvent_t enc_ev[3] = {nullptr, nullptr, nullptr};              // start / end of the pass (timing), done (other streams wait on it)
+    // candidates of a batched beam-search step (opt-in, SS_BATCH_BEAM=1): device / pinned [kMaxBatch][8]
+    TokData *beam_cand = nullptr, *beam_h_cand = nullptr;
     ~Engine();
 };
 

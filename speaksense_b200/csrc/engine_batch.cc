@@ -30,6 +30,8 @@ Engine::~Engine() {
     if (batch_scratch) cudaFree(batch_scratch);
     if (batch_h_flags) cudaFreeHost(batch_h_flags);
     if (enc_scratch) { cudaSetDevice(device); cudaFree(enc_scratch); }
+    if (beam_cand) { cudaSetDevice(device); cudaFree(beam_cand); }
+    if (beam_h_cand) cudaFreeHost(beam_h_cand);
     for (auto &e : enc_ev) if (e) cudaEventDestroy(e);
 }
 
@@ -390,6 +392,115 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// beam search on the batched step (opt-in: SS_BATCH_BEAM=1; written after the round's GPU budget was spent, NOT yet run).
+// The default beam path (engine.cc) launches the batch-1 kernel once per live beam and token and filters / sorts 51 866
+// logits per beam on the host; here the live beams of the window are the sequences of ONE batched step (they share the
+// state's cross-KV cache, each decoder keeps its own self-KV cache and control block) and bd_topk_kernel leaves k
+// candidates per beam.  Candidate ranking, duplicate skipping, the self-KV shuffle (beam_advance) and the per-token
+// bookkeeping stay on the host, exactly as in engine.cc.
+// ------------------------------------------------------------------------------------------------
+bool batch_beam_enabled() {
+    const char *e = getenv("SS_BATCH_BEAM");
+    return e && e[0] == '1';
+}
+bool batch_beam_supported(const State &s) {
+    const HParams &hp = s.engine->model.hp;
+    return hp.n_text_state == hp.n_text_head * 64 && hp.n_text_state <= 1280 && hp.n_text_ctx <= 512 && hp.n_audio_ctx <= 1536;
+}
+
+void decode_beam_batched(State &s, const FullParams &P, float t_cur, int n_cur, const std::vector<int> &prompt, int seek, int seek_end,
+                         int n_max, int tid0_init) {
+    Engine &E = *s.engine;
+    const Model &m = E.model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
+    std::lock_guard<std::mutex> lk(E.batch_mu);      // the operand buffers are the engine's
+    ensure_batch_resources(E);
+    if (!E.beam_cand) {
+        if (cudaMalloc(&E.beam_cand, (size_t)kMaxBatch * 8 * sizeof(TokData)) != cudaSuccess) SS_THROW(-5, "cudaMalloc failed");
+        if (cudaMallocHost(&E.beam_h_cand, (size_t)kMaxBatch * 8 * sizeof(TokData)) != cudaSuccess) SS_THROW(-5, "cudaMallocHost failed");
+    }
+    const int n_prompt = (int)prompt.size(), K = P.beam_size;
+    // the prompt goes through the batch-1 kernel on decoder 0 and is filtered on the host once, as in engine.cc
+    for (int j = 0; j < n_cur; j++) set_sampling(*s.dec[j], P, tid0_init);
+    step_host_sampled(s, *s.dec[0], prompt.data(), n_prompt, 0);
+    s.n_decoded += n_prompt - 1;
+    process_logits_host(m, P, *s.dec[0], s.h_logits, t_cur);
+    for (int j = 1; j < n_cur; j++) {
+        kv_copy(s, *s.dec[0], *s.dec[j], n_prompt);
+        s.dec[j]->probs = s.dec[0]->probs; s.dec[j]->logits = s.dec[0]->logits; s.dec[j]->logprobs = s.dec[0]->logprobs;
+    }
+    BatchParams bp{};
+    bp.d = hp.n_text_state; bp.H = hp.n_text_head; bp.L = hp.n_text_layer; bp.T = hp.n_audio_ctx; bp.ctx = hp.n_text_ctx; bp.n_vocab = hp.n_vocab;
+    bp.s4 = powf((float)(bp.d / bp.H), -0.25f);
+    bp.tok_emb = m.tok_emb; bp.d_pos = m.d_pos; bp.lnf_w = m.d_ln.w; bp.lnf_b = m.d_ln.b;
+    bp.eot = v.eot; bp.sot = v.sot; bp.translate = v.translate; bp.transcribe = v.transcribe; bp.solm = v.solm; bp.prev = v.prev;
+    bp.nosp = v.nosp; bp.not_ = v.not_; bp.beg = v.beg; bp.blank = v.blank;
+    bp.suppress_blank = P.suppress_blank; bp.tdrz = P.tdrz_enable; bp.tid0_init = tid0_init;
+    decode_batch_bind(bp, E.batch_scratch);
+    const MegaParams &w = s.dec[0]->mp;
+    const BeamStep bstep{t_cur, K, E.beam_cand};
+    std::vector<std::vector<TokData>> dev_cands(n_cur);      // candidates of decoder j from the last batched step
+    std::vector<BeamCandidate> cands;
+    for (int i = 0; i < n_max; i++) {
+        cands.clear();
+        for (int j = 0; j < n_cur; j++) {
+            Decoder &dc = *s.dec[j];
+            if (dc.completed || dc.failed) continue;
+            const std::vector<TokData> list = i == 0 ? sample_topk_host(m, dc, K) : dev_cands[j];
+            for (const TokData &t : list) {
+                cands.push_back({j, dc.seek_delta, dc.has_ts, dc.seq});
+                cands.back().seq.tokens.push_back(t);
+                cands.back().seq.sum_logprobs_all += t.plog;
+            }
+        }
+        beam_advance(s, cands, n_cur, i, n_prompt + i);
+        for (int j = 0; j < n_cur; j++) {
+            Decoder &dc = *s.dec[j];
+            if (dc.completed || dc.failed) continue;
+            const TokData &tk = dc.seq.tokens.back();
+            if (tk.id > v.beg) {
+                const int sd_new = 2 * (tk.id - v.beg);
+                if (dc.has_ts && dc.seek_delta > sd_new && dc.seq.result_len < i) { dc.failed = true; continue; }
+                dc.seek_delta = sd_new; dc.seq.result_len = i + 1; dc.has_ts = true;
+            }
+            if (tk.id == v.eot || (P.max_tokens > 0 && i >= P.max_tokens) || (dc.has_ts && seek + dc.seek_delta + 100 >= seek_end)) {
+                if (dc.seq.result_len == 0) {
+                    if (seek + dc.seek_delta + 100 >= seek_end) dc.seq.result_len = i + 1;
+                    else { dc.failed = true; continue; }
+                }
+                if (P.single_segment) { dc.seq.result_len = i + 1; dc.seek_delta = 100 * kChunkSec; }
+                dc.completed = true; continue;
+            }
+            if (i == n_max - 1 && (dc.seq.result_len == 0 || dc.seek_delta < 100 * kChunkSec / 2)) { dc.failed = true; continue; }
+        }
+        std::vector<int> live;
+        for (int j = 0; j < n_cur; j++) if (!(s.dec[j]->completed || s.dec[j]->failed)) live.push_back(j);
+        if (live.empty()) break;
+        // ---- one batched step for the live beams (on the state's stream: it follows beam_advance's cache copies)
+        const int n_past = n_prompt + i;
+        bp.B = (int)live.size();
+        for (int k = 0; k < bp.B; k++) {
+            Decoder &dc = *s.dec[live[k]];
+            DecCtl &c = *dc.h_ctl;
+            memset(&c, 0, offsetof(DecCtl, prompt));
+            const auto &tk = dc.seq.tokens;
+            c.pos = n_past; c.pos0 = n_past; c.token = tk.back().id; c.n_prompt = 1; c.sample = 2;
+            c.n_sampled = (int)tk.size(); c.last_id = tk.back().id; c.penult_id = tk.size() >= 2 ? tk[tk.size() - 2].id : -1;
+            c.has_ts = dc.has_ts; c.seek_delta = dc.seek_delta; c.result_len = dc.seq.result_len;
+            c.seek = seek; c.seek_end = seek_end; c.n_max = n_max;
+            CUDA_CHECK(cudaMemcpyAsync(dc.mp.ctl, dc.h_ctl, offsetof(DecCtl, prompt), cudaMemcpyHostToDevice, s.stream));
+            bp.seq[k] = BatchSeq{dc.mp.ctl, dc.mp.self_k, dc.mp.self_v, s.cross_k, s.cross_v, dc.mp.tok_out};
+        }
+        for (int k = bp.B; k < kMaxBatch; k++) bp.seq[k] = bp.seq[0];
+        CUDA_CHECK(cudaMemsetAsync(bp.n_done, 0, sizeof(int), s.stream));
+        decode_batch_step_enqueue(bp, w, /*need_logits=*/true, decode_batch_xsplit(bp.B, bp.H, E.sms), s.stream, &s.n_launches, &bstep);
+        CUDA_CHECK(cudaMemcpyAsync(E.beam_h_cand, E.beam_cand, (size_t)bp.B * 8 * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        for (int k = 0; k < bp.B; k++) dev_cands[live[k]].assign(E.beam_h_cand + (size_t)k * 8, E.beam_h_cand + (size_t)k * 8 + K);
+        s.n_decoded += bp.B;
+    }
+}
 
 int transcribe_batch(State *const *states, const float *const *pcm, const size_t *n, int batch, const FullParams &P, bool stream_mode) {
     if (batch <= 0) return 0;

@@ -148,6 +148,9 @@ void decode_batch_bind(BatchParams &P, void *scratch);
 int decode_batch_xsplit(int B, int H, int sms);
 // enqueue one step (all layers; LM head + sampling / prompt feeding) for the live sequences of P.  `w` carries the
 // weight pointers (any decoder's MegaParams of the same engine).
-void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st, int *launches);
+struct BeamStep { float temperature; int k; TokData *cand; };   // cand: device [kMaxBatch][8]
+// `beam` != nullptr (opt-in beam search on the batched step): the step ends with k candidates per sequence instead of a greedy token
+void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st, int *launches,
+                               const BeamStep *beam = nullptr);
 
 }  // namespace ss

@@ -187,3 +187,25 @@ def test_batched_encoder_pass_equals_per_clip_encoders(batch_on, shape, lang, n_
     for g, r in zip(got, ref):
         assert g[1] == r[1] and g[2] == r[2] and g[0] == r[0]
     eng.close()
+
+
+@pytest.mark.skipif(os.environ.get("SS_TEST_BATCH_BEAM") != "1",
+                    reason="beam search on the batched step (SS_BATCH_BEAM=1) was written after the round's GPU budget was spent and is "
+                           "off by default: set SS_TEST_BATCH_BEAM=1 to run it")
+@pytest.mark.parametrize("fixture,lang,beam", [("tiny_en_peaked", None, 5), ("micro_v3_peaked", "zh", 5), ("tiny_en_peaked", None, 2),
+                                                ("micro_v3_random", "zh", 3)])
+def test_beam_on_batched_step_equals_default_beam(request, audio30, fixture, lang, beam):
+    """SS_BATCH_BEAM=1: the live beams as sequences of one batched step, k candidates per beam selected on the device - same
+    tokens, segments and fallback count as the default beam path (one batch-1 launch per beam and token, host top-k), which
+    tests/test_gpu_transcribe.py holds to the oracle"""
+    from speaksense_b200 import AsrParams, WhisperAsr
+    eng = WhisperAsr(request.getfixturevalue(fixture))
+    p = AsrParams(language=lang, stream_mode=True, beam_size=beam)
+    ref = _single(eng, [audio30], p)[0]
+    os.environ["SS_BATCH_BEAM"] = "1"
+    try:
+        got = _single(eng, [audio30], p)[0]
+    finally:
+        os.environ.pop("SS_BATCH_BEAM", None)
+    assert got[1] == ref[1] and got[2] == ref[2] and got[3] == ref[3] and got[0] == ref[0]
+    eng.close()

@@ -14,6 +14,10 @@ SS_BATCH_PDL=0 timeout 60 python tools/batch_bench.py large-v3 32 2 1 > $OUT/${T
 # opt-in batched encoder pass (unverified at the end of round 1): parity, then its effect on configs[2]
 SS_TEST_BATCH_ENCODER=1 timeout 120 python -m pytest tests/test_gpu_batch.py -x -q -m gpu -k encoder_pass > $OUT/${TAG}_tests_batch_encoder.log 2>&1; echo "batched encoder rc=$? $(tail -1 $OUT/${TAG}_tests_batch_encoder.log)"
 SS_BATCH_ENCODER=1 timeout 60 python tools/batch_bench.py large-v3 32 2 1 > $OUT/${TAG}_batch_bench_encoder.json 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_batch_bench_encoder.json
+# opt-in beam search on the batched step (unverified at the end of round 1): parity, then one stream with beam 5 both ways
+SS_TEST_BATCH_BEAM=1 timeout 120 python -m pytest tests/test_gpu_batch.py -x -q -m gpu -k beam_on_batched > $OUT/${TAG}_tests_batch_beam.log 2>&1; echo "batched beam rc=$? $(tail -1 $OUT/${TAG}_tests_batch_beam.log)"
+timeout 120 python tools/stream_bench.py large-v3 60 5 > $OUT/${TAG}_stream_beam5.json 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_stream_beam5.json
+SS_BATCH_BEAM=1 timeout 120 python tools/stream_bench.py large-v3 60 5 > $OUT/${TAG}_stream_beam5_batched.json 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_stream_beam5_batched.json
 # smaller batches (where the step is launch / latency bound)
 for B in 4 8 16; do timeout 60 python tools/batch_bench.py large-v3 $B 2 1 2>> $OUT/${TAG}_bench.err | tee -a $OUT/${TAG}_batch_small.json; done
 # concurrent gRPC streams on one GPU: taking turns against the micro-batching front end
