@@ -169,3 +169,30 @@ def test_stream_sessions_through_the_front_end():
     finally:
         st_mod.denoise_audio = orig
         be.close()
+
+
+def test_rest_tasks_through_the_front_end(tmp_path, monkeypatch):
+    """two REST tasks (processors/transcribe.rs:62-167 mirror) running concurrently against one front end: their 30 s buffers
+    may share batches, their aggregated texts must not mix"""
+    import wave
+    from speaksense_b200 import audio, rest
+    monkeypatch.setattr(audio, "denoise_frames", lambda eng, st, fr, cfg=None: np.asarray(fr, np.float32).copy())
+    paths = []
+    for k, level in enumerate((0.25, 0.5)):
+        x = np.full(16000 * 65, level, np.float32)                     # 65 s -> three buffers per task
+        p = tmp_path / ("t%d.wav" % k)
+        with wave.open(str(p), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+            w.writeframes((x * 32767).astype("<i2").tobytes())
+        paths.append(str(p))
+    eng = _Engine(delay=0.01)
+    be = BatchingEngine(eng, linger_s=0.05)
+    res = _run_threads([lambda p=p: rest.TranscribeProcessor(be).process_audio(p, language="zh") for p in paths])
+    assert all(not isinstance(r, Exception) for r in res), res
+    assert res[0].n_calls == res[1].n_calls == 3
+    for r in res:                                                     # every piece of a task's text comes from ITS state
+        names = {piece.split(":")[0] for piece in r.text.replace("zh", "zh|").split("|") if piece}
+        assert len(names) == 1
+    assert {s.text.split(":")[0] for s in res[0].segments}.isdisjoint({s.text.split(":")[0] for s in res[1].segments})
+    assert sum(len(b[1]) for b in eng.batches) == 6
+    be.close()
