@@ -86,13 +86,13 @@ def _run_threads(fns):
 
 def test_concurrent_calls_are_merged_and_routed():
     eng = _Engine(delay=0.02)
-    be = BatchingEngine(eng, max_batch=8, linger_s=0.05)
+    be = BatchingEngine(eng, max_batch=8, linger_s=0.5)
     states = [be.create_state() for _ in range(6)]
     p = AsrParams(language="zh", stream_mode=True)
     res = _run_threads([lambda i=i: be.transcribe_with_state(states[i], np.full(4, i, np.float32), p) for i in range(6)])
     assert [r.full_text for r in res] == ["s%d:%d:zh" % (i + 1, i) for i in range(6)]
     assert sum(len(b[1]) for b in eng.batches) == 6
-    assert any(b[0] == "batch" and len(b[1]) >= 2 for b in eng.batches)       # merged (the 50 ms linger catches all six threads)
+    assert any(b[0] == "batch" and len(b[1]) >= 2 for b in eng.batches)       # merged (the 0.5 s linger catches the six threads even on a loaded box)
     assert be.n_requests == 6 and be.max_seen >= 2
     be.close()
 

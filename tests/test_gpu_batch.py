@@ -133,7 +133,7 @@ def test_batch_resident_clips_and_front_end(batch_on, tiny_en_peaked):
         eng.upload_pcm(s, c)
     assert eng.transcribe_batch(sts, [None, None, None], p) == ref
     assert eng.transcribe_batch(sts, [clips[0], None, clips[2]], p) == ref
-    be = BatchingEngine(eng, linger_s=0.2)
+    be = BatchingEngine(eng, linger_s=0.5)
     out = [None] * 3
 
     def call(i):
