@@ -54,7 +54,7 @@ def test_batch_equals_single_tiny(batch_on, tiny_en_peaked, n_clips):
     assert [g[1] for g in got] == [r[1] for r in ref]          # tokens
     assert [g[2] for g in got] == [r[2] for r in ref]          # raw segments (t0 / t1 / text)
     assert [g[0] for g in got] == [r[0] for r in ref]          # TranscribeResult after the Rust-side rules
-    assert all(n > 10 for n in launches)                        # the batched kernels ran (the batch-1 path is 1 launch per window)
+    assert all(n > 100 for n in launches)                       # the batched kernels ran (clip by clip: ~40 launches, encoder included)
     eng.close()
 
 

@@ -23,7 +23,7 @@ def test_one_clip_outlives_the_batch(tiny_en_peaked, stream_mode):
     got = eng.transcribe_batch(states, clips, p)
     for g, st, r in zip(got, states, ref):
         assert st.result_tokens()[0] == r[1] and st.raw_segments() == r[2] and g == r[0] and st.stats()["n_windows"] == r[3]
-    assert states[0].stats()["n_launches"] > 10                          # the first round went through the batched step
+    assert states[0].stats()["n_launches"] > 100                         # the first round went through the batched step (clip by clip: ~40)
     for st in states:
         st.close()
     eng.close()
