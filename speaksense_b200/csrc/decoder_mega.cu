@@ -42,13 +42,39 @@ constexpr int kMaxXs = 5120;          // largest mat-vec input (4 * d, d <= 1280
 constexpr int kMaxRowsPerCta = 512;   // per phase (LM head: n_vocab / grid)
 constexpr int kMaxScores = 512;
 constexpr int kMaxJ = 5;              // flagged pairs per thread and poll batch
-constexpr int kPre = 3;               // chunks per phase whose bias / residual operands are prefetched into registers
+#ifndef SS_MAX_INFLIGHT
+#define SS_MAX_INFLIGHT 0      // > 0: the producer keeps at most this many bulk copies outstanding (the ring still buffers kSlots chunks)
+#endif
+#ifndef SS_NO_STREAM
+#define SS_NO_STREAM 0         // 1 (timing experiment only, results are garbage): the producer copies 16 bytes per chunk instead of the chunk
+#endif
+#ifndef SS_SELF_ONLINE
+#define SS_SELF_ONLINE 0     // self-attention as one online (max, sum, P.V) reduction with two CTA barriers; 0: the five-barrier version (faster)
+#endif
+#ifndef SS_XEXP_INLINE
+#define SS_XEXP_INLINE 0     // cross-attention: exp(s - m) inside the P.V loop instead of a separate pass + barrier (slower)
+#endif
+#ifndef SS_XATTN8
+#define SS_XATTN8 0          // cross-attention: 8 lanes per key row (scores and P.V), 0: one thread per key / one lane per channel pair
+#endif
+#ifndef SS_NA
+#define SS_NA 2
+#endif
+#ifndef SS_KG
+#define SS_KG 2
+#endif
+constexpr int kG = SS_KG;                 // chunks of a phase that are in flight together (their reductions and epilogues overlap): FC1 / FC2 have 3 per CTA on 148 SMs
 typedef unsigned long long u64;
 constexpr int kProfN = 96;
 #ifndef SS_MEGA_PROFILE
 #define SS_MEGA_PROFILE 0      // 1: per-phase / per-stage cycle counters (tools/mega_prof.py; costs ~13 % of a step)
 #endif
 constexpr bool kProf = SS_MEGA_PROFILE != 0;
+#ifndef SS_MEGA_TRACE
+#define SS_MEGA_TRACE 0        // 1: thread 0 of every CTA timestamps (globaltimer) "input complete" / "outputs published" of every phase of ONE step
+#endif                         //    into P.prof[cta][kTraceN] (SS_MEGA_TRACE=<file> dumps it; tools/mega_trace.py rebuilds the critical path)
+constexpr int kTraceN = 1024, kTraceStep = 40;
+enum TracePhase : int { TP_QKV = 0, TP_SELF, TP_O, TP_CQ, TP_CROSS, TP_FOLD, TP_CO, TP_FC1, TP_FC2, TP_COUNT };
 
 enum SegKind : int { SEG_QKV = 0, SEG_O, SEG_CQ, SEG_XK, SEG_XV, SEG_CO, SEG_FC1, SEG_FC2, SEG_LM, SEG_COUNT };
 
@@ -77,6 +103,8 @@ struct __align__(128) MegaSmem {
     volatile int stop_req;      // consumers -> producer: stop issuing
     volatile int prod_done;     // producer -> consumers: `issued` is final
     volatile uint32_t issued;
+    long long trace_last;
+    int trace_on, trace_layer;  // (SS_MEGA_TRACE builds) the traced step is running / its current layer
     long long prof[kProfN];     // thread-0 cycle counters: [0..23] totals / per phase kind, [24 + kind * 8 + stage] per-stage breakdown
 };
 
@@ -98,6 +126,26 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+__device__ __forceinline__ void trace_event(int phase, int which) {
+#if SS_MEGA_TRACE
+    MegaSmem &sm = *reinterpret_cast<MegaSmem *>(mega_smem_raw);
+    if (threadIdx.x == 0 && sm.trace_on && sm.P.prof != nullptr) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sm.P.prof[(size_t)blockIdx.x * kTraceN + (sm.trace_layer * TP_COUNT + phase) * 2 + which] = (long long)t;
+    }
+#endif
+}
+// sub-stage durations of the traced step, summed over the layers: prof[cta][600 + k] += time since the previous mark / event
+__device__ __forceinline__ void trace_mark(int k) {
+#if SS_MEGA_TRACE
+    MegaSmem &sm = *reinterpret_cast<MegaSmem *>(mega_smem_raw);
+    if (threadIdx.x == 0 && sm.trace_on && sm.P.prof != nullptr) {
+        const long long t = clock64();      // (cycles: %globaltimer costs ~0.3 us per read)
+        if (k >= 0) sm.prof[k] += t - sm.trace_last;      // (shared memory; flushed to P.prof[cta][600 + k] when the kernel ends)
+        sm.trace_last = t;
+    }
+#endif
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
@@ -287,23 +335,19 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
     long long tq = prof_on ? clock64() : 0;
 #define SS_STAGE(k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + KIND * 8 + (k)] += tn - tq; tq = tn; }
     // ---- static / already-valid operands of the epilogue, fetched now so that their L2 latency hides behind the poll
-    float pb[kPre], pr[kPre];       // bias / residual of the rows this (finishing) lane publishes in chunks 0..kPre-1
-#pragma unroll
-    for (int c = 0; c < kPre; c++) { pb[c] = 0.f; pr[c] = 0.f; }
+    // epilogue role of this lane inside a group of kG chunks: lanes 2g, 2g+1 finish rows 2w, 2w+1 of the group's chunk g
+    const int eg = lane >> 1, el = lane & 1;
+    float pb = 0.f, pr = 0.f;      // bias / residual of the row this lane publishes in the phase's first group
     float fb = 0.f, fr = 0.f;      // FC2: bias and residual of output row `tid` (folded after the tiles)
     const int tok = sm.st.token, pos = sm.st.pos;
     if (KIND == SEG_FC2) {
         if (tid < sm.seg[KIND].rows) { fb = __ldg(P.layer[il].b[5] + row0 + tid); fr = ll_value(P.xC + row0 + tid); }
-    } else if (KIND != SEG_LM && lane < 2) {
-        const float *bias = P.layer[il].b[widx] + row0;
-#pragma unroll
-        for (int c = 0; c < kPre; c++) {
-            const int R = tile_row<KIND>(c, warp, lane);
-            if (R < prows) {
-                pb[c] = __ldg(bias + R);
-                if (KIND == SEG_O) pr[c] = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * D + row0 + R)) + __ldg(P.d_pos + (size_t)pos * D + row0 + R) : ll_value(P.xA + row0 + R);
-                else if (KIND == SEG_CO) pr[c] = ll_value(P.xB + row0 + R);
-            }
+    } else if (KIND != SEG_LM && lane < 2 * kG) {
+        const int R = tile_row<KIND>(eg, warp, el);
+        if (R < prows) {
+            pb = __ldg(P.layer[il].b[widx] + row0 + R);
+            if (KIND == SEG_O) pr = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * D + row0 + R)) + __ldg(P.d_pos + (size_t)pos * D + row0 + R) : ll_value(P.xA + row0 + R);
+            else if (KIND == SEG_CO) pr = ll_value(P.xB + row0 + R);
         }
     }
     // ---- A fragments of the first chunk: the weights are static and the producer runs ahead, so they are fetched
@@ -389,6 +433,8 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
         SS_STAGE(0)
     }
     consumer_sync();
+    trace_event(KIND == SEG_QKV ? TP_QKV : KIND == SEG_O ? TP_O : KIND == SEG_CQ ? TP_CQ : KIND == SEG_CO ? TP_CO : KIND == SEG_FC1 ? TP_FC1 : TP_FC2, 0);
+    trace_mark(-1);
     SS_STAGE(2)
     // ---- B fragments: the x side of every k-step, in registers for the whole phase
     uint32_t bf[2 * KS];
@@ -400,80 +446,99 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
             bf[2 * j + 1] = *reinterpret_cast<const uint32_t *>(xq + 128 * j + 64);
         }
     }
-    const int g = lane >> 2;
-    const bool diag = (lane & 3) == (g >> 1), odd = (g & 1) != 0;
+    const int g4 = lane >> 2;
+    const bool diag = (lane & 3) == (g4 >> 1), odd = (g4 & 1) != 0;
     // where this finishing lane publishes (kinds with one flagged output buffer)
-    u64 *outp = (KIND == SEG_O ? P.xB : KIND == SEG_CO ? P.xC : KIND == SEG_CQ ? P.q2 : P.hbuf) + row0 + tile_row<KIND>(0, warp, lane & 1);
+    u64 *outp = (KIND == SEG_O ? P.xB : KIND == SEG_CO ? P.xC : KIND == SEG_CQ ? P.q2 : P.hbuf) + row0 + tile_row<KIND>(0, warp, el);
     const float s4 = P.s4;
+    // The chunks of a phase go through the tensor cores in groups of kG: per chunk ldmatrix (chunk 0: done above) -> KS mma -> slot
+    // handed back; the slice reductions (5 shuffle levels per row) and the epilogues of the whole group then run interleaved, so a
+    // phase pays the shuffle / activation / store latency chain once per group instead of once per chunk.
 #pragma unroll 1
-    for (int ch = 0; ch < n_chunks; ch++) {
-        constexpr int NA = KS >= 2 ? 2 : 1;     // independent accumulator sets
-        float cc[NA][4];
+    for (int c0 = 0; c0 < n_chunks; c0 += kG) {
+        float v0[kG], v1[kG];
 #pragma unroll
-        for (int i = 0; i < NA; i++) { cc[i][0] = 0.f; cc[i][1] = 0.f; cc[i][2] = 0.f; cc[i][3] = 0.f; }
+        for (int g = 0; g < kG; g++) {
+            v0[g] = 0.f; v1[g] = 0.f;
+            const int ch = c0 + g;
+            if (ch < n_chunks) {        // (CTA-uniform)
+                if (ch > 0) {
+                    const int slot = cons % kSlots;
+                    if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[13] += clock64() - tw0; }
+                    else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
+                    const uint32_t abase = smem_u32(sm.ring[slot]) + a_off;
 #pragma unroll
-        for (int j = 0; j < KS; j++)
-            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                         : "+f"(cc[j % NA][0]), "+f"(cc[j % NA][1]), "+f"(cc[j % NA][2]), "+f"(cc[j % NA][3])
-                         : "r"(af[j][0]), "r"(af[j][1]), "r"(af[j][2]), "r"(af[j][3]), "r"(bf[2 * j]), "r"(bf[2 * j + 1]));
-        if (ch > 0) {      // (chunk 0 was released in the prologue)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[cons % kSlots]);      // every ldmatrix of this warp has been consumed by an issued mma
-        }
-        cons++;
-        if (ch + 1 < n_chunks) {       // A fragments of the next chunk: in flight while this chunk's rows are reduced and published
-            const int slot = cons % kSlots;
-            if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[13] += clock64() - tw0; }
-            else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
-            const uint32_t abase = smem_u32(sm.ring[slot]) + a_off;
-#pragma unroll
-            for (int j = 0; j < KS; j++)
-                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 256u * j));
-        }
-#pragma unroll
-        for (int i = 1; i < NA; i++) { cc[0][0] += cc[i][0]; cc[0][1] += cc[i][1]; cc[0][2] += cc[i][2]; cc[0][3] += cc[i][3]; }
-        float v0 = diag ? (odd ? cc[0][1] : cc[0][0]) : 0.f;      // row 2w   : sum over its 8 slices
-        float v1 = diag ? (odd ? cc[0][3] : cc[0][2]) : 0.f;      // row 2w+1
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
-        float hid = 0.f, hid_hi = 0.f;
-        if (KIND == SEG_FC1) {       // hidden units leave in pairs (this CTA's slice starts and ends on even rows)
-            const float b1 = ch == 0 ? pb[0] : ch == 1 ? pb[1] : ch == 2 ? pb[2] : (lane < 2 ? __ldg(P.layer[il].b[widx] + row0 + min(tile_row<KIND>(ch, warp, lane), prows - 1)) : 0.f);
-            hid = gelu16((lane ? v1 : v0) + b1);
-            hid_hi = __shfl_down_sync(0xffffffffu, hid, 1);
-        }
-        if (lane < 2) {
-            const int R = tile_row<KIND>(ch, warp, lane);
-            if (R < prows) {
-                const float val = lane ? v1 : v0;
-                if (KIND == SEG_FC2) sm.p4[R] = val;
-                else if (KIND == SEG_LM) sm.acc[R] = val;
-                else {
-                    float b, r;
-                    if (ch == 0) { b = pb[0]; r = pr[0]; } else if (ch == 1) { b = pb[1]; r = pr[1]; } else if (ch == 2) { b = pb[2]; r = pr[2]; }
-                    else {      // more chunks per phase than prefetch registers (fewer SMs than the design point)
-                        b = __ldg(P.layer[il].b[widx] + row0 + R); r = 0.f;
-                        if (KIND == SEG_O) r = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * D + row0 + R)) + __ldg(P.d_pos + (size_t)pos * D + row0 + R) : ll_value(P.xA + row0 + R);
-                        else if (KIND == SEG_CO) r = ll_value(P.xB + row0 + R);
-                    }
-                    const float v = val + b;
-                    if (KIND == SEG_QKV) {
-                        const int row = row0 + R;
-                        if (row < D) ll_store(P.q1 + row, r16(v * s4), ep_out);
-                        else if (row < 2 * D) {
-                            const int n = row - D; const __half hk = __float2half_rn(v * s4);
-                            (P.self_k + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
-                        } else {
-                            const int n = row - 2 * D; const __half hv = __float2half_rn(v);
-                            (P.self_v + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
-                        }
-                    } else if (KIND == SEG_O || KIND == SEG_CO) ll_store(outp + kChunkRows * ch, r + v, ep_out);
-                    else if (KIND == SEG_CQ) ll_store(outp + kChunkRows * ch, r16(v * s4), ep_out);
-                    else if (lane == 0) ll_store_h2(P.hbuf + ((row0 + R) >> 1), hid, hid_hi, ep_out);
+                    for (int j = 0; j < KS; j++)
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(af[j][0]), "=r"(af[j][1]), "=r"(af[j][2]), "=r"(af[j][3]) : "r"(abase + 256u * j));
                 }
+                constexpr int NA = KS >= SS_NA ? SS_NA : KS;     // independent accumulator sets
+                float cc[NA][4];
+#pragma unroll
+                for (int i = 0; i < NA; i++) { cc[i][0] = 0.f; cc[i][1] = 0.f; cc[i][2] = 0.f; cc[i][3] = 0.f; }
+#pragma unroll
+                for (int j = 0; j < KS; j++)
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(cc[j % NA][0]), "+f"(cc[j % NA][1]), "+f"(cc[j % NA][2]), "+f"(cc[j % NA][3])
+                                 : "r"(af[j][0]), "r"(af[j][1]), "r"(af[j][2]), "r"(af[j][3]), "r"(bf[2 * j]), "r"(bf[2 * j + 1]));
+                if (ch > 0) {      // (chunk 0 was released in the prologue)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty[cons % kSlots]);      // every ldmatrix of this warp has been consumed by an issued mma
+                }
+                cons++;
+#pragma unroll
+                for (int i = 1; i < NA; i++) { cc[0][0] += cc[i][0]; cc[0][1] += cc[i][1]; cc[0][2] += cc[i][2]; cc[0][3] += cc[i][3]; }
+                v0[g] = diag ? (odd ? cc[0][1] : cc[0][0]) : 0.f;      // row 2w   : its 8 slices sit on the diagonal
+                v1[g] = diag ? (odd ? cc[0][3] : cc[0][2]) : 0.f;      // row 2w+1
             }
         }
+        trace_mark(KIND * 8 + 0);      // B fragments, ldmatrix, mma of the group
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int g = 0; g < kG; g++) { v0[g] += __shfl_xor_sync(0xffffffffu, v0[g], o); v1[g] += __shfl_xor_sync(0xffffffffu, v1[g], o); }
+        }
+        if (SS_MEGA_TRACE) { float z = 0.f; for (int g = 0; g < kG; g++) z += v0[g] + v1[g]; asm volatile("" ::"f"(z)); }
+        trace_mark(KIND * 8 + 1);      // slice reductions
+        // every lane now holds every row sum of the group: lanes 2g, 2g+1 finish chunk c0 + g
+        float val = el ? v1[0] : v0[0];
+#pragma unroll
+        for (int g = 1; g < kG; g++) if (eg == g) val = el ? v1[g] : v0[g];
+        const int ch = c0 + eg;
+        const int R = tile_row<KIND>(ch, warp, el);
+        const bool mine = lane < 2 * kG && ch < n_chunks && R < prows;
+        float b = pb, r = pr;
+        if (c0 > 0 && mine && KIND != SEG_FC2 && KIND != SEG_LM) {      // more chunks per phase than one group (fewer SMs than the design point)
+            b = __ldg(P.layer[il].b[widx] + row0 + R); r = 0.f;
+            if (KIND == SEG_O) r = il == 0 ? __half2float(__ldg(P.tok_emb + (size_t)tok * D + row0 + R)) + __ldg(P.d_pos + (size_t)pos * D + row0 + R) : ll_value(P.xA + row0 + R);
+            else if (KIND == SEG_CO) r = ll_value(P.xB + row0 + R);
+        }
+        float hid = 0.f, hid_hi = 0.f;
+        if (KIND == SEG_FC1) {       // hidden units leave in pairs (this CTA's slice starts and ends on even rows)
+            hid = gelu16(val + b);
+            hid_hi = __shfl_down_sync(0xffffffffu, hid, 1);
+        }
+        if (mine) {
+            if (KIND == SEG_FC2) sm.p4[R] = val;
+            else if (KIND == SEG_LM) sm.acc[R] = val;
+            else {
+                const float v = val + b;
+                if (KIND == SEG_QKV) {
+                    const int row = row0 + R;
+                    if (row < D) ll_store(P.q1 + row, r16(v * s4), ep_out);
+                    else if (row < 2 * D) {
+                        const int n = row - D; const __half hk = __float2half_rn(v * s4);
+                        (P.self_k + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
+                    } else {
+                        const int n = row - 2 * D; const __half hv = __float2half_rn(v);
+                        (P.self_v + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
+                    }
+                } else if (KIND == SEG_O || KIND == SEG_CO) ll_store(outp + kChunkRows * ch, r + v, ep_out);
+                else if (KIND == SEG_CQ) ll_store(outp + kChunkRows * ch, r16(v * s4), ep_out);
+                else if (el == 0) ll_store_h2(P.hbuf + ((row0 + R) >> 1), hid, hid_hi, ep_out);
+            }
+        }
+        trace_mark(KIND * 8 + 2);      // epilogue + stores
     }
     if (prof_on) sm.prof[1] += clock64() - tq;
     SS_STAGE(3)
@@ -485,6 +550,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
         }
         SS_STAGE(4)
     } else if (KIND == SEG_LM) consumer_sync();     // lm_epilogue reads other warps' rows
+    if (KIND != SEG_LM) trace_event(KIND == SEG_QKV ? TP_QKV : KIND == SEG_O ? TP_O : KIND == SEG_CQ ? TP_CQ : KIND == SEG_CO ? TP_CO : KIND == SEG_FC1 ? TP_FC1 : TP_FC2, 1);
 #undef SS_STAGE
     return cons;
 }
@@ -555,7 +621,7 @@ __device__ __forceinline__ float xattn_scores(const uint8_t *K, int n, int sc_ba
     }
     return lmax;
 }
-__device__ __forceinline__ void xattn_pv(const uint8_t *V, int n, int sc_base, float &o0, float &o1) {
+__device__ __forceinline__ void xattn_pv_p(const uint8_t *V, int n, int sc_base, float &o0, float &o1) {
     MegaSmem &sm = SM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint8_t *col = V + lane * 4;
@@ -570,6 +636,41 @@ __device__ __forceinline__ void xattn_pv(const uint8_t *V, int n, int sc_base, f
     o0 += b0; o1 += b1;
 }
 
+// P.V with the soft-max numerator computed in place: every lane of a warp turns the warp's raw scores into exp(s - m) itself
+// (one MUFU per key and lane), so no separate exp pass / barrier; `lsum` accumulates the warp's share of the denominator
+__device__ __forceinline__ void xattn_pv(const uint8_t *V, int n, int sc_base, float m, float &o0, float &o1, float &lsum) {
+    MegaSmem &sm = SM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint8_t *col = V + lane * 4;
+    float b0 = 0.f, b1 = 0.f, l1 = 0.f;
+    int j = warp;
+    for (; j + 8 < n; j += 16) {
+        const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)), vb = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)(j + 8) * 128));
+        const float pa = __expf(sm.sc[sc_base + j] - m), pb = __expf(sm.sc[sc_base + j + 8] - m);
+        lsum += pa; l1 += pb;
+        o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); b0 = fmaf(pb, vb.x, b0); b1 = fmaf(pb, vb.y, b1);
+    }
+    if (j < n) { const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)); const float pa = __expf(sm.sc[sc_base + j] - m); lsum += pa; o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); }
+    o0 += b0; o1 += b1; lsum += l1;
+}
+
+// 8 lanes per key row, 4 rows per warp and step (as attn_scores); exp(s - m) in place; every lane of an 8-lane group adds the
+// same numerators, so `lsum` is the group's share of the denominator
+__device__ __forceinline__ void xattn_pv8(const uint8_t *V, int n, int sc_base, float m, float (&acc)[8], float &lsum) {
+    MegaSmem &sm = SM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+    for (int jb = 0; jb < n; jb += 128) {
+        uint4 vv[4]; float pp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = jb + u * 32 + warp * 4 + sub;
+            if (j < n) { vv[u] = *reinterpret_cast<const uint4 *>(V + (size_t)j * 128 + l8 * 16); pp[u] = __expf(sm.sc[sc_base + j] - m); }
+            else { vv[u] = make_uint4(0, 0, 0, 0); pp[u] = 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { lsum += pp[u]; axpy8(vv[u], pp[u], acc); }
+    }
+}
 // fold the per-lane P.V partial sums of the CTA into 64 channel sums (thread c < 64 returns channel c)
 __device__ __forceinline__ float attn_fold(float (&acc)[8]) {
     MegaSmem &sm = SM;
@@ -586,10 +687,11 @@ __device__ __forceinline__ float attn_fold(float (&acc)[8]) {
     return o;
 }
 
+// (v1: separate max / sum / P.V reductions, five CTA barriers - measured 1.5 % faster than the online variant below)
 // self-attention, one CTA per head: past keys/values from the KV cache in L2 (the first 128 positions are fetched into
 // registers BEFORE the poll: their addresses do not depend on the current token, so the L2 latency hides behind the wait
 // for q), the current token's q/k/v from the flagged exchange buffers
-__device__ __noinline__ void self_attn(int il, uint32_t ep) {
+__device__ __noinline__ void self_attn_v1(int il, uint32_t ep) {
     MegaSmem &sm = SM;
     const MegaParams &P = sm.P;
     const int h = blockIdx.x, tid = threadIdx.x;
@@ -597,6 +699,7 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
     const int n_past = sm.st.pos, d = P.d, l8 = tid & 7, r8 = tid >> 3;
     const bool prof_on = kProf && P.prof != nullptr && tid == 0;
     long long tq = prof_on ? clock64() : 0;
+#undef SS_STAGE
 #define SS_STAGE(kd, k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + (kd) * 8 + (k)] += tn - tq; tq = tn; }
     const uint8_t *Kh = reinterpret_cast<const uint8_t *>(P.self_k + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
     const uint8_t *Vh = reinterpret_cast<const uint8_t *>(P.self_v + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
@@ -615,6 +718,7 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
         sm.qkv[which * 64 + 2 * i2] = __uint_as_float((uint32_t)v.x); sm.qkv[which * 64 + 2 * i2 + 1] = __uint_as_float((uint32_t)v.y);
     }
     consumer_sync();
+    trace_event(TP_SELF, 0);
     SS_STAGE(SEG_XV, 0)
     const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
     float lmax = -INFINITY;
@@ -651,8 +755,125 @@ __device__ __noinline__ void self_attn(int il, uint32_t ep) {
         const float o_hi = __shfl_down_sync(0xffffffffu, o, 1);
         if ((tid & 1) == 0) ll_store_h2(P.att1 + h * 32 + (tid >> 1), o, o_hi, ep);
     }
+    trace_event(TP_SELF, 1);
     SS_STAGE(SEG_XV, 4)
 }
+
+// self-attention, one CTA per head: past keys/values from the KV cache in L2 (the first 128 positions are fetched into
+// registers BEFORE the poll: their addresses do not depend on the current token, so the L2 latency hides behind the wait
+// for q), the current token's q/k/v from the flagged exchange buffers.  Soft-max and P.V run as ONE online reduction
+// (every 8-lane group keeps {max, sum, 8 channels} of its keys; groups merge by shuffles, warps through shared memory):
+// two CTA barriers per call instead of five.
+__device__ __forceinline__ void osm_merge(float &m, float &l, float (&acc)[8], float m2, float l2, const float (&a2)[8]) {
+    const float mn = fmaxf(m, m2);
+    const float s1 = m > -INFINITY ? __expf(m - mn) : 0.f, s2 = m2 > -INFINITY ? __expf(m2 - mn) : 0.f;
+    l = l * s1 + l2 * s2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = acc[i] * s1 + a2[i] * s2;
+    m = mn;
+}
+__device__ __noinline__ void self_attn_online(int il, uint32_t ep) {
+    MegaSmem &sm = SM;
+    const MegaParams &P = sm.P;
+    const int h = blockIdx.x, tid = threadIdx.x;
+    if (h >= P.H) return;
+    const int n_past = sm.st.pos, d = P.d, l8 = tid & 7, r8 = tid >> 3, warp = tid >> 5, lane = tid & 31;
+    const bool prof_on = kProf && P.prof != nullptr && tid == 0;
+    long long tq = prof_on ? clock64() : 0;
+#undef SS_STAGE
+#define SS_STAGE(kd, k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + (kd) * 8 + (k)] += tn - tq; tq = tn; }
+    const uint8_t *Kh = reinterpret_cast<const uint8_t *>(P.self_k + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
+    const uint8_t *Vh = reinterpret_cast<const uint8_t *>(P.self_v + (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64);
+    uint4 kr[4], vr[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = min(u * 32 + r8, max(n_past - 1, 0));      // clamped: rows past the end are fetched but not used
+        kr[u] = __ldcg(reinterpret_cast<const uint4 *>(Kh + (size_t)j * 128 + l8 * 16));
+        vr[u] = __ldcg(reinterpret_cast<const uint4 *>(Vh + (size_t)j * 128 + l8 * 16));
+    }
+    if (tid < 96) {   // 3 x 64 flagged floats: q, k, v of this head
+        const int which = tid >> 5, i2 = tid & 31;
+        const u64 *src = (which == 0 ? P.q1 : which == 1 ? P.kcur : P.vcur) + h * 64 + 2 * i2;
+        ulonglong2 v;
+        do { v = ll_load2(src); } while ((uint32_t)(v.x >> 32) != ep || (uint32_t)(v.y >> 32) != ep);
+        sm.qkv[which * 64 + 2 * i2] = __uint_as_float((uint32_t)v.x); sm.qkv[which * 64 + 2 * i2 + 1] = __uint_as_float((uint32_t)v.y);
+    }
+    consumer_sync();
+    trace_event(TP_SELF, 0);
+    trace_mark(-1);
+    SS_STAGE(SEG_XV, 0)
+    const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
+    float m = -INFINITY, l = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int jb = 0; jb < n_past; jb += 128) {      // (one trip unless the window has more than 128 tokens)
+        if (jb > 0) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = min(jb + u * 32 + r8, n_past - 1);
+                kr[u] = __ldcg(reinterpret_cast<const uint4 *>(Kh + (size_t)j * 128 + l8 * 16));
+                vr[u] = __ldcg(reinterpret_cast<const uint4 *>(Vh + (size_t)j * 128 + l8 * 16));
+            }
+        }
+        float sv[4], bm = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float ds = dot8(kr[u], qa, qb, 0.f);
+            ds += __shfl_xor_sync(0xffffffffu, ds, 1);
+            ds += __shfl_xor_sync(0xffffffffu, ds, 2);
+            ds += __shfl_xor_sync(0xffffffffu, ds, 4);
+            sv[u] = jb + u * 32 + r8 < n_past ? ds : -INFINITY;
+            bm = fmaxf(bm, sv[u]);
+        }
+        if (bm > -INFINITY) {       // (uniform inside an 8-lane group)
+            float bl = 0.f, ba[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const float pu = sv[u] > -INFINITY ? __expf(sv[u] - bm) : 0.f; bl += pu; axpy8(vr[u], pu, ba); }
+            osm_merge(m, l, acc, bm, bl, ba);
+        }
+    }
+    trace_mark(90);      // scores + online soft-max of the group
+    // the four 8-lane groups of a warp
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+        float a2[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) a2[i] = __shfl_xor_sync(0xffffffffu, acc[i], o);
+        osm_merge(m, l, acc, m2, l2, a2);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) sm.red[warp][l8 * 8 + i] = acc[i];
+        if (lane == 0) sm.red2[warp] = make_float2(m, l);
+    }
+    // the current token's own key (warps 0 and 1 each need it for their channels)
+    float s_self = 0.f;
+    if (tid < 64) { s_self = sm.qkv[lane] * sm.qkv[64 + lane] + sm.qkv[32 + lane] * sm.qkv[96 + lane]; s_self = warp_sum(s_self); }
+    SS_STAGE(SEG_XV, 1)
+    trace_mark(91);      // group merges, own key
+    consumer_sync();
+    trace_mark(92);      // barrier
+    SS_STAGE(SEG_XV, 2)
+    if (tid < 64) {
+        float M = s_self;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; w++) M = fmaxf(M, sm.red2[w].x);
+        const float e0 = __expf(s_self - M);
+        float L = e0, o = e0 * sm.qkv[128 + tid];
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; w++) {
+            const float2 ml = sm.red2[w];
+            if (ml.x > -INFINITY) { const float e = __expf(ml.x - M); L += ml.y * e; o += sm.red[w][tid] * e; }
+        }
+        o /= L;
+        const float o_hi = __shfl_down_sync(0xffffffffu, o, 1);
+        if ((tid & 1) == 0) ll_store_h2(P.att1 + h * 32 + (tid >> 1), o, o_hi, ep);
+    }
+    trace_mark(93);      // final merge + store
+    trace_event(TP_SELF, 1);
+    SS_STAGE(SEG_XV, 4)
+}
+
+__device__ __forceinline__ void self_attn(int il, uint32_t ep) { if (SS_SELF_ONLINE) self_attn_online(il, ep); else self_attn_v1(il, ep); }
 
 // cross-attention; K then V of this CTA's (head, key split) streamed through the ring; split 0 of every head
 // folds the head's partials into the attention vector
@@ -672,6 +893,8 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
         sm.qkv[2 * tid] = __uint_as_float((uint32_t)v.x); sm.qkv[2 * tid + 1] = __uint_as_float((uint32_t)v.y);
     }
     consumer_sync();
+    trace_event(TP_CROSS, 0);
+    trace_mark(-1);
     SS_STAGE(SEG_XK, 0)
     float lmax = -INFINITY;
     for (int ch = 0; ch < sk.n_chunks; ch++) {
@@ -679,51 +902,83 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
         if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[14] += clock64() - tw0; }
         else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
-        lmax = xattn_scores(sm.ring[slot], nk, kbase, lmax);
+        if (SS_XATTN8) {
+            const int l8 = lane & 7;
+            const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
+            lmax = attn_scores<true>(sm.ring[slot], nk, kbase, qa, qb, lmax);
+        } else lmax = xattn_scores(sm.ring[slot], nk, kbase, lmax);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
     }
     SS_STAGE(SEG_XK, 1)
-    const float m = consumer_max(lmax);
-    float lsum = 0.f;
-    for (int j = tid; j < n; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; lsum += e; }
-    const float l = consumer_sum(lsum);        // its barrier also publishes the probabilities
+    trace_mark(80);      // scores
+    const float m = consumer_max(lmax);        // its barrier also publishes the raw scores
+    trace_mark(81);      // max
+    float l_cta = 0.f;
+    if (!SS_XEXP_INLINE) {
+        float ls = 0.f;
+        for (int j = tid; j < n; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; ls += e; }
+        l_cta = consumer_sum(ls);        // its barrier also publishes the probabilities
+    }
     SS_STAGE(SEG_XK, 2)
-    float o0 = 0.f, o1 = 0.f;
+    float o0 = 0.f, o1 = 0.f, lsum = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int ch = 0; ch < sk.n_chunks; ch++) {     // the V slice has the same chunking as the K slice
         const int slot = cons % kSlots;
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
-        xattn_pv(sm.ring[slot], nk, kbase, o0, o1);
+        if (SS_XATTN8) xattn_pv8(sm.ring[slot], nk, kbase, m, acc, lsum);
+        else if (SS_XEXP_INLINE) xattn_pv(sm.ring[slot], nk, kbase, m, o0, o1, lsum);
+        else xattn_pv_p(sm.ring[slot], nk, kbase, o0, o1);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
     }
     SS_STAGE(SEG_XK, 3)
-    *reinterpret_cast<float2 *>(&sm.red[tid >> 5][2 * lane]) = make_float2(o0, o1);
-    consumer_sync();
+    trace_mark(82);      // P.V
     float o = 0.f;
-    if (tid < 64) for (int w = 0; w < kConsumerWarps; w++) o += sm.red[w][tid];
+    if (SS_XATTN8) {
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, 8); lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+        if (lane == 0) sm.red2[tid >> 5].x = lsum;
+        o = attn_fold(acc);
+    } else {
+        *reinterpret_cast<float2 *>(&sm.red[tid >> 5][2 * lane]) = make_float2(o0, o1);
+        if (lane == 0) sm.red2[tid >> 5].x = lsum;      // (every lane of a warp holds the same sum)
+        consumer_sync();
+        if (tid < 64) for (int w = 0; w < kConsumerWarps; w++) o += sm.red[w][tid];
+    }
     u64 *out = P.part + ((size_t)h * ns + sp) * 66;
     if (tid < 64) ll_store(out + 2 + tid, o, ep);
-    if (tid == 0) { ll_store(out, m, ep); ll_store(out + 1, l, ep); }
+    if (tid == 0) {
+        float l = l_cta;
+        if (SS_XEXP_INLINE || SS_XATTN8) { l = 0.f; for (int w = 0; w < kConsumerWarps; w++) l += sm.red2[w].x; }
+        ll_store(out, m, ep); ll_store(out + 1, l, ep);
+    }
+    trace_mark(83);      // fold + stores
+    trace_event(TP_CROSS, 1);
     SS_STAGE(SEG_XK, 4)
     if (sp != 0) return cons;
     // ---- split 0 folds all ns (<= 8) partial records of head h
     poll_vec<false>(P.part + (size_t)h * ns * 66, ns * 66, ep, sm.xs);
     consumer_sync();
-    if (tid < 64) {
-        float M = -INFINITY;
-        for (int s2 = 0; s2 < ns; s2++) M = fmaxf(M, sm.xs[s2 * 66]);
-        float Lsum = 0.f, oo = 0.f;
-        for (int s2 = 0; s2 < ns; s2++) {
-            const float pm = sm.xs[s2 * 66];
-            if (pm > -INFINITY) { const float e = __expf(pm - M); Lsum += sm.xs[s2 * 66 + 1] * e; oo += sm.xs[s2 * 66 + 2 + tid] * e; }
+    trace_event(TP_FOLD, 0);
+    if (tid < 64) {      // (ns <= 8: all loads first, independent exponentials, no loop-carried latency chains)
+        float pm[8], pl[8], po[8];
+#pragma unroll
+        for (int s2 = 0; s2 < 8; s2++) {
+            const bool on = s2 < ns;
+            pm[s2] = on ? sm.xs[s2 * 66] : -INFINITY; pl[s2] = on ? sm.xs[s2 * 66 + 1] : 0.f; po[s2] = on ? sm.xs[s2 * 66 + 2 + tid] : 0.f;
         }
+        float M = pm[0];
+#pragma unroll
+        for (int s2 = 1; s2 < 8; s2++) M = fmaxf(M, pm[s2]);
+        float Lsum = 0.f, oo = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < 8; s2++) { const float e = pm[s2] > -INFINITY ? __expf(pm[s2] - M) : 0.f; Lsum = fmaf(pl[s2], e, Lsum); oo = fmaf(po[s2], e, oo); }
         const float a = oo / Lsum, a_hi = __shfl_down_sync(0xffffffffu, a, 1);
         if ((tid & 1) == 0) ll_store_h2(P.att2 + h * 32 + (tid >> 1), a, a_hi, ep);
     }
+    trace_event(TP_FOLD, 1);
     consumer_sync();
     SS_STAGE(SEG_XK, 5)
 #undef SS_STAGE
@@ -923,6 +1178,7 @@ __device__ __noinline__ uint32_t consumer_main(const ConsArgs a) {
 #pragma unroll 1
         for (int il = 0; il < L; il++) {
             const uint32_t ep = ep0 + (uint32_t)il;
+            if (SS_MEGA_TRACE && tid == 0) { sm.trace_on = t == kTraceStep; sm.trace_layer = il; }
             long long tp = kProf ? clock64() : 0;
 #define SS_PROF_PHASE(k) if (kProf) { const long long tn = clock64(); if (tid == 0) sm.prof[4 + (k)] += tn - tp; tp = tn; }
             cons = gemv_phase<KS, SEG_QKV>(cons, il, ep, ep, ph++);       SS_PROF_PHASE(0)
@@ -988,7 +1244,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
 
     if (tid == 0) {
         for (int s = 0; s < kSlots; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kConsumerWarps); }
-        sm.stop_req = 0; sm.prod_done = 0; sm.issued = 0;
+        sm.stop_req = 0; sm.prod_done = 0; sm.issued = 0; sm.trace_on = 0; sm.trace_layer = 0;
         for (int i = 0; i < kProfN; i++) sm.prof[i] = 0;
         DecState st;
         st.pos = pos_start; st.token = ctl->token; st.n_sampled = ctl->n_sampled; st.has_ts = ctl->has_ts; st.seek_delta = ctl->seek_delta;
@@ -1023,12 +1279,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
                     if (lane == 0) {
                         while (!mbar_try_wait(&sm.empty[slot], par)) { if (sm.stop_req) { stopped = true; break; } __nanosleep(128); }   // do not out-prioritise the consumer warps of this scheduler
                         if (sm.stop_req) stopped = true;
-                        if (!stopped) mbar_expect_tx(&sm.full[slot], (uint32_t)nrows * seg.row_bytes);
+                        if (SS_MAX_INFLIGHT > 0 && !stopped && issued >= (uint32_t)SS_MAX_INFLIGHT) {      // copy issued - SS_MAX_INFLIGHT must have landed
+                            const uint32_t o = issued - (uint32_t)SS_MAX_INFLIGHT;
+                            while (!mbar_try_wait(&sm.full[o % kSlots], (o / kSlots) & 1)) { if (sm.stop_req) { stopped = true; break; } }
+                        }
+                        if (!stopped) mbar_expect_tx(&sm.full[slot], SS_NO_STREAM ? 16u : (uint32_t)nrows * seg.row_bytes);
                     }
                     stopped = __shfl_sync(0xffffffffu, (int)stopped, 0) != 0;
                     __syncwarp();
                     if (stopped) break;
-                    if (lane == 0) bulk_g2s(sm.ring[slot], base + (size_t)rbase * seg.row_bytes, (uint32_t)nrows * seg.row_bytes, &sm.full[slot], policy);
+                    if (lane == 0) bulk_g2s(sm.ring[slot], base + (size_t)rbase * seg.row_bytes, SS_NO_STREAM ? 16u : (uint32_t)nrows * seg.row_bytes, &sm.full[slot], policy);
                     issued++;
                 }
             }
@@ -1063,7 +1323,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const Mega
         const uint32_t issued = sm.issued;
         for (uint32_t c = cons; c < issued; c++) mbar_wait(&sm.full[c % kSlots], (c / kSlots) & 1);
         const DecState st = sm.st;
-        if (P.prof) {
+        if (P.prof && SS_MEGA_TRACE) for (int i = 0; i < kProfN; i++) P.prof[(size_t)cta * kTraceN + 600 + i] = sm.prof[i];
+        if (P.prof && !SS_MEGA_TRACE) {
             sm.prof[3] = clock64() - t_begin;
             for (int i = 0; i < kProfN; i++) P.prof[(size_t)cta * kProfN + i] = sm.prof[i];
         }

@@ -171,7 +171,8 @@ Decoder *new_decoder(State &s, bool with_keep) {
     CUDA_CHECK(cudaMemset(b.self_k, 0, kv * 2)); CUDA_CHECK(cudaMemset(b.self_v, 0, kv * 2));
     b.cross_k = s.cross_k; b.cross_v = s.cross_v;
     b.keep = with_keep ? s.keep : nullptr; b.keep_cap = with_keep ? s.keep_cap : 0;
-    b.prof = getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 96) : nullptr;
+    b.prof = getenv("SS_MEGA_TRACE") ? dmalloc<long long>((size_t)s.mega_grid * 1024) : getenv("SS_MEGA_PROF") ? dmalloc<long long>((size_t)s.mega_grid * 96) : nullptr;
+    if (b.prof && getenv("SS_MEGA_TRACE")) CUDA_CHECK(cudaMemset(b.prof, 0, (size_t)s.mega_grid * 1024 * 8));
     b.eot = v.eot; b.sot = v.sot; b.translate = v.translate; b.transcribe = v.transcribe; b.solm = v.solm; b.prev = v.prev;
     b.nosp = v.nosp; b.not_ = v.not_; b.beg = v.beg; b.blank = v.blank;
     b.suppress_blank = 1; b.tdrz = 0; b.tid0_init = -1;
@@ -426,7 +427,11 @@ float bench_decode_steps(State &s, int n_steps, int n_past0) {
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     float total = 0.f; CUDA_CHECK(cudaEventElapsedTime(&total, s.ev[2], s.ev[3]));
     s.n_launches += 1;
-    if (d.mp.prof) {
+    if (d.mp.prof && getenv("SS_MEGA_TRACE")) {      // SS_MEGA_TRACE=1 build of the decode kernel: raw per-CTA timestamps of one step (tools/mega_trace.py)
+        std::vector<long long> h((size_t)s.mega_grid * 1024);
+        CUDA_CHECK(cudaMemcpy(h.data(), d.mp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(getenv("SS_MEGA_TRACE"), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    } else if (d.mp.prof) {
         const int PN = 96;
         std::vector<long long> h((size_t)s.mega_grid * PN);
         CUDA_CHECK(cudaMemcpy(h.data(), d.mp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
