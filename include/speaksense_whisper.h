@@ -69,12 +69,26 @@ int  ss_engine_open(const char *ggml_path, int device, ss_engine **out);
 int  ss_nccl_unique_id(unsigned char out[128]);
 int  ss_engine_open_dist(const char *ggml_path, int device, int rank, int world,
                          const unsigned char nccl_id[128], ss_engine **out);
+/* One process that owns several GPUs (the reference is ONE server process whose context is shared by every
+ * session: src/main.rs:38-39, src/asr/whisper.rs:17,26).  The file is parsed once; the packed arena is uploaded to devices[0]
+ * and broadcast to the other devices with an in-process ncclBroadcast (ncclCommInitAll + one group call) over NVLink.
+ * The engine then holds one immutable weight replica per device; every state is pinned to one of them. */
+int  ss_engine_open_multi(const char *ggml_path, const int *devices, int n_devices, ss_engine **out);
+int  ss_engine_n_devices(const ss_engine *e);
+int  ss_engine_device(const ss_engine *e, int i);          /* CUDA ordinal of replica i, -1 if out of range */
+int  ss_engine_n_states(const ss_engine *e, int i);        /* live states on replica i */
+/* FNV-1a (64 bit) of replica i's weight arena as it sits in HBM: equals ss_model_probe()'s arena_fnv1a when the upload / broadcast
+ * was exact (bench.py checks it on every rank) */
+int  ss_engine_arena_fnv1a(const ss_engine *e, int i, uint64_t *out);
 void ss_engine_close(ss_engine *e);                        /* refcounted: states keep it alive */
 int  ss_engine_info(const ss_engine *e, int *n_vocab, int *n_audio_state, int *n_audio_layer,
                     int *n_text_layer, int *n_mels, int64_t *weight_bytes);
 
 /* == WhisperContext::create_state()                      whisper.rs:30-39 */
-int  ss_state_new(ss_engine *e, ss_state **out);
+int  ss_state_new(ss_engine *e, ss_state **out);            /* multi-device engine: == ss_state_new_on(e, -1, out) */
+/* state on the replica that lives on CUDA device `device`; -1 = the replica with the fewest live states */
+int  ss_state_new_on(ss_engine *e, int device, ss_state **out);
+int  ss_state_device(const ss_state *s);
 void ss_state_free(ss_state *s);
 
 /* == transcribe_with_state up to and including the segment read-back and Rust post-processing

@@ -32,9 +32,16 @@ SYMBOLS = [
     ("ss_engine_open", C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     ("ss_nccl_unique_id", C.c_int, [C.c_char_p]),
     ("ss_engine_open_dist", C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(_P)]),
+    ("ss_engine_open_multi", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    ("ss_engine_n_devices", C.c_int, [_P]),
+    ("ss_engine_device", C.c_int, [_P, C.c_int]),
+    ("ss_engine_n_states", C.c_int, [_P, C.c_int]),
+    ("ss_engine_arena_fnv1a", C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
     ("ss_engine_close", None, [_P]),
     ("ss_engine_info", C.c_int, [_P] + [C.POINTER(C.c_int)] * 5 + [C.POINTER(C.c_int64)]),
     ("ss_state_new", C.c_int, [_P, C.POINTER(_P)]),
+    ("ss_state_new_on", C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    ("ss_state_device", C.c_int, [_P]),
     ("ss_state_free", None, [_P]),
     ("ss_transcribe", C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(SsParams)]),
     ("ss_upload_pcm", C.c_int, [_P, _P, _P, C.c_size_t]),

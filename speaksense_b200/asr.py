@@ -77,12 +77,16 @@ class WhisperState:
     """== Arc<Mutex<Box<WhisperState>>> (whisper.rs:30-39): caller-owned session; the lock serialises
     calls on the same state exactly like the reference's Mutex (whisper.rs:51-54)."""
 
-    def __init__(self, engine: "WhisperAsr"):
+    def __init__(self, engine: "WhisperAsr", device: Optional[int] = None):
         self._engine = engine            # keeps the engine alive (fixes the transmute hazard, whisper.rs:34-36)
         self._lock = threading.Lock()
         h = C.c_void_p()
-        _native.check(_native.lib().ss_state_new(engine._h, C.byref(h)))
+        if device is None:               # multi-device engine: the replica with the fewest live states
+            _native.check(_native.lib().ss_state_new(engine._h, C.byref(h)))
+        else:
+            _native.check(_native.lib().ss_state_new_on(engine._h, device, C.byref(h)))
         self._h = h
+        self.device = _native.lib().ss_state_device(h)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -149,11 +153,18 @@ class AsrEngine(abc.ABC):             # mod.rs:58-73
 
 class WhisperAsr(AsrEngine):          # whisper.rs:16-129
     def __init__(self, model_path: str, device: int = 0, *, rank: int = 0, world_size: int = 1,
-                 nccl_id: Optional[bytes] = None):
+                 nccl_id: Optional[bytes] = None, devices: Optional[Sequence[int]] = None):
+        """device: one GPU (the reference's one context per process, main.rs:38).  devices=[...]: one process that owns
+        several GPUs - the file is parsed once and the arena is broadcast to every listed device inside the process
+        (ss_engine_open_multi); create_state(device=None) then pins each session to the least loaded replica."""
         L = _native.lib()
         h = C.c_void_p()
         path = model_path.encode() if model_path else None
-        if world_size > 1:
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = L.ss_engine_open_multi(path, arr, len(devices), C.byref(h))
+            device = devices[0] if len(devices) else device
+        elif world_size > 1:
             rc = L.ss_engine_open_dist(path, device, rank, world_size, nccl_id, C.byref(h))
         else:
             rc = L.ss_engine_open(path, device, C.byref(h))
@@ -184,8 +195,20 @@ class WhisperAsr(AsrEngine):          # whisper.rs:16-129
         except Exception:
             pass
 
-    def create_state(self) -> WhisperState:
-        return WhisperState(self)
+    def create_state(self, device: Optional[int] = None) -> WhisperState:
+        return WhisperState(self, device)
+
+    @property
+    def devices(self):
+        L = _native.lib()
+        return [L.ss_engine_device(self._h, i) for i in range(L.ss_engine_n_devices(self._h))]
+
+    def arena_fnv1a(self, replica: int = 0) -> int:
+        """FNV-1a of the weight arena as it sits in HBM on replica `replica` (== model_probe()'s checksum if the upload /
+        NCCL broadcast was exact)"""
+        out = C.c_uint64()
+        _native.check(_native.lib().ss_engine_arena_fnv1a(self._h, replica, C.byref(out)))
+        return out.value
 
     @staticmethod
     def _read_result(state: WhisperState) -> TranscribeResult:

@@ -1,6 +1,8 @@
 // api.cc - the C ABI declared in include/speaksense_whisper.h.
 #include <cstring>
+#include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/speaksense_whisper.h"
@@ -8,10 +10,22 @@
 
 using namespace ss;
 
-struct ss_engine { std::shared_ptr<Engine> e; };
+// `e` is replicas[0]; an engine opened with ss_engine_open / ss_engine_open_dist has one replica (one device)
+struct ss_engine {
+    std::shared_ptr<Engine> e;
+    std::vector<std::shared_ptr<Engine>> replicas;
+    explicit ss_engine(std::shared_ptr<Engine> one) : e(one), replicas{one} {}
+    explicit ss_engine(std::vector<std::shared_ptr<Engine>> all) : e(all.at(0)), replicas(std::move(all)) {}
+    bool owns(const ss_state *s) const;
+};
 struct ss_state { State *s; };
 
 static thread_local std::string g_err;
+
+bool ss_engine::owns(const ss_state *s) const {
+    for (const auto &r : replicas) if (s->s->engine.get() == r.get()) return true;
+    return false;
+}
 
 template <typename F>
 static int guard(F &&f) {
@@ -57,6 +71,33 @@ int ss_engine_open(const char *path, int device, ss_engine **out) {
         return 0;
     });
 }
+int ss_engine_open_multi(const char *path, const int *devices, int n_devices, ss_engine **out) {
+    return guard([&]() -> int {
+        if (!path || !out || !devices || n_devices <= 0) SS_THROW(SS_ERR_INVALID, "null argument");
+        *out = new ss_engine{engine_open_multi(path, devices, n_devices)};
+        return 0;
+    });
+}
+int ss_engine_n_devices(const ss_engine *e) { return e ? (int)e->replicas.size() : 0; }
+int ss_engine_device(const ss_engine *e, int i) { return (e && i >= 0 && i < (int)e->replicas.size()) ? e->replicas[i]->device : -1; }
+int ss_engine_n_states(const ss_engine *e, int i) { return (e && i >= 0 && i < (int)e->replicas.size()) ? e->replicas[i]->n_states.load() : -1; }
+int ss_engine_arena_fnv1a(const ss_engine *e, int i, uint64_t *out) {
+    return guard([&]() -> int {
+        if (!e || !out || i < 0 || i >= (int)e->replicas.size()) SS_THROW(SS_ERR_INVALID, "bad argument");
+        const Model &m = e->replicas[i]->model;
+        CUDA_CHECK(cudaSetDevice(m.device));
+        const size_t blk = (size_t)64 << 20;
+        std::vector<unsigned char> buf(std::min(blk, m.arena_bytes));
+        uint64_t h = 1469598103934665603ull;
+        for (size_t off = 0; off < m.arena_bytes; off += blk) {
+            const size_t nb = std::min(blk, m.arena_bytes - off);
+            CUDA_CHECK(cudaMemcpy(buf.data(), m.arena + off, nb, cudaMemcpyDeviceToHost));
+            for (size_t k = 0; k < nb; k++) { h ^= buf[k]; h *= 1099511628211ull; }
+        }
+        *out = h;
+        return 0;
+    });
+}
 int ss_nccl_unique_id(unsigned char out[128]) {
     return guard([&]() -> int { if (!out) SS_THROW(SS_ERR_INVALID, "null argument"); nccl_unique_id(out); return 0; });
 }
@@ -84,16 +125,30 @@ int ss_engine_info(const ss_engine *e, int *n_vocab, int *n_audio_state, int *n_
 int ss_state_new(ss_engine *e, ss_state **out) {
     return guard([&]() -> int {
         if (!e || !out) SS_THROW(SS_ERR_INVALID, "null argument");
-        *out = new ss_state{state_new(e->e)};
+        return ss_state_new_on(e, e->replicas.size() > 1 ? -1 : e->e->device, out);
+    });
+}
+int ss_state_new_on(ss_engine *e, int device, ss_state **out) {
+    return guard([&]() -> int {
+        if (!e || !out) SS_THROW(SS_ERR_INVALID, "null argument");
+        std::shared_ptr<Engine> pick;
+        if (device < 0) {      // least loaded replica (ties: the first in the ss_engine_open_multi order)
+            for (const auto &r : e->replicas) if (!pick || r->n_states.load() < pick->n_states.load()) pick = r;
+        } else {
+            for (const auto &r : e->replicas) if (r->device == device) pick = r;
+            if (!pick) SS_THROW(SS_ERR_INVALID, "engine has no replica on CUDA device %d", device);
+        }
+        *out = new ss_state{state_new(pick)};
         return 0;
     });
 }
+int ss_state_device(const ss_state *s) { return s ? s->s->engine->device : -1; }
 void ss_state_free(ss_state *s) { if (s) { delete s->s; delete s; } }
 
 int ss_transcribe(ss_engine *e, ss_state *s, const float *pcm, size_t n, const ss_params *p) {
     return guard([&]() -> int {
         if (!e || !s || (!pcm && n)) SS_THROW(SS_ERR_INVALID, "null argument");
-        if (s->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
+        if (!e->owns(s)) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
         return transcribe(*s->s, pcm, n, make_params(p), p && p->stream_mode);
     });
 }
@@ -112,7 +167,7 @@ void ss_denoise_config_default(ss_denoise_config *c) {
 int ss_denoise_audio(ss_engine *e, ss_state *s, const float *pcm, size_t n, const ss_denoise_config *cfg, float *out, int *noise_type, float *spectral_variance) {
     return guard([&]() -> int {
         if (!e || !s || !pcm) SS_THROW(SS_ERR_INVALID, "null argument");
-        if (s->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
+        if (!e->owns(s)) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
         ss_denoise_config c; ss_denoise_config_default(&c);
         if (cfg) c = *cfg;
         const int t = denoise_audio(*s->s, pcm, n, c.frame_size, c.overlap, c.strength, out, spectral_variance);
@@ -123,7 +178,7 @@ int ss_denoise_audio(ss_engine *e, ss_state *s, const float *pcm, size_t n, cons
 int ss_denoise_frames(ss_engine *e, ss_state *s, const float *frames, int n_frames, const ss_denoise_config *cfg, float *out) {
     return guard([&]() -> int {
         if (!e || !s || !frames || !out || n_frames < 0) SS_THROW(SS_ERR_INVALID, "null argument");
-        if (s->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
+        if (!e->owns(s)) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
         ss_denoise_config c; ss_denoise_config_default(&c);
         if (cfg) c = *cfg;
         if (!c.enable_noise_reduction) {      // mod.rs:131-133: only the noise gate applies
@@ -153,7 +208,7 @@ int ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *cons
         if (!e || !states || !pcm || !n || batch < 0) SS_THROW(SS_ERR_INVALID, "null argument");
         std::vector<size_t> len(batch);
         for (int i = 0; i < batch; i++) {
-            if (!states[i] || states[i]->s->engine.get() != e->e.get()) SS_THROW(SS_ERR_INVALID, "bad state %d", i);
+            if (!states[i] || !e->owns(states[i])) SS_THROW(SS_ERR_INVALID, "bad state %d", i);
             len[i] = n[i];
             if (!pcm[i]) {      // NULL clip: the state's resident PCM (ss_upload_pcm / ss_denoise_audio), as ss_transcribe_resident
                 if (!states[i]->s->d_pcm) SS_THROW(SS_ERR_INVALID, "clip %d: no resident PCM: call ss_upload_pcm / ss_denoise_audio first", i);
@@ -161,9 +216,32 @@ int ss_transcribe_batch(ss_engine *e, ss_state *const *states, const float *cons
             }
         }
         if (batch_decode_enabled()) {      // one batched decoder step per token for all clips (engine_batch.cc); SS_BATCH_DECODE=0: clip by clip
-            std::vector<State *> st(batch);
-            for (int i = 0; i < batch; i++) st[i] = states[i]->s;
-            return transcribe_batch(st.data(), pcm, len.data(), batch, make_params(p), p && p->stream_mode);
+            // states of a multi-device engine are grouped by the device they live on; the groups run concurrently, one host thread each
+            std::vector<std::vector<int>> groups;
+            for (const auto &r : e->replicas) {
+                std::vector<int> g;
+                for (int i = 0; i < batch; i++) if (states[i]->s->engine.get() == r.get()) g.push_back(i);
+                if (!g.empty()) groups.push_back(std::move(g));
+            }
+            const FullParams fp = make_params(p);
+            const bool sm = p && p->stream_mode;
+            auto run_group = [&](const std::vector<int> &g) -> int {
+                std::vector<State *> st; std::vector<const float *> pc; std::vector<size_t> ln;
+                for (int i : g) { st.push_back(states[i]->s); pc.push_back(pcm[i]); ln.push_back(len[i]); }
+                return transcribe_batch(st.data(), pc.data(), ln.data(), (int)g.size(), fp, sm);
+            };
+            if (groups.size() <= 1) return groups.empty() ? 0 : run_group(groups[0]);
+            std::vector<int> rcs(groups.size(), 0); std::vector<std::string> errs(groups.size());
+            std::vector<std::thread> th;
+            for (size_t k = 0; k < groups.size(); k++)
+                th.emplace_back([&, k]() {
+                    try { rcs[k] = run_group(groups[k]); }
+                    catch (const ss::Error &er) { rcs[k] = er.code; errs[k] = er.what(); }
+                    catch (const std::exception &er) { rcs[k] = SS_ERR_INTERNAL; errs[k] = er.what(); }
+                });
+            for (auto &t : th) t.join();
+            for (size_t k = 0; k < groups.size(); k++) if (rcs[k]) { if (!errs[k].empty()) g_err = errs[k]; return rcs[k]; }
+            return 0;
         }
         int rc = 0;
         for (int i = 0; i < batch; i++) {

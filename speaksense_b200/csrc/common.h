@@ -1,5 +1,6 @@
 // common.h - shared host/device helpers for the speaksense_b200 CUDA engine.
 #pragma once
+#include <atomic>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -40,5 +41,14 @@ constexpr int kChunkSec = 30;
 
 template <typename T>
 static inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// Per-device one-time setup (function attributes, constant tables are per device / context, not per process): `need(dev)` is true
+// until `done(dev)` has been called for that device.  Two threads racing on the first use both run the (idempotent) setup.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};      // devices 0..63
+    bool need(int dev) const { return dev < 0 || dev >= 64 || !((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void done(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+static inline int current_device() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) dev = -1; return dev; }
 
 }  // namespace ss

@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------------
-// beam search (opt-in, SS_BATCH_BEAM=1; written after round 1's GPU budget was spent, NOT yet run): end of a step whose
+// beam search (engine_batch.cc decode_beam_batched; SS_BATCH_BEAM=0 turns it off): end of a step whose
 // sequences are the live beams of one window.  Same filter and statistics as bd_sample_kernel (whisper_process_logits, with
 // the temperature division of the t > 0 rungs), then whisper_sample_token_topk: the k most likely tokens in (log-prob
 // descending, id ascending) order - masked tokens stay at -inf, so a list that runs out of allowed tokens fills up with the

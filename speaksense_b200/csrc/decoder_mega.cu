@@ -376,7 +376,11 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
     }
     // ---- input vector -> f16 operand in shared memory
     if (has_ln) {
+#ifdef SS_EXP_HALF_POLL      // timing experiment (garbage results): the LayerNorm phases poll only half of their input words
+        constexpr int n2 = D >> 2;
+#else
         constexpr int n2 = D >> 1;                                          // flagged pairs
+#endif
         constexpr int NK = (n2 + kConsumerThreads - 1) / kConsumerThreads;   // per thread (<= 3)
         const float *lw = KIND == SEG_LM ? P.lnf_w : P.layer[il].lnw[lidx], *lb = KIND == SEG_LM ? P.lnf_b : P.layer[il].lnb[lidx];
         float2 w2[NK], b2[NK], xv[NK];
@@ -526,13 +530,8 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
                 if (KIND == SEG_QKV) {
                     const int row = row0 + R;
                     if (row < D) ll_store(P.q1 + row, r16(v * s4), ep_out);
-                    else if (row < 2 * D) {
-                        const int n = row - D; const __half hk = __float2half_rn(v * s4);
-                        (P.self_k + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hk; ll_store(P.kcur + n, __half2float(hk), ep_out);
-                    } else {
-                        const int n = row - 2 * D; const __half hv = __float2half_rn(v);
-                        (P.self_v + (size_t)il * P.ctx * D)[((size_t)(n >> 6) * P.ctx + pos) * 64 + (n & 63)] = hv; ll_store(P.vcur + n, __half2float(hv), ep_out);
-                    }
+                    else if (row < 2 * D) ll_store(P.kcur + (row - D), r16(v * s4), ep_out);          // (the head's CTA appends k / v to the self-KV
+                    else ll_store(P.vcur + (row - 2 * D), r16(v), ep_out);                             //  cache itself: see self_attn)
                 } else if (KIND == SEG_O || KIND == SEG_CO) ll_store(outp + kChunkRows * ch, r + v, ep_out);
                 else if (KIND == SEG_CQ) ll_store(outp + kChunkRows * ch, r16(v * s4), ep_out);
                 else if (el == 0) ll_store_h2(P.hbuf + ((row0 + R) >> 1), hid, hid_hi, ep_out);
@@ -756,6 +755,13 @@ __device__ __noinline__ void self_attn_v1(int il, uint32_t ep) {
         if ((tid & 1) == 0) ll_store_h2(P.att1 + h * 32 + (tid >> 1), o, o_hi, ep);
     }
     trace_event(TP_SELF, 1);
+    // KV-cache append by the CTA that will read it: the rows of head h are written and (from the next token on) read by this CTA
+    // only, ordered by program order + CTA barriers - no cross-CTA visibility assumption (the flagged k / v words are f16 values)
+    if (tid < 64) {
+        const int which = tid >> 5, i2 = tid & 31;      // 0: k, 1: v
+        __half *row = (which == 0 ? P.self_k : P.self_v) + (size_t)il * P.ctx * d + ((size_t)h * P.ctx + n_past) * 64;
+        reinterpret_cast<__half2 *>(row)[i2] = __floats2half2_rn(sm.qkv[64 + which * 64 + 2 * i2], sm.qkv[64 + which * 64 + 2 * i2 + 1]);
+    }
     SS_STAGE(SEG_XV, 4)
 }
 
@@ -870,6 +876,13 @@ __device__ __noinline__ void self_attn_online(int il, uint32_t ep) {
     }
     trace_mark(93);      // final merge + store
     trace_event(TP_SELF, 1);
+    // KV-cache append by the CTA that will read it: the rows of head h are written and (from the next token on) read by this CTA
+    // only, ordered by program order + CTA barriers - no cross-CTA visibility assumption (the flagged k / v words are f16 values)
+    if (tid < 64) {
+        const int which = tid >> 5, i2 = tid & 31;      // 0: k, 1: v
+        __half *row = (which == 0 ? P.self_k : P.self_v) + (size_t)il * P.ctx * d + ((size_t)h * P.ctx + n_past) * 64;
+        reinterpret_cast<__half2 *>(row)[i2] = __floats2half2_rn(sm.qkv[64 + which * 64 + 2 * i2], sm.qkv[64 + which * 64 + 2 * i2 + 1]);
+    }
     SS_STAGE(SEG_XV, 4)
 }
 

@@ -199,8 +199,9 @@ void denoise_frames_enqueue(const float *d_in, int n_frames, int fs, float stren
     if (fs < 64 || fs > kDnMaxFrame || (fs & (fs - 1))) SS_THROW(-1, "denoise: frame_size must be a power of two in [64, %d]", kDnMaxFrame);
     if (n_frames <= 0) return;
     int log2fs = 0; while ((1 << log2fs) < fs) log2fs++;
-    static bool attr_done = false;
-    if (!attr_done) { CUDA_CHECK(cudaFuncSetAttribute(dn_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DnSmem))); attr_done = true; }
+    static PerDeviceOnce once;      // (function attributes are per device)
+    const int dev = current_device();
+    if (once.need(dev)) { CUDA_CHECK(cudaFuncSetAttribute(dn_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DnSmem))); once.done(dev); }
     dn_frames_kernel<<<n_frames, kDnThreads, sizeof(DnSmem), st>>>(d_in, fs, log2fs, strength, noise_gate, d_out);
     *launches += 1;
     CUDA_CHECK(cudaGetLastError());
@@ -225,11 +226,12 @@ int denoise_enqueue(const float *d_in, size_t n, int fs, float overlap, float st
     float *power = scratch, *noise = power + (size_t)nf * fs, *signal = noise + fs, *fvar = signal + fs;
     int *d_type = reinterpret_cast<int *>(fvar + nf); float *d_nv = fvar + nf + 1;
     float *frames = fvar + nf + 8, *tmp = frames + (size_t)nov * fs;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;      // (function attributes are per device)
+    const int dev = current_device();
+    if (once.need(dev)) {
         CUDA_CHECK(cudaFuncSetAttribute(dn_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DnSmem)));
         CUDA_CHECK(cudaFuncSetAttribute(dn_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DnSmem)));
-        attr_done = true;
+        once.done(dev);
     }
     auto spectra = [&](const float *src) {
         dn_power_kernel<<<nf, kDnThreads, sizeof(DnSmem), st>>>(src, fs, log2fs, power);

@@ -72,6 +72,9 @@ struct NcclApi {
     int (*CommInitRank)(void **, int, unsigned char[128] /* by value in the real ABI */, int) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 struct NcclId { char internal[128]; };
@@ -88,6 +91,9 @@ NcclApi &nccl() {
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.h, "ncclBroadcast"));
     api.CommDestroy = reinterpret_cast<int (*)(void *)>(dlsym(api.h, "ncclCommDestroy"));
     api.GetErrorString = reinterpret_cast<const char *(*)(int)>(dlsym(api.h, "ncclGetErrorString"));
+    api.CommInitAll = reinterpret_cast<int (*)(void **, int, const int *)>(dlsym(api.h, "ncclCommInitAll"));
+    api.GroupStart = reinterpret_cast<int (*)()>(dlsym(api.h, "ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<int (*)()>(dlsym(api.h, "ncclGroupEnd"));
     if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.CommDestroy) SS_THROW(-8, "libnccl lacks expected symbols");
     return api;
 }
@@ -109,27 +115,80 @@ std::shared_ptr<Engine> engine_open_dist(const char *path, int device, int rank,
     if (world <= 1) { if (!path) SS_THROW(-1, "model path required"); return engine_open(path, device); }
     NcclApi &api = nccl();
     NcclId id; memcpy(id.internal, nccl_id, 128);
-    void *comm = nullptr;
-    NCCL_CHECK(reinterpret_cast<CommInitRankFn>(api.CommInitRank)(&comm, world, id, rank));
-    cudaStream_t st; CUDA_CHECK(cudaStreamCreate(&st));
-    unsigned long long *d_sz = dmalloc<unsigned long long>(1);
+    // rank 0 parses the file BEFORE the rendezvous; a failure there is broadcast as size 0 so that the other ranks return an
+    // error instead of waiting in ncclBroadcast for ever
     std::vector<unsigned char> img;
     unsigned long long sz = 0;
+    std::string load_error;
     if (rank == 0) {
-        if (!path) SS_THROW(-1, "rank 0 needs the model path");
-        img = build_arena_image(path); sz = img.size();
-        CUDA_CHECK(cudaMemcpy(d_sz, &sz, 8, cudaMemcpyHostToDevice));
+        try {
+            if (!path) SS_THROW(-1, "rank 0 needs the model path");
+            img = build_arena_image(path); sz = img.size();
+        } catch (const Error &e) { load_error = e.what(); sz = 0; }
     }
-    NCCL_CHECK(api.Broadcast(d_sz, d_sz, 8, /*ncclUint8*/ 1, 0, comm, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    CUDA_CHECK(cudaMemcpy(&sz, d_sz, 8, cudaMemcpyDeviceToHost));
-    unsigned char *d = dmalloc<unsigned char>(sz);
-    if (rank == 0) CUDA_CHECK(cudaMemcpy(d, img.data(), sz, cudaMemcpyHostToDevice));
-    NCCL_CHECK(api.Broadcast(d, d, sz, 1, 0, comm, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    api.CommDestroy(comm);
-    cudaFree(d_sz); cudaStreamDestroy(st);
-    return finish_open(d, sz, device, path ? path : "<nccl broadcast>");
+    struct Res {      // released on every path
+        NcclApi &api; void *comm = nullptr; cudaStream_t st = nullptr; unsigned long long *d_sz = nullptr; unsigned char *d = nullptr;
+        ~Res() { if (comm) api.CommDestroy(comm); if (d_sz) cudaFree(d_sz); if (st) cudaStreamDestroy(st); if (d) cudaFree(d); }
+    } r{api};
+    NCCL_CHECK(reinterpret_cast<CommInitRankFn>(api.CommInitRank)(&r.comm, world, id, rank));
+    CUDA_CHECK(cudaStreamCreate(&r.st));
+    r.d_sz = dmalloc<unsigned long long>(1);
+    if (rank == 0) CUDA_CHECK(cudaMemcpy(r.d_sz, &sz, 8, cudaMemcpyHostToDevice));
+    NCCL_CHECK(api.Broadcast(r.d_sz, r.d_sz, 8, /*ncclUint8*/ 1, 0, r.comm, r.st));
+    CUDA_CHECK(cudaStreamSynchronize(r.st));
+    CUDA_CHECK(cudaMemcpy(&sz, r.d_sz, 8, cudaMemcpyDeviceToHost));
+    if (sz == 0) SS_THROW(-2, "rank 0 could not load the model%s%s", load_error.empty() ? "" : ": ", load_error.c_str());
+    r.d = dmalloc<unsigned char>(sz);
+    if (rank == 0) CUDA_CHECK(cudaMemcpy(r.d, img.data(), sz, cudaMemcpyHostToDevice));
+    NCCL_CHECK(api.Broadcast(r.d, r.d, sz, 1, 0, r.comm, r.st));
+    CUDA_CHECK(cudaStreamSynchronize(r.st));
+    unsigned char *arena = r.d; r.d = nullptr;      // ownership moves to the engine
+    return finish_open(arena, sz, device, path ? path : "<nccl broadcast>");
+}
+
+std::vector<std::shared_ptr<Engine>> engine_open_multi(const std::string &path, const int *devices, int n) {
+    if (!devices || n <= 0) SS_THROW(-1, "engine_open_multi: no devices");
+    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) if (devices[i] == devices[j]) SS_THROW(-1, "engine_open_multi: device %d listed twice", devices[i]);
+    std::vector<std::shared_ptr<Engine>> out;
+    if (n == 1) { out.push_back(engine_open(path, devices[0])); return out; }
+    for (int i = 0; i < n; i++) check_device(devices[i]);
+    const std::vector<unsigned char> img = build_arena_image(path);
+    const size_t sz = img.size();
+    NcclApi &api = nccl();
+    if (!api.CommInitAll || !api.GroupStart || !api.GroupEnd) SS_THROW(-8, "libnccl lacks ncclCommInitAll / ncclGroupStart / ncclGroupEnd");
+    struct Res {
+        NcclApi &api; std::vector<void *> comm; std::vector<cudaStream_t> st; std::vector<unsigned char *> d; std::vector<int> dev;
+        ~Res() {
+            for (size_t i = 0; i < dev.size(); i++) {
+                cudaSetDevice(dev[i]);
+                if (i < comm.size() && comm[i]) api.CommDestroy(comm[i]);
+                if (i < st.size() && st[i]) cudaStreamDestroy(st[i]);
+                if (i < d.size() && d[i]) cudaFree(d[i]);
+            }
+        }
+    } r{api};
+    r.dev.assign(devices, devices + n); r.comm.assign(n, nullptr); r.st.assign(n, nullptr); r.d.assign(n, nullptr);
+    for (int i = 0; i < n; i++) {
+        CUDA_CHECK(cudaSetDevice(devices[i]));
+        r.d[i] = dmalloc<unsigned char>(sz);
+        CUDA_CHECK(cudaStreamCreate(&r.st[i]));
+    }
+    CUDA_CHECK(cudaSetDevice(devices[0]));
+    CUDA_CHECK(cudaMemcpy(r.d[0], img.data(), sz, cudaMemcpyHostToDevice));
+    NCCL_CHECK(api.CommInitAll(r.comm.data(), n, devices));
+    NCCL_CHECK(api.GroupStart());
+    for (int i = 0; i < n; i++) {
+        CUDA_CHECK(cudaSetDevice(devices[i]));
+        NCCL_CHECK(api.Broadcast(r.d[i], r.d[i], sz, /*ncclUint8*/ 1, 0, r.comm[i], r.st[i]));
+    }
+    NCCL_CHECK(api.GroupEnd());
+    for (int i = 0; i < n; i++) { CUDA_CHECK(cudaSetDevice(devices[i])); CUDA_CHECK(cudaStreamSynchronize(r.st[i])); }
+    for (int i = 0; i < n; i++) {
+        CUDA_CHECK(cudaSetDevice(devices[i]));
+        unsigned char *arena = r.d[i]; r.d[i] = nullptr;
+        out.push_back(finish_open(arena, sz, devices[i], path));
+    }
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,6 +247,7 @@ State *state_new(const std::shared_ptr<Engine> &e) {
     CUDA_CHECK(cudaSetDevice(e->device));
     auto s = std::make_unique<State>();
     s->engine = e;
+    e->n_states.fetch_add(1);
     const HParams &hp = e->model.hp;
     const size_t T = hp.n_audio_ctx, d = hp.n_audio_state, dd = hp.n_text_state;
     CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -210,6 +270,7 @@ State *state_new(const std::shared_ptr<Engine> &e) {
 
 State::~State() {
     if (!engine) return;
+    engine->n_states.fetch_sub(1);
     cudaSetDevice(engine->device);
     if (stream) cudaStreamSynchronize(stream);
     for (auto &d : dec) {
@@ -759,7 +820,7 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
                     s.n_keep += nk;
                 }
             } else if (beam && batch_beam_enabled() && batch_beam_supported(s)) {
-                // ------- opt-in (SS_BATCH_BEAM=1): the live beams as sequences of one batched decoder step (engine_batch.cc) -------
+                // ------- default (SS_BATCH_BEAM=0: off): the live beams as sequences of one batched decoder step (engine_batch.cc) -------
                 decode_beam_batched(s, P, t_cur, n_cur, prompt, seek, seek_end, n_max, tid0_init);
             } else {
                 // ------- t > 0: best_of sampled decoders; beam search at any temperature: host-side sampling -------

@@ -1,6 +1,7 @@
 // engine.h - host side of the engine: sessions (ss_state), KV caches, the whisper_full decode loop,
 // segment assembly and the reference's Rust-side post-processing.
 #pragma once
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <random>
@@ -15,6 +16,7 @@ struct Engine {
     Model model;
     int device = 0;
     std::string path;
+    std::atomic<int> n_states{0};      // live sessions on this device (ss_state_new_on(e, -1) picks the least loaded replica)
     // operand buffers of the batched decoder (engine_batch.cc): one batch at a time per engine
     std::mutex batch_mu;
     void *batch_scratch = nullptr;
@@ -22,10 +24,10 @@ struct Engine {
     cudaEvent_t batch_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0, 1: termination polls; 2, 3: timing
     int *batch_h_flags = nullptr;                                     // pinned [2]: finished-sequence counts read back by the polls
     int sms = 0;
-    // activations of the batched encoder pass (opt-in, SS_BATCH_ENCODER=1): [clips * n_audio_ctx] rows
+    // activations of the batched encoder pass (SS_BATCH_ENCODER, on by default): [clips * n_audio_ctx] rows
     void *enc_scratch = nullptr;
     cudaEvent_t enc_ev[3] = {nullptr, nullptr, nullptr};              // start / end of the pass (timing), done (other streams wait on it)
-    // candidates of a batched beam-search step (opt-in, SS_BATCH_BEAM=1): device / pinned [kMaxBatch][8]
+    // candidates of a batched beam-search step (SS_BATCH_BEAM, on by default): device / pinned [kMaxBatch][8]
     TokData *beam_cand = nullptr, *beam_h_cand = nullptr;
     ~Engine();
 };
@@ -98,6 +100,9 @@ struct State {
 
 std::shared_ptr<Engine> engine_open(const std::string &path, int device);
 std::shared_ptr<Engine> engine_open_dist(const char *path, int device, int rank, int world, const unsigned char *nccl_id);
+// one process, several GPUs (the reference is ONE server process: main.rs:38-39): the file is parsed once, the arena goes to
+// devices[0] and from there to the others with an in-process ncclBroadcast (ncclCommInitAll + group call) over NVLink
+std::vector<std::shared_ptr<Engine>> engine_open_multi(const std::string &path, const int *devices, int n_devices);
 void nccl_unique_id(unsigned char out[128]);
 State *state_new(const std::shared_ptr<Engine> &e);
 

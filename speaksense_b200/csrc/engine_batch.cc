@@ -204,14 +204,15 @@ int emit_window(State &s, const FullParams &P, const Common &C, const ClipRun &r
     return seek_delta;
 }
 
-// ---- batched encoder pass (opt-in: SS_BATCH_ENCODER=1; written after the round's GPU budget was spent, NOT yet run) ----
+// ---- batched encoder pass (default; SS_BATCH_ENCODER=0 turns it off) ----
 // The windows of all clips of a round as ONE pass over [clips * 1500] rows: the conv stem and the cross-KV projection stay
 // per clip (their operands live in each State), the 32 layers run once with M = clips * 1500 - the N = 1280 GEMMs, 120 tiles
 // on 148 SMs for one clip, become 375 * clips tiles - and the fused attention kernel takes the clip as its outer batch.
-// By default the clips' encoders run concurrently on their own streams (run_encode), which is what round 1 measured.
+// SS_BATCH_ENCODER=0: the clips' encoders run concurrently on their own streams (run_encode) - round 1's path; measured on
+// 32 x 30 s clips (profiles/r2a_batch_bench*.json): log-mel + encoders 157 ms per clip stream -> 131 ms batched.
 bool batch_encoder_enabled() {
     const char *e = getenv("SS_BATCH_ENCODER");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 struct EncBuf { float *x, *enc_out; __half *xn, *qkv, *att, *ff, *enc16; };
@@ -394,8 +395,8 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// beam search on the batched step (opt-in: SS_BATCH_BEAM=1; written after the round's GPU budget was spent, NOT yet run).
-// The default beam path (engine.cc) launches the batch-1 kernel once per live beam and token and filters / sorts 51 866
+// beam search on the batched step (default; SS_BATCH_BEAM=0 turns it off).
+// The SS_BATCH_BEAM=0 path (engine.cc) launches the batch-1 kernel once per live beam and token and filters / sorts 51 866
 // logits per beam on the host; here the live beams of the window are the sequences of ONE batched step (they share the
 // state's cross-KV cache, each decoder keeps its own self-KV cache and control block) and bd_topk_kernel leaves k
 // candidates per beam.  Candidate ranking, duplicate skipping, the self-KV shuffle (beam_advance) and the per-token
@@ -403,7 +404,7 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
 // ------------------------------------------------------------------------------------------------
 bool batch_beam_enabled() {
     const char *e = getenv("SS_BATCH_BEAM");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 bool batch_beam_supported(const State &s) {
     const HParams &hp = s.engine->model.hp;

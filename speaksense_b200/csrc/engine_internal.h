@@ -20,7 +20,7 @@ void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos);
 struct BeamCandidate { int decoder_idx, seek_delta; bool has_ts; Sequence seq; };
 std::vector<TokData> sample_topk_host(const Model &m, const Decoder &dc, int k);
 void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i, int n_past);
-// opt-in (SS_BATCH_BEAM=1): one window's beam search with the live beams as sequences of one batched decoder step
+// (SS_BATCH_BEAM, on by default): one window's beam search with the live beams as sequences of one batched decoder step
 bool batch_beam_enabled();
 bool batch_beam_supported(const State &s);
 void decode_beam_batched(State &s, const FullParams &P, float t_cur, int n_cur, const std::vector<int> &prompt, int seek, int seek_end,

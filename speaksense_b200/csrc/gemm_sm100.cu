@@ -241,15 +241,21 @@ void make_map(CUtensorMap *map, const GemmOperand &op, long inner, long rows, in
     if (rc != CUDA_SUCCESS) SS_THROW(-4, "cuTensorMapEncodeTiled failed with %d (inner %ld rows %ld ld %ld)", (int)rc, inner, rows, op.ld);
 }
 
-int g_sms = 0;
+// per device (one process may own several GPUs): SM count, and the > 48 KB dynamic shared memory opt-in of every instantiation
+int g_sms_tab[64] = {0};
+PerDeviceOnce g_gemm_ready;
+thread_local int t_sms = 0;      // SM count of the device gemm_enqueue is launching on
+
+template <int BN, int kStages, int EPI>
+void configure_one() {
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kStages, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, kStages>()));
+}
+template <int EPI>
+void configure_epi() { configure_one<128, 4, EPI>(); configure_one<256, 4, EPI>(); }
 
 template <int BN, int kStages, int EPI>
 void launch(const GemmOperand &A, const GemmOperand &B, const GemmDev &p, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, kStages, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN, kStages>()));
-        configured = true;
-    }
+    const int g_sms = t_sms;
     CUtensorMap ta, tb;
     make_map(&ta, A, p.K, A.rows, BK, BM);
     make_map(&tb, B, p.K, B.rows, BK, BN);
@@ -279,7 +285,13 @@ void gemm_init() {
     }
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
-    CUDA_CHECK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!g_gemm_ready.need(dev)) return;
+    int sms = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    configure_epi<EPI_F16_HEADMAJOR>(); configure_epi<EPI_F16_BIAS_GELU>(); configure_epi<EPI_F16_BIAS>();
+    configure_epi<EPI_F32_RESID>(); configure_epi<EPI_F32_GELU_POS>(); configure_epi<EPI_F32_PLAIN>();
+    if (dev >= 0 && dev < 64) g_sms_tab[dev] = sms;
+    g_gemm_ready.done(dev);
 }
 
 void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int K, bool b_mn_major, const GemmEpilogue &ep,
@@ -295,7 +307,10 @@ void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int 
     if (!p.a_bcast && (A.batch0 != B.batch0 || A.batch1 != B.batch1)) SS_THROW(-9, "GEMM batch mismatch");
     p.nb0 = (int)B.batch0; p.nbatch = (int)(B.batch0 * B.batch1);
     if (b_mn_major) SS_THROW(-1, "MN-major B is only supported inside the fused attention kernel");
-    if (!g_sms) gemm_init();
+    const int dev = current_device();
+    if (dev < 0 || dev >= 64) SS_THROW(-3, "GEMM on CUDA device %d: only devices 0..63 are supported", dev);
+    if (g_gemm_ready.need(dev)) gemm_init();
+    const int g_sms = t_sms = g_sms_tab[dev];
     // tile width: rounds of the persistent grid x relative tile cost (a 128x256 tile costs ~1.6x a 128x128 one)
     const long t128 = (long)ceil_div(N, 128) * ceil_div(M, BM) * p.nbatch, t256 = (long)ceil_div(N, 256) * ceil_div(M, BM) * p.nbatch;
     const double c128 = (double)ceil_div<long>(t128, g_sms), c256 = 1.6 * (double)ceil_div<long>(t256, g_sms);

@@ -14,7 +14,7 @@
 namespace ss {
 
 __constant__ float2 c_twiddle[kNFft];    // {cos, sin}(2 pi i / 400), computed on the host like the reference
-static bool g_twiddle_ready[64] = {false};
+static PerDeviceOnce g_twiddle_ready;      // (__constant__ tables are per device)
 
 constexpr int kFramesPerCta = 16;
 constexpr int kXsPitch = 16;
@@ -149,14 +149,14 @@ __global__ void __launch_bounds__(256) mel_window_kernel(const float *__restrict
 }
 
 static void ensure_twiddles(int device) {
-    if (device >= 0 && device < 64 && g_twiddle_ready[device]) return;
+    if (!g_twiddle_ready.need(device)) return;
     float2 h[kNFft];
     for (int i = 0; i < kNFft; i++) {
         const double theta = (2.0 * M_PI * i) / kNFft;
         h[i].x = cosf((float)theta); h[i].y = sinf((float)theta);
     }
     CUDA_CHECK(cudaMemcpyToSymbol(c_twiddle, h, sizeof h));
-    if (device >= 0 && device < 64) g_twiddle_ready[device] = true;
+    g_twiddle_ready.done(device);
 }
 
 void mel_enqueue(const Model &m, const float *d_pcm, size_t n_samples, float *d_mel, int n_len, int *d_max_bits,

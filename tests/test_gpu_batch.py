@@ -167,44 +167,41 @@ def test_batch_matches_oracle_directly(batch_on, oracle_mod, tiny_en_peaked, aud
     eng.close()
 
 
-@pytest.mark.skipif(os.environ.get("SS_TEST_BATCH_ENCODER") != "1",
-                    reason="batched encoder pass (SS_BATCH_ENCODER=1) was written after the round's GPU budget was spent and is off by "
-                           "default: set SS_TEST_BATCH_ENCODER=1 to run it")
 @pytest.mark.parametrize("shape,lang,n_clips", [("tiny.en", None, 5), ("large-v3-l2", "en", 3)])
 def test_batched_encoder_pass_equals_per_clip_encoders(batch_on, shape, lang, n_clips):
-    """SS_BATCH_ENCODER=1: the windows of all clips as one encoder pass over [clips * 1500] rows - same tokens and segments"""
+    """the windows of all clips as one encoder pass over [clips * 1500] rows (default) - same tokens and segments as the clip by
+    clip reference AND as the per-clip encoders on their own streams (SS_BATCH_ENCODER=0)"""
     from tests.conftest import model_path
     from speaksense_b200 import AsrParams, WhisperAsr, synth
     eng = WhisperAsr(model_path(shape, "peaked", 0))
     clips = [synth.synth_audio(seed=1234 + i) for i in range(n_clips)] + [synth.synth_audio(45 * 16000, seed=11)]
     p = AsrParams(language=lang, stream_mode=True)
     ref = _single(eng, clips, p)
-    os.environ["SS_BATCH_ENCODER"] = "1"
+    got, _ = _batched(eng, clips, p)
+    os.environ["SS_BATCH_ENCODER"] = "0"
     try:
-        got, _ = _batched(eng, clips, p)
+        got_off, _ = _batched(eng, clips, p)
     finally:
         os.environ.pop("SS_BATCH_ENCODER", None)
-    for g, r in zip(got, ref):
+    for g, o, r in zip(got, got_off, ref):
         assert g[1] == r[1] and g[2] == r[2] and g[0] == r[0]
+        assert o[1] == r[1] and o[2] == r[2] and o[0] == r[0]
     eng.close()
 
 
-@pytest.mark.skipif(os.environ.get("SS_TEST_BATCH_BEAM") != "1",
-                    reason="beam search on the batched step (SS_BATCH_BEAM=1) was written after the round's GPU budget was spent and is "
-                           "off by default: set SS_TEST_BATCH_BEAM=1 to run it")
 @pytest.mark.parametrize("fixture,lang,beam", [("tiny_en_peaked", None, 5), ("micro_v3_peaked", "zh", 5), ("tiny_en_peaked", None, 2),
                                                 ("micro_v3_random", "zh", 3)])
 def test_beam_on_batched_step_equals_default_beam(request, audio30, fixture, lang, beam):
-    """SS_BATCH_BEAM=1: the live beams as sequences of one batched step, k candidates per beam selected on the device - same
-    tokens, segments and fallback count as the default beam path (one batch-1 launch per beam and token, host top-k), which
-    tests/test_gpu_transcribe.py holds to the oracle"""
+    """the live beams as sequences of one batched step, k candidates per beam selected on the device (default) - same tokens,
+    segments and fallback count as the host-stepped beam path (SS_BATCH_BEAM=0: one batch-1 launch per beam and token, host
+    top-k); tests/test_gpu_transcribe.py holds both to the oracle"""
     from speaksense_b200 import AsrParams, WhisperAsr
     eng = WhisperAsr(request.getfixturevalue(fixture))
     p = AsrParams(language=lang, stream_mode=True, beam_size=beam)
-    ref = _single(eng, [audio30], p)[0]
-    os.environ["SS_BATCH_BEAM"] = "1"
+    got = _single(eng, [audio30], p)[0]
+    os.environ["SS_BATCH_BEAM"] = "0"
     try:
-        got = _single(eng, [audio30], p)[0]
+        ref = _single(eng, [audio30], p)[0]
     finally:
         os.environ.pop("SS_BATCH_BEAM", None)
     assert got[1] == ref[1] and got[2] == ref[2] and got[3] == ref[3] and got[0] == ref[0]
