@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "real-time factor (audio-sec/wall-sec) large-v3 30s clip"
 UNIT = "x realtime (audio s / wall s)"
 CLIP_SEC = 30.0
-NCU_DRAM_BYTES_PER_TOKEN = (29.549974e9 + 6.441216e6) / 16   # ncu --set full capture of one 16-step launch (profiles/r1b_ncu_decode_mega.txt)
+NCU_PROFILE = os.path.join(ROOT, "profiles", "r2_ncu_decode_mega.json")   # written by tools/ncu_summary.py from the --set full capture
 MODEL_DIR = os.environ.get("SS_MODEL_DIR", "/tmp/ss_models")
 
 
@@ -112,6 +112,46 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak():
+    """sustained bf16 peak: the encoder is timed inside a long step (B200_PROFILING.md)"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+
+
+def encoder_flops_per_window(info) -> float:
+    """Algorithmic FLOPs of one 30 s window through conv stem + encoder layers + cross-KV projection (SURVEY.md §8d:
+    2.5883 TFLOP for large-v3)."""
+    d, L, Ld, T, nm = info["n_audio_state"], info["n_audio_layer"], info["n_text_layer"], 1500, info["n_mels"]
+    conv = 2.0 * (2 * T) * d * (3 * nm) + 2.0 * T * d * (3 * d)
+    proj = 2.0 * T * d * d * 4
+    attn = 2.0 * 2 * T * T * d
+    mlp = 2.0 * 2 * T * d * 4 * d
+    cross = 2.0 * T * d * 2 * d * Ld
+    return conv + L * (proj + attn + mlp) + cross
+
+
+def src_sha16(rel: str) -> str:
+    import hashlib
+    return hashlib.sha256(open(os.path.join(ROOT, rel), "rb").read()).hexdigest()[:16]
+
+
+def measured_traffic(shape: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per decode step from the committed `ncu --set full` capture of the decode
+    kernel.  ncu cannot run inside the timed bench, so the capture names the sha of the kernel source it was taken from;
+    a capture of another build is reported as null."""
+    try:
+        j = json.load(open(NCU_PROFILE))
+        cur = src_sha16("speaksense_b200/csrc/decoder_mega.cu")
+        ok = j.get("kernel_src_sha16") == cur and j.get("shape") == shape
+        return (j["dram_bytes_per_step"] if ok else None), {"file": os.path.relpath(NCU_PROFILE, ROOT), "capture_src_sha16": j.get("kernel_src_sha16"),
+                                                            "current_src_sha16": cur, "same_build": ok}
+    except Exception as ex:   # noqa: BLE001
+        return None, {"error": str(ex)[:120]}
+
+
 def cpu_port_run(path: str, pcm, language, n_threads: int):
     """One whole-clip pass of the CPU restatement (oracle); returns (seconds, result dict)."""
     from oracle import oracle
@@ -149,8 +189,8 @@ def run_reference(args, rank, world):
     sample = "whole 30 s clip, full path (mel+encoder+%d decoded tokens), %d of %d requested steps" % (
         r["n_decoded"], n_run, args.steps)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rtf, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "steps_run": n_run, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": rtf, "unit": UNIT, "n_gpus": args.gpus, "steps": n_run,
+        "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 weights / f32 accumulate", "data": "synthetic",
         "config": {"workload": "ggml-%s (synthetic, peaked), one 30 s 16 kHz clip, greedy, CPU restatement of "
                                "whisper.cpp (NOT whisper.cpp itself: un-vendored crates.io dependency)" % shape},
@@ -260,12 +300,20 @@ def main():
     bytes_tok = decode_bytes_per_token(info, (n_probe - 1) / 2.0)
     peak, peak_src = peaks()
     achieved = bytes_tok / (step_ms * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(args.shape)
     roofline = {"bound": "hbm", "kernel": "decode_mega_kernel (persistent cooperative kernel; per-token time of one %d-step launch)" % n_probe,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 16-step launch / 16 (profiles/r1b_ncu_decode_mega.txt)
-                "traffic": NCU_DRAM_BYTES_PER_TOKEN if args.shape == "large-v3" else None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_tok, "launch_ms": step_ms,
                 "decode_share_of_step": stage["decode_ms"] / max(ms_total, 1e-9)}
+
+    tpeak, tpeak_src = tensor_peak()
+    enc_flops = encoder_flops_per_window(info)
+    enc_ms = stage["encoder_ms"] / max(args.steps * max(stats["n_windows"], 1), 1)
+    roofline_encoder = {"bound": "tensor", "kernels": "gemm_tcgen05_kernel<*> + attention_tcgen05_kernel + layernorm (conv stem, encoder layers, cross-KV)",
+                        "flops_per_window": enc_flops, "ms_per_window": enc_ms, "achieved": enc_flops / (enc_ms * 1e-3) / 1e12 if enc_ms > 0 else None,
+                        "peak": tpeak, "unit": "TFLOP/s", "frac": (enc_flops / (enc_ms * 1e-3) / 1e12 / tpeak) if enc_ms > 0 else None,
+                        "peak_source": tpeak_src}
 
     # ---------------- denoise of one 5 s stream chunk (the gRPC handler's shape), host buffer in,
     #                  denoised chunk left resident for the transcribe that follows ----------------
@@ -282,6 +330,55 @@ def main():
               "gpu_ms_per_chunk_e2e": (time.perf_counter() - t0) / 20 * 1e3, "noise_type": ntype,
               "h2d_bytes": int(chunk.size * 4), "note": "latency-bound (320 KB chunk); includes H2D, one 8-byte D2H for the noise type, stream sync"}
 
+    # ---------------- multi-GPU row (BASELINE configs[3]): 256 clips, contiguous shards of 256 / N per rank through
+    #                  ss_transcribe_batch (batched decoder step), no data-path collective; results gathered as host strings ----------------
+    dp = None
+    if world > 1 and not os.environ.get("SS_BENCH_NO_DP256"):
+        from speaksense_b200 import dp as dpmod
+        n_total = int(os.environ.get("SS_BENCH_DP_CLIPS", "256"))
+        lo, hi = dpmod.shard_bounds(n_total, rank, world)
+        mine = dpmod.shard(list(range(n_total)), rank, world)
+        clips = [synth.synth_audio(seed=1234 + i) for i in mine]
+        sts = [eng.create_state() for _ in clips]
+        eng.transcribe_batch(sts, clips, params)                      # warm-up pass
+        sync_all()
+        t0 = time.perf_counter()
+        res = eng.transcribe_batch(sts, clips, params)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        local = [(i, r.full_text, len(st.result_tokens()[0]), st.stats()["n_fallbacks"]) for i, r, st in zip(mine, res, sts)]
+        allr = dpmod.gather_results(local, dst=0)
+        # every rank's broadcast arena against rank 0's (FNV-1a of the bytes in HBM) and against the host packer's image
+        fnvs = [None] * world
+        dist.all_gather_object(fnvs, eng.arena_fnv1a(0))
+        # one rank != 0 checks its own headline clip against the CPU oracle (rank 0 does so in cpu_baseline)
+        oracle_ok = None
+        if rank == 1 and not args.no_cpu_baseline:
+            try:
+                _, rr = cpu_port_run(path, pcm, lang, min(16, os.cpu_count() or 1))
+                oracle_ok = rr["tokens"] == toks
+            except Exception as ex:   # noqa: BLE001
+                oracle_ok = "failed: %s" % str(ex)[:80]
+        oks = [None] * world
+        dist.all_gather_object(oks, oracle_ok)
+        for st in sts:
+            st.close()
+        if rank == 0:
+            import ctypes as C
+            from speaksense_b200 import _native
+            probe = C.c_uint64()
+            _native.check(_native.lib().ss_model_probe(path.encode(), None, None, C.byref(probe), None, None, None))
+            per_rank = [sum(x[2] for x in allr if dpmod.shard_bounds(n_total, r, world)[0] <= x[0] < dpmod.shard_bounds(n_total, r, world)[1])
+                        for r in range(world)]
+            dp = {"workload": "BASELINE configs[3]: %d x 30 s clips (seed 1234+i), contiguous shards of %d per rank, ss_transcribe_batch "
+                              "(batched decoder step), host buffers, weights NCCL-broadcast at init" % (n_total, hi - lo),
+                  "rtf": n_total * CLIP_SEC / float(dt.item()), "wall_s_max_over_ranks": float(dt.item()), "clips": len(allr),
+                  "tokens_per_rank": per_rank, "n_fallbacks": sum(x[3] for x in allr),
+                  "transcripts_in_clip_order": [x[0] for x in allr] == list(range(n_total)) and all(x[1] for x in allr),
+                  "arena_fnv1a_equal_on_all_ranks": len(set(fnvs)) == 1, "arena_fnv1a_equals_host_image": fnvs[0] == probe.value,
+                  "rank1_tokens_match_oracle": oks[1] if world > 1 else None}
+
     if rank == 0:
         value = world * args.steps * CLIP_SEC / (ms_total * 1e-3)
         e2e = world * args.steps * CLIP_SEC / (ms_e2e * 1e-3)
@@ -297,7 +394,7 @@ def main():
                     "d2h_bytes_per_step": int(len(toks) * 24 + 80), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-            "roofline": roofline, "clocks": clocks,
+            "roofline": roofline, "roofline_encoder": roofline_encoder, "clocks": clocks,
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -319,6 +416,8 @@ def main():
             except Exception:   # noqa: BLE001
                 pass
         line["next_rows"] = {"f1_denoise": f1}
+        if dp is not None:
+            line["next_rows"]["dp256"] = dp
         if world == 1 and not os.environ.get("SS_BENCH_NO_BATCH"):
             # BASELINE configs[2] beside the headline (informational; the headline stays configs[1]): 32 x 30 s clips through
             # ss_transcribe_batch (batched decoder step, csrc/decoder_batch.cu) in a child process - a failure there cannot
