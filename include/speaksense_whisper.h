@@ -89,6 +89,10 @@ int  ss_state_new(ss_engine *e, ss_state **out);            /* multi-device engi
 /* state on the replica that lives on CUDA device `device`; -1 = the replica with the fewest live states */
 int  ss_state_new_on(ss_engine *e, int device, ss_state **out);
 int  ss_state_device(const ss_state *s);
+/* outcome of the last transcribe on this state: 0 or the negative ss_status; a batch call fails clip by clip (the read-back of one
+ * clip failing - whisper.rs:85 - leaves the other clips' results in place) */
+int  ss_state_status(const ss_state *s);
+const char *ss_state_error(const ss_state *s);
 void ss_state_free(ss_state *s);
 
 /* == transcribe_with_state up to and including the segment read-back and Rust post-processing

@@ -42,6 +42,8 @@ SYMBOLS = [
     ("ss_state_new", C.c_int, [_P, C.POINTER(_P)]),
     ("ss_state_new_on", C.c_int, [_P, C.c_int, C.POINTER(_P)]),
     ("ss_state_device", C.c_int, [_P]),
+    ("ss_state_status", C.c_int, [_P]),
+    ("ss_state_error", C.c_char_p, [_P]),
     ("ss_state_free", None, [_P]),
     ("ss_transcribe", C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(SsParams)]),
     ("ss_upload_pcm", C.c_int, [_P, _P, _P, C.c_size_t]),

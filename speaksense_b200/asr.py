@@ -240,9 +240,12 @@ class WhisperAsr(AsrEngine):          # whisper.rs:16-129
         _native.check(_native.lib().ss_bench_decode_steps(self._h, state._h, n_steps, n_past0, C.byref(ms)))
         return ms.value
 
-    def transcribe_batch(self, states: Sequence[WhisperState], audios: Sequence[Optional[np.ndarray]], params: AsrParams):
+    def transcribe_batch(self, states: Sequence[WhisperState], audios: Sequence[Optional[np.ndarray]], params: AsrParams,
+                         return_exceptions: bool = False):
         """Data-parallel batch inside one GPU (BASELINE configs 3/4): result i belongs to audios[i].  audios[i] = None
-        takes the PCM resident on states[i] (upload_pcm / denoise_audio), like transcribe_resident."""
+        takes the PCM resident on states[i] (upload_pcm / denoise_audio), like transcribe_resident.  A clip whose read-back fails
+        (whisper.rs:85) fails alone: with return_exceptions its slot holds the NativeError and the other slots their results;
+        without, the first error is raised."""
         n = len(states)
         pcms = [None if a is None else np.ascontiguousarray(a, dtype=np.float32) for a in audios]
         sp = (C.c_void_p * n)(*[s._h for s in states])
@@ -253,8 +256,15 @@ class WhisperAsr(AsrEngine):          # whisper.rs:16-129
         for _, lk in locks:
             lk.acquire()
         try:
-            _native.check(_native.lib().ss_transcribe_batch(self._h, sp, pp, ns, n, C.byref(p)))
-            return [self._read_result(s) for s in states]
+            L = _native.lib()
+            rc = L.ss_transcribe_batch(self._h, sp, pp, ns, n, C.byref(p))
+            if rc == 0:
+                return [self._read_result(s) for s in states]
+            per = [L.ss_state_status(s._h) for s in states]
+            if not return_exceptions or not any(per):      # (no per-clip status: the call failed as a whole)
+                _native.check(rc)
+            return [NativeError(c, L.ss_state_error(s._h).decode("utf-8", "replace")) if c else self._read_result(s)
+                    for c, s in zip(per, states)]
         finally:
             for _, lk in reversed(locks):
                 lk.release()

@@ -50,6 +50,8 @@ class BatchingEngine(AsrEngine):
         self.max_seen = 0
         self._q: "queue.Queue[Optional[_Request]]" = queue.Queue()
         self._closed = False
+        self._broken: Optional[BaseException] = None      # the worker died: every later call fails with this
+        self._mu = threading.Lock()                        # orders _submit's enqueue against close()'s sentinel
         self._thread = threading.Thread(target=self._run, name="ss-batching", daemon=True)
         self._thread.start()
 
@@ -71,20 +73,36 @@ class BatchingEngine(AsrEngine):
         return self._submit(state, None, params)
 
     def close(self, close_engine: bool = False):
-        if not self._closed:
+        with self._mu:
+            first = not self._closed
             self._closed = True
-            self._q.put(None)
+            if first:
+                self._q.put(None)      # nothing can be enqueued behind the sentinel: _submit checks _closed under the same lock
+        if first:
             self._thread.join()
+            self._fail_queued(RuntimeError("BatchingEngine is closed"))
         if close_engine:
             self.engine.close()
 
     # ------------------------------------------------------------------------------------------
     def _submit(self, state, pcm, params) -> TranscribeResult:
-        if self._closed:
-            raise RuntimeError("BatchingEngine is closed")
         fut: Future = Future()
-        self._q.put(_Request(state, pcm, params, fut))
+        with self._mu:
+            if self._broken is not None:
+                raise RuntimeError("BatchingEngine worker died: %r" % (self._broken,))
+            if self._closed:
+                raise RuntimeError("BatchingEngine is closed")
+            self._q.put(_Request(state, pcm, params, fut))
         return fut.result()
+
+    def _fail_queued(self, exc: BaseException):
+        while True:
+            try:
+                r = self._q.get_nowait()
+            except queue.Empty:
+                return
+            if r is not None and not r.future.done():
+                r.future.set_exception(exc)
 
     def _single(self, r: _Request) -> TranscribeResult:
         if r.pcm is None:
@@ -98,14 +116,22 @@ class BatchingEngine(AsrEngine):
         self.max_seen = max(self.max_seen, len(group))
         if len(group) > 1:
             try:
-                results = self.engine.transcribe_batch([r.state for r in group], [r.pcm for r in group], group[0].params)
+                # a clip whose read-back fails (whisper.rs:85) fails alone inside the native batch call: its slot comes back as the
+                # error, the other clips keep their results - nothing is decoded twice and no state is advanced twice
+                results = self.engine.transcribe_batch([r.state for r in group], [r.pcm for r in group], group[0].params,
+                                                       return_exceptions=True)
                 for r, res in zip(group, results):
-                    r.future.set_result(res)
+                    if isinstance(res, BaseException):
+                        r.future.set_exception(res)
+                    else:
+                        r.future.set_result(res)
                 return
-            except Exception:      # noqa: BLE001
-                # One clip failed the batch call; the others must not suffer.  Run the clips again one by one: a call starts
-                # from its clip, not from what an earlier call left in the state (stream mode sets no_context, whisper.rs:67).
+            except TypeError:      # an engine without per-clip error reporting (test stubs): clip by clip below
                 pass
+            except Exception as e:      # noqa: BLE001  the call failed as a whole (bad language, out of memory, ...): so does every clip
+                for r in group:
+                    r.future.set_exception(e)
+                return
         for r in group:
             try:
                 r.future.set_result(self._single(r))
@@ -114,6 +140,17 @@ class BatchingEngine(AsrEngine):
 
     def _run(self):
         pending: List[_Request] = []
+        try:
+            self._loop(pending)
+        except BaseException as e:      # noqa: BLE001  never leave a caller blocked in fut.result()
+            with self._mu:
+                self._broken = e
+            for r in pending:
+                if not r.future.done():
+                    r.future.set_exception(e)
+            self._fail_queued(e)
+
+    def _loop(self, pending: List[_Request]):
         stop = False
         while not (stop and not pending):
             if not pending:
@@ -142,5 +179,11 @@ class BatchingEngine(AsrEngine):
                     seen.add(id(r.state))
                 else:
                     rest.append(r)
-            pending = rest
-            self._execute(group)
+            pending[:] = rest
+            try:
+                self._execute(group)
+            except BaseException as e:      # noqa: BLE001
+                for r in group:
+                    if not r.future.done():
+                        r.future.set_exception(e)
+                raise

@@ -143,13 +143,18 @@ int ss_state_new_on(ss_engine *e, int device, ss_state **out) {
     });
 }
 int ss_state_device(const ss_state *s) { return s ? s->s->engine->device : -1; }
+int ss_state_status(const ss_state *s) { return s ? s->s->last_status : SS_ERR_INVALID; }
+const char *ss_state_error(const ss_state *s) { return s ? s->s->last_error.c_str() : ""; }
 void ss_state_free(ss_state *s) { if (s) { delete s->s; delete s; } }
 
 int ss_transcribe(ss_engine *e, ss_state *s, const float *pcm, size_t n, const ss_params *p) {
     return guard([&]() -> int {
         if (!e || !s || (!pcm && n)) SS_THROW(SS_ERR_INVALID, "null argument");
         if (!e->owns(s)) SS_THROW(SS_ERR_INVALID, "state belongs to another engine");
-        return transcribe(*s->s, pcm, n, make_params(p), p && p->stream_mode);
+        State &st = *s->s;
+        st.last_status = 0; st.last_error.clear();
+        try { return transcribe(st, pcm, n, make_params(p), p && p->stream_mode); }
+        catch (const ss::Error &er) { st.last_status = er.code; st.last_error = er.what(); throw; }
     });
 }
 int ss_upload_pcm(ss_engine *e, ss_state *s, const float *pcm, size_t n) {

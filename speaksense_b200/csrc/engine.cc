@@ -297,15 +297,20 @@ State::~State() {
 void upload_pcm(State &s, const float *pcm, size_t n) {
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     if (n + 1 > s.pcm_cap) {
+        // (pointers and capacities are reset BEFORE the throwing allocation: a failed cudaMalloc must not leave dangling pointers)
         if (s.d_pcm_alt) { cudaFree(s.d_pcm_alt); s.d_pcm_alt = nullptr; }
-        if (s.d_pcm) cudaFree(s.d_pcm);
-        s.pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
-        s.d_pcm = dmalloc<float>(s.pcm_cap);
+        if (s.d_pcm) { cudaFree(s.d_pcm); s.d_pcm = nullptr; }
+        s.pcm_cap = 0; s.n_resident = 0;
+        const size_t want_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.d_pcm = dmalloc<float>(want_cap);
+        s.pcm_cap = want_cap;
     }
     if (n + 1 > s.h_pcm_cap) {
-        if (s.h_pcm) cudaFreeHost(s.h_pcm);
-        s.h_pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
-        s.h_pcm = hmalloc<float>(s.h_pcm_cap);
+        if (s.h_pcm) { cudaFreeHost(s.h_pcm); s.h_pcm = nullptr; }
+        s.h_pcm_cap = 0;
+        const size_t want_h = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.h_pcm = hmalloc<float>(want_h);
+        s.h_pcm_cap = want_h;
     }
     if (n) memcpy(s.h_pcm, pcm, n * sizeof(float));      // caller memory is pageable: stage through pinned
     if (n) CUDA_CHECK(cudaMemcpyAsync(s.d_pcm, s.h_pcm, n * sizeof(float), cudaMemcpyHostToDevice, s.stream));
@@ -316,9 +321,10 @@ int denoise_audio(State &s, const float *pcm, size_t n, int frame_size, float ov
     upload_pcm(s, pcm, n);
     const size_t need = denoise_scratch_floats(n, frame_size, overlap);
     if (need > s.dn_cap || !s.d_pcm_alt) {
-        if (s.d_dn) cudaFree(s.d_dn);
-        if (s.d_pcm_alt) cudaFree(s.d_pcm_alt);
-        s.dn_cap = need; s.d_dn = dmalloc<float>(need); s.d_pcm_alt = dmalloc<float>(s.pcm_cap);
+        if (s.d_dn) { cudaFree(s.d_dn); s.d_dn = nullptr; }
+        if (s.d_pcm_alt) { cudaFree(s.d_pcm_alt); s.d_pcm_alt = nullptr; }
+        s.dn_cap = 0;
+        s.d_dn = dmalloc<float>(need); s.dn_cap = need; s.d_pcm_alt = dmalloc<float>(s.pcm_cap);
     }
     const int type = denoise_enqueue(s.d_pcm, n, frame_size, overlap, strength, s.d_pcm_alt, s.d_dn, s.stream, &s.n_launches, nv_out);
     std::swap(s.d_pcm, s.d_pcm_alt);      // the denoised chunk is now the resident PCM (ss_transcribe_resident)
@@ -346,25 +352,30 @@ void run_log_mel(State &s, const float *pcm, size_t n) {
     if (pcm == nullptr && n == s.n_resident && s.d_pcm) {   // PCM already resident in HBM (ss_upload_pcm)
         s.n_len = mel_n_len(n); s.n_len_org = mel_n_len_org(n);
         const size_t need0 = (size_t)m.hp.n_mels * s.n_len;
-        if (need0 > s.mel_cap) { if (s.d_mel) cudaFree(s.d_mel); s.mel_cap = need0; s.d_mel = dmalloc<float>(need0); }
+        if (need0 > s.mel_cap) { if (s.d_mel) { cudaFree(s.d_mel); s.d_mel = nullptr; } s.mel_cap = 0; s.d_mel = dmalloc<float>(need0); s.mel_cap = need0; }
         mel_enqueue(m, s.d_pcm, n, s.d_mel, s.n_len, s.d_max, s.stream, &s.n_launches);
         CUDA_CHECK(cudaGetLastError());
         return;
     }
     if (n + 1 > s.pcm_cap) {
+        // (pointers and capacities are reset BEFORE the throwing allocation: a failed cudaMalloc must not leave dangling pointers)
         if (s.d_pcm_alt) { cudaFree(s.d_pcm_alt); s.d_pcm_alt = nullptr; }
-        if (s.d_pcm) cudaFree(s.d_pcm);
-        s.pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
-        s.d_pcm = dmalloc<float>(s.pcm_cap);
+        if (s.d_pcm) { cudaFree(s.d_pcm); s.d_pcm = nullptr; }
+        s.pcm_cap = 0; s.n_resident = 0;
+        const size_t want_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.d_pcm = dmalloc<float>(want_cap);
+        s.pcm_cap = want_cap;
     }
     if (n + 1 > s.h_pcm_cap) {
-        if (s.h_pcm) cudaFreeHost(s.h_pcm);
-        s.h_pcm_cap = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
-        s.h_pcm = hmalloc<float>(s.h_pcm_cap);
+        if (s.h_pcm) { cudaFreeHost(s.h_pcm); s.h_pcm = nullptr; }
+        s.h_pcm_cap = 0;
+        const size_t want_h = std::max<size_t>(n + 1, (size_t)kSampleRate * kChunkSec);
+        s.h_pcm = hmalloc<float>(want_h);
+        s.h_pcm_cap = want_h;
     }
     s.n_len = mel_n_len(n); s.n_len_org = mel_n_len_org(n);
     const size_t need = (size_t)m.hp.n_mels * s.n_len;
-    if (need > s.mel_cap) { if (s.d_mel) cudaFree(s.d_mel); s.mel_cap = need; s.d_mel = dmalloc<float>(need); }
+    if (need > s.mel_cap) { if (s.d_mel) { cudaFree(s.d_mel); s.d_mel = nullptr; } s.mel_cap = 0; s.d_mel = dmalloc<float>(need); s.mel_cap = need; }
     if (n) memcpy(s.h_pcm, pcm, n * sizeof(float));      // caller memory is pageable: stage through pinned
     if (n) CUDA_CHECK(cudaMemcpyAsync(s.d_pcm, s.h_pcm, n * sizeof(float), cudaMemcpyHostToDevice, s.stream));
     s.n_resident = n;

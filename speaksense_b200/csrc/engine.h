@@ -93,6 +93,7 @@ struct State {
     std::string full_text;
     std::vector<TokData> result_tokens;
     int n_fallbacks = 0, n_decoded = 0, n_windows = 0, n_launches = 0;
+    int last_status = 0; std::string last_error;      // outcome of the last transcribe on this state (a batch call fails clip by clip)
     float ms_mel = 0, ms_enc = 0, ms_dec = 0;
 
     ~State();

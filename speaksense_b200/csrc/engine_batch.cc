@@ -512,9 +512,15 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
     for (int i = 0; i < batch && batched; i++)
         for (int j = 0; j < i; j++) if (states[i] == states[j]) batched = false;      // one state twice: the calls must serialise
     if (!batched) {
-        int rc = 0;
-        for (int i = 0; i < batch; i++) { const int r = transcribe(*states[i], pcm[i], n[i], P, stream_mode); if (r && !rc) rc = r; }
-        return rc;
+        int bad = -1;
+        for (int i = 0; i < batch; i++) {      // clip by clip; a failing clip does not stop the others
+            states[i]->last_status = 0; states[i]->last_error.clear();
+            try { const int r = transcribe(*states[i], pcm[i], n[i], P, stream_mode); if (r) { states[i]->last_status = r; states[i]->last_error = "transcribe failed"; } }
+            catch (const Error &e) { states[i]->last_status = e.code; states[i]->last_error = e.what(); }
+            if (states[i]->last_status && bad < 0) bad = i;
+        }
+        if (bad >= 0) SS_THROW(states[bad]->last_status, "clip %d: %s (the other clips of the batch completed)", bad, states[bad]->last_error.c_str());
+        return 0;
     }
     std::lock_guard<std::mutex> lk(E.batch_mu);
     CUDA_CHECK(cudaSetDevice(E.device));
@@ -534,6 +540,14 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
     C.tid0_init = P.max_initial_ts > 0.0f ? (int)std::round(P.max_initial_ts / precision) : -1;
 
     std::vector<ClipRun> runs(batch);
+    // A clip whose read-back fails (invalid UTF-8 in a segment: whisper.rs:85 fails that call) fails alone: its State records the
+    // error, the other clips of the batch complete and keep their results (ss_state_status); the batch call reports the first error.
+    auto finish_clip = [&](ClipRun &r) {
+        try { postprocess(*r.s, stream_mode); }
+        catch (const Error &e) { r.s->last_status = e.code; r.s->last_error = e.what(); }
+        r.finished = true;
+    };
+    for (int i = 0; i < batch; i++) { states[i]->last_status = 0; states[i]->last_error.clear(); }
     for (int i = 0; i < batch; i++) {      // log-mel of every clip, each on its own stream
         State &s = *states[i];
         runs[i].s = &s;
@@ -549,7 +563,7 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         { float ms; cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.ms_mel += ms; }
         runs[i].seek = 0; runs[i].seek_end = s.n_len_org;
-        if (runs[i].seek_end < 100) { postprocess(s, stream_mode); runs[i].finished = true; continue; }
+        if (runs[i].seek_end < 100) { finish_clip(runs[i]); continue; }
         if (P.no_context) s.prompt_past.clear();
     }
 
@@ -557,7 +571,7 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
         std::vector<ClipRun *> act;
         for (auto &r : runs) {
             if (r.finished) continue;
-            if (r.seek + 100 >= r.seek_end) { postprocess(*r.s, stream_mode); r.finished = true; continue; }
+            if (r.seek + 100 >= r.seek_end) { finish_clip(r); continue; }
             act.push_back(&r);
         }
         if (act.empty()) break;
@@ -634,6 +648,8 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
             r->seek += emit_window(s, P, C, *r);
         }
     }
+    for (int i = 0; i < batch; i++)
+        if (states[i]->last_status) SS_THROW(states[i]->last_status, "clip %d: %s (the other clips of the batch completed)", i, states[i]->last_error.c_str());
     return 0;
 }
 

@@ -50,6 +50,11 @@ size_t parse_meta(const unsigned char *b, size_t sz, HParams &hp, const float **
     memcpy(&hp, b + o, 44); o += 44;
     int n_mel, n_fft; memcpy(&n_mel, b + o, 4); memcpy(&n_fft, b + o + 4, 4); o += 8;
     if (n_mel != hp.n_mels || n_fft != kNBins) SS_THROW(-2, "unexpected mel filterbank %dx%d", n_mel, n_fft);
+    // (every count is validated BEFORE it is used as a divisor or a size: a malformed file must come back as an error)
+    if (hp.n_audio_head <= 0 || hp.n_text_head <= 0 || hp.n_audio_state <= 0 || hp.n_text_state <= 0 || hp.n_audio_layer <= 0 ||
+        hp.n_text_layer <= 0 || hp.n_audio_ctx <= 0 || hp.n_text_ctx <= 0 || hp.n_mels <= 0 || hp.n_audio_layer > 256 || hp.n_text_layer > 256 ||
+        hp.n_audio_state > 16384 || hp.n_text_state > 16384 || hp.n_audio_ctx > 65536 || hp.n_text_ctx > 65536 || hp.n_mels > 1024)
+        SS_THROW(-2, "model header holds a non-positive / absurd hyper-parameter");
     if (hp.n_vocab < 50000 || hp.n_vocab > 100000 || hp.n_audio_state % 128 || hp.n_text_state % 128 ||
         hp.n_audio_state / hp.n_audio_head != 64 || hp.n_text_state / hp.n_text_head != 64)
         SS_THROW(-2, "unsupported hyper-parameters (need d %% 128 == 0, head dim 64)");
@@ -110,14 +115,20 @@ void parse_file(const std::string &path, ParsedFile &pf) {
         if (t.n_dims < 1 || t.n_dims > 4 || nlen <= 0 || nlen > 256) SS_THROW(-2, "bad tensor header at %zu", o);
         if (t.ttype != 0 && t.ttype != 1 && quant_block_bytes(t.ttype) == 0) SS_THROW(-2, "unsupported ggml tensor type %d (f32, f16, q4_0, q4_1, q5_0, q5_1, q8_0 are)", t.ttype);
         if (o + 4 * (size_t)t.n_dims + (size_t)nlen > sz) SS_THROW(-2, "truncated tensor header");
-        for (int d = 0; d < t.n_dims; d++) { memcpy(&t.ne[d], b + o, 4); o += 4; }
+        if (o + 4 * (size_t)t.n_dims + (size_t)nlen > sz) SS_THROW(-2, "truncated tensor header");
+        for (int d = 0; d < t.n_dims; d++) {
+            memcpy(&t.ne[d], b + o, 4); o += 4;
+            if (t.ne[d] <= 0 || t.ne[d] > (1 << 28)) SS_THROW(-2, "tensor dimension %d out of range at byte %zu", t.ne[d], o);
+        }
         std::string name(reinterpret_cast<const char *>(b + o), (size_t)nlen); o += (size_t)nlen;
+        if (t.ttype != 0 && t.ttype != 1 && !quant_block_bytes(t.ttype)) SS_THROW(-2, "tensor '%s': unsupported ggml type %d", name.c_str(), t.ttype);
+        if ((double)t.ne[0] * t.ne[1] * t.ne[2] * t.ne[3] > 4e9) SS_THROW(-2, "tensor '%s' is absurdly large", name.c_str());
         size_t nb = t.count() * (t.ttype == 1 ? 2 : 4);
         if (quant_block_bytes(t.ttype)) {
             if (t.ne[0] % 32) SS_THROW(-2, "quantised tensor '%s': row length %d is not a multiple of 32", name.c_str(), t.ne[0]);
             nb = t.count() / 32 * quant_block_bytes(t.ttype);
         }
-        if (o + nb > sz) SS_THROW(-2, "tensor '%s' truncated", name.c_str());
+        if (nb > sz - o) SS_THROW(-2, "tensor '%s' truncated", name.c_str());
         t.data = b + o; o += nb;
         pf.tensors[name] = t;
     }

@@ -461,6 +461,39 @@ def quantize_model(src: str, dst: str, qtype: str, dequantized_f16_twin: str | N
         os.replace(tmp, path)
 
 
+def write_twin_from_raw(qpath: str, twin_path: str, dequantize) -> None:
+    """Copy the (possibly block-quantised) file `qpath` to `twin_path` with every quantised tensor replaced by the f16 rounding
+    of dequantize(raw_block_bytes, numpy_shape) -> f32 array; header (hparams incl. ftype), filters, vocabulary and all other
+    tensors are copied byte for byte.  tests/test_quantized.py passes gguf.quants.dequantize here."""
+    buf = open(qpath, "rb").read()
+    o = 4 + 44
+    n_mel, n_fft = struct.unpack_from("<2i", buf, o); o += 8 + 4 * n_mel * n_fft
+    n_tok, = struct.unpack_from("<i", buf, o); o += 4
+    for _ in range(n_tok):
+        ln, = struct.unpack_from("<I", buf, o); o += 4 + ln
+    by_type = {t: bs for t, _, bs in QTYPES.values()}
+    tmp = twin_path + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as f:
+        f.write(buf[:o])
+        while o < len(buf):
+            n_dims, nlen, tt = struct.unpack_from("<3i", buf, o)
+            ne = struct.unpack_from("<%di" % n_dims, buf, o + 12)
+            name = buf[o + 12 + 4 * n_dims:o + 12 + 4 * n_dims + nlen]
+            head = 12 + 4 * n_dims + nlen
+            cnt = int(np.prod(ne))
+            if tt in by_type:
+                nbytes = cnt // 32 * by_type[tt]
+                shape = tuple(reversed(ne))
+                vals = np.asarray(dequantize(buf[o + head:o + head + nbytes], shape), np.float32).reshape(shape)
+                f.write(struct.pack("<3i", n_dims, nlen, 1)); f.write(struct.pack("<%di" % n_dims, *ne)); f.write(name)
+                f.write(vals.astype("<f2").tobytes())
+            else:
+                nbytes = cnt * (2 if tt == 1 else 4)
+                f.write(buf[o:o + head + nbytes])
+            o += head + nbytes
+    os.replace(tmp, twin_path)
+
+
 def ensure_model(path: str, **kw) -> str:
     if not os.path.exists(path):
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)

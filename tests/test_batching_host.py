@@ -57,12 +57,21 @@ class _Engine:
             self.batches.append(("resident", [state.name], params.language))
         return self._one(state, None, params)
 
-    def transcribe_batch(self, states, audios, params):
+    def transcribe_batch(self, states, audios, params, return_exceptions=False):
+        """like WhisperAsr.transcribe_batch: a failing clip fails alone (its slot holds the exception with return_exceptions)"""
         time.sleep(self.delay)
         with self.lock:
             self.batches.append(("batch", [s.name for s in states], params.language))
         assert len({id(s) for s in states}) == len(states)
-        return [self._one(s, a, params) for s, a in zip(states, audios)]
+        out = []
+        for s, a in zip(states, audios):
+            try:
+                out.append(self._one(s, a, params))
+            except Exception as e:      # noqa: BLE001
+                if not return_exceptions:
+                    raise
+                out.append(e)
+        return out
 
     def close(self):
         pass
@@ -196,3 +205,73 @@ def test_rest_tasks_through_the_front_end(tmp_path, monkeypatch):
     assert {s.text.split(":")[0] for s in res[0].segments}.isdisjoint({s.text.split(":")[0] for s in res[1].segments})
     assert sum(len(b[1]) for b in eng.batches) == 6
     be.close()
+
+
+def test_failing_clip_is_not_decoded_twice_and_worker_survives():
+    """a clip that fails inside the batch call fails alone: nothing is re-run clip by clip (no state is advanced twice)"""
+    eng = _Engine(delay=0.02)
+    be = BatchingEngine(eng, max_batch=8, linger_s=0.5)
+    states = [be.create_state() for _ in range(4)]
+    p = AsrParams(language="en", stream_mode=True)
+    clips = [np.full(4, i, np.float32) for i in range(4)]
+    clips[2][0] = np.nan
+    out = [None] * 4
+
+    def call(i):
+        try:
+            out[i] = be.transcribe_with_state(states[i], clips[i], p)
+        except Exception as e:      # noqa: BLE001
+            out[i] = e
+
+    th = [threading.Thread(target=call, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert isinstance(out[2], ValueError)
+    assert [o.full_text for i, o in enumerate(out) if i != 2] == ["s1:0:en", "s2:1:en", "s4:3:en"]
+    merged = [b for b in eng.batches if b[0] == "batch" and len(b[1]) >= 2]
+    if merged:      # the merged clips were not run again one by one
+        names = [n for b in merged for n in b[1]]
+        assert not any(b[0] == "single" and b[1][0] in names for b in eng.batches)
+    assert be.transcribe_with_state(states[0], clips[0], p).full_text == "s1:0:en"      # the worker is still alive
+    be.close()
+
+
+def test_worker_death_fails_callers_instead_of_hanging():
+    class _Boom(_Engine):
+        def transcribe_with_state(self, state, audio, params):
+            raise KeyboardInterrupt()      # not an Exception: escapes every handler of the worker loop
+
+    be = BatchingEngine(_Boom(), max_batch=4, linger_s=0.0)
+    st = be.create_state()
+    with pytest.raises(BaseException):
+        be.transcribe_with_state(st, np.zeros(4, np.float32), AsrParams())
+    with pytest.raises(RuntimeError):
+        be.transcribe_with_state(st, np.zeros(4, np.float32), AsrParams())
+    be.close()
+
+
+def test_close_races_with_submit():
+    eng = _Engine(delay=0.001)
+    be = BatchingEngine(eng, max_batch=4, linger_s=0.0)
+    states = [be.create_state() for _ in range(8)]
+    done = []
+
+    def call(i):
+        try:
+            be.transcribe_with_state(states[i], np.full(4, i, np.float32), AsrParams())
+            done.append("ok")
+        except RuntimeError:
+            done.append("closed")
+
+    th = [threading.Thread(target=call, args=(i,)) for i in range(8)]
+    for t in th[:4]:
+        t.start()
+    be.close()
+    for t in th[4:]:
+        t.start()
+    for t in th:
+        t.join(timeout=5)
+    assert not any(t.is_alive() for t in th)      # nobody blocked for ever behind the sentinel
+    assert len(done) == 8

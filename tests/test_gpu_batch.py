@@ -206,3 +206,57 @@ def test_beam_on_batched_step_equals_default_beam(request, audio30, fixture, lan
         os.environ.pop("SS_BATCH_BEAM", None)
     assert got[1] == ref[1] and got[2] == ref[2] and got[3] == ref[3] and got[0] == ref[0]
     eng.close()
+
+
+def _model_with_invalid_utf8_token(src: str, dst: str, token_id: int):
+    """copy of the model file `src` whose vocabulary string of `token_id` is replaced by invalid UTF-8 of the same length"""
+    import struct
+    buf = bytearray(open(src, "rb").read())
+    o = 4 + 44
+    n_mel, n_fft = struct.unpack_from("<2i", buf, o); o += 8 + 4 * n_mel * n_fft
+    n_tok, = struct.unpack_from("<i", buf, o); o += 4
+    assert token_id < n_tok
+    for i in range(n_tok):
+        ln, = struct.unpack_from("<I", buf, o); o += 4
+        if i == token_id:
+            assert ln > 0
+            buf[o:o + ln] = b"\xff" * ln
+            break
+        o += ln
+    open(dst, "wb").write(bytes(buf))
+
+
+def test_failing_clip_fails_alone_in_a_batch(batch_on, tiny_en_peaked, tmp_path):
+    """whisper.rs:85: a segment that is not valid UTF-8 fails that call.  In a batch the failing clips fail alone - the others keep
+    the results their own call would have produced, nothing is decoded twice.  The model's scripted transcript reaches the broken
+    vocabulary entry only in its 3rd segment (after 11.8 s), so 30 s clips fail and 5 s clips do not."""
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    from speaksense_b200._native import NativeError
+    hp = synth.SHAPES["tiny.en"]
+    tgt = synth.scripted_targets(hp, 0)
+    bad_tok = int(tgt[1 + 24 + 2 + 24 + 2 + 5])          # a text token of the third segment
+    assert 256 <= bad_tok < synth.special_tokens(hp.n_vocab)["eot"]
+    path = str(tmp_path / "ggml-tiny.en-badutf8.bin")
+    _model_with_invalid_utf8_token(tiny_en_peaked, path, bad_tok)
+    eng = WhisperAsr(path)
+    p = AsrParams(stream_mode=True)
+    long_a, long_b = synth.synth_audio(seed=1234), synth.synth_audio(seed=99)
+    short = [synth.synth_audio(5 * 16000, seed=5 + i) for i in range(4)]
+    clips = [long_a, short[0], short[1], long_b, short[2], short[3]]
+    ref_short = _single(eng, short, p)
+    with pytest.raises(NativeError) as ei:
+        eng.transcribe(long_a, p)
+    assert ei.value.code == -7
+    states = [eng.create_state() for _ in clips]
+    got = eng.transcribe_batch(states, clips, p, return_exceptions=True)
+    assert isinstance(got[0], NativeError) and got[0].code == -7 and isinstance(got[3], NativeError) and got[3].code == -7
+    assert [got[i] for i in (1, 2, 4, 5)] == [r[0] for r in ref_short]
+    assert all(r[0].full_text for r in ref_short)
+    with pytest.raises(NativeError):                      # without return_exceptions the first error is raised, as before
+        eng.transcribe_batch(states, clips, p)
+    # the states of the clips that failed are usable afterwards
+    ok = eng.transcribe_batch(states, [short[0]] * len(states), p)
+    assert all(r == ref_short[0][0] for r in ok)
+    for st in states:
+        st.close()
+    eng.close()

@@ -98,3 +98,65 @@ def test_cxx_loader_arena_is_bit_identical_to_the_f16_twin(micro_v3_peaked, qtyp
         hs.append((h.value, ab.value))
     assert hs[0] == hs[1]
     os.remove(twin2)
+
+
+# ---- pin to ggml-owned arithmetic: the ggml project's own Python package (gguf.quants, shipped in this image) ----
+GGUF_T = {"q4_0": "Q4_0", "q4_1": "Q4_1", "q5_0": "Q5_0", "q5_1": "Q5_1", "q8_0": "Q8_0"}
+
+
+@pytest.mark.parametrize("qtype", QT)
+def test_block_formats_match_ggml_python_package(qtype):
+    """synth.quantize_blocks / dequantize_blocks (the specification csrc/model.cc and the oracle are held to above) against
+    gguf.quants - written by the ggml authors, the only ggml-owned code available offline: the raw block BYTES of the
+    quantiser and the f32 values of the dequantiser must be identical."""
+    gguf = pytest.importorskip("gguf")
+    from gguf import quants
+    from speaksense_b200 import synth
+    qt = getattr(gguf.GGMLQuantizationType, GGUF_T[qtype])
+    rng = np.random.default_rng(11)
+    for scale in (0.02, 1.0, 37.5):
+        x = (rng.standard_normal((64, 96)) * scale).astype(np.float32)
+        x[0, :32] = 0.0                       # an all-zero block (d == 0)
+        x[1, 5] = np.float32(scale * 9.0)     # an outlier that sets the block scale
+        theirs = quants.quantize(x, qt)
+        ours = np.frombuffer(synth.quantize_blocks(x.reshape(-1), qtype), np.uint8).reshape(theirs.shape)
+        assert np.array_equal(ours, theirs), "%s quantiser differs from gguf.quants in %d bytes" % (qtype, int((ours != theirs).sum()))
+        deq_theirs = quants.dequantize(theirs, qt).astype(np.float32)
+        deq_ours = synth.dequantize_blocks(theirs.tobytes(), qtype, x.size).reshape(x.shape)
+        assert np.array_equal(deq_ours, deq_theirs)
+
+
+@pytest.mark.parametrize("qtype", QT)
+def test_cxx_and_oracle_loaders_match_ggml_python_package(oracle_mod, micro_v3_peaked, qtype):
+    """End to end through a model FILE: the tensors of a quantised file, dequantised by gguf.quants and written as an f16 twin,
+    give the C++ loader the same arena hash and the oracle the same logits as the quantised file itself."""
+    import ctypes as C
+    import struct
+    gguf = pytest.importorskip("gguf")
+    from gguf import quants
+    from speaksense_b200 import _native, build, synth
+    build.build()
+    q, _ = quant_pair(micro_v3_peaked, qtype)
+    qt = getattr(gguf.GGMLQuantizationType, GGUF_T[qtype])
+    ttype, _, bs = synth.QTYPES[qtype]
+    twin = os.path.join(MODEL_DIR, os.path.basename(q)[:-4] + "-gguf-twin.bin")
+    synth.write_twin_from_raw(q, twin, lambda raw, shape: quants.dequantize(
+        np.frombuffer(raw, np.uint8).reshape(-1, (shape[-1] // 32) * bs), qt).astype(np.float32).reshape(shape))
+    hs = []
+    for path in (q, twin):
+        h, ab = C.c_uint64(), C.c_int64()
+        assert _native.lib().ss_model_probe(path.encode(), None, C.byref(ab), C.byref(h), None, None, None) == 0
+        hs.append((h.value, ab.value))
+    assert hs[0] == hs[1]
+    toks = [int(t) for t in np.random.default_rng(3).integers(0, 50000, size=6)]
+    outs = []
+    pcm = synth.synth_audio(16000 * 3, seed=2)
+    for path in (q, twin):
+        om = oracle_mod.OracleModel(path)
+        st = om.new_state()
+        mel, _, _ = om.log_mel(pcm)
+        st.encode(mel, 0)
+        outs.append(st.decode(toks, 0).copy())
+        st.close(); om.close()
+    assert np.array_equal(outs[0], outs[1])
+    os.remove(twin)
