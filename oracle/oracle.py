@@ -82,6 +82,10 @@ def lib():
     L.wo_segment_t1.argtypes = [C.c_void_p, C.c_int]
     L.wo_segment_speaker_turn_next.argtypes = [C.c_void_p, C.c_int]
     L.wo_result_token.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.wo_min_sample_margin.restype = C.c_double
+    L.wo_min_sample_margin.argtypes = [C.c_void_p]
+    L.wo_n_draws.restype = C.c_long
+    L.wo_n_draws.argtypes = [C.c_void_p]
     L.wo_kept_logits.restype = C.POINTER(C.c_float)
     L.wo_kept_logits.argtypes = [C.c_void_p, C.c_int]
     _lib = L
@@ -186,7 +190,8 @@ class OracleState:
             toks.append(self.L.wo_result_token(self.h, i, C.byref(p), C.byref(pl)))
             plogs.append(pl.value)
         return dict(segments=segs, tokens=toks, plogs=plogs, n_fallbacks=self.L.wo_n_fallbacks(self.h),
-                    n_decoded=self.L.wo_n_decoded(self.h), n_windows=self.L.wo_n_windows(self.h))
+                    n_decoded=self.L.wo_n_decoded(self.h), n_windows=self.L.wo_n_windows(self.h),
+                    n_draws=self.L.wo_n_draws(self.h), min_sample_margin=self.L.wo_min_sample_margin(self.h))
 
     def process_logits(self, ids, raw, has_ts=False, seek_delta=0, temperature=0.0, **over) -> np.ndarray:
         """whisper_process_logits probe: filtered logits (-inf = masked) for the history `ids` of sampled tokens"""

@@ -582,6 +582,7 @@ typedef struct {
     sequence_t seq; int seek_delta, failed, completed, has_ts;
     float *probs, *logits, *logprobs;
     uint32_t mt[624]; int mti;
+    double min_margin; long n_draws;   /* diagnostics of the draws since the last wo_full started (wo_min_sample_margin) */
 } decoder_t;
 typedef struct { int64_t t0, t1; char *text; int speaker_turn_next; } segment_t;
 
@@ -938,7 +939,17 @@ static int sample_discrete(decoder_t *dc, const float *probs, int n) {
     double r = ((double)a + (double)b * 4294967296.0) / 18446744073709551616.0;
     if (r >= 1.0) r = nextafter(1.0, 0.0);
     double c = 0.0;
-    for (int i = 0; i < n - 1; i++) { c += (double)probs[i] / sum; if (!(c < r)) return i; }
+    dc->n_draws++;
+    for (int i = 0; i < n - 1; i++) {
+        const double lo = c;
+        c += (double)probs[i] / sum;
+        if (!(c < r)) {      /* distance of the uniform to the nearest boundary of the winner's interval: how much the cumulative */
+            const double mg = (r - lo) < (c - r) ? (r - lo) : (c - r);      /* probabilities may move before the draw changes */
+            if (mg < dc->min_margin) dc->min_margin = mg;
+            return i;
+        }
+    }
+    if (1.0 - r < dc->min_margin) dc->min_margin = 1.0 - r;
     return n - 1;
 }
 
@@ -951,6 +962,13 @@ int wo_probe_sample(wo_state *s, uint32_t seed, const float *probs, int n, int c
     mt_seed(dc, 0);
     return 0;
 }
+
+double wo_min_sample_margin(const wo_state *s) {
+    double m = 1.0;
+    for (int j = 0; j < WO_MAX_DECODERS; j++) if (s->dec[j].n_draws > 0 && s->dec[j].min_margin < m) m = s->dec[j].min_margin;
+    return m;
+}
+long wo_n_draws(const wo_state *s) { long n = 0; for (int j = 0; j < WO_MAX_DECODERS; j++) n += s->dec[j].n_draws; return n; }
 
 static tokdata_t sample_token(wo_state *s, decoder_t *dc, int best) {
     const wo_model *m = s->m; const int nv = m->hp.n_vocab;
@@ -1027,6 +1045,7 @@ int wo_full(wo_state *s, const float *pcm, size_t n_samples, const wo_params *P)
     wo_model *m = s->m; const wo_hparams *hp = &m->hp; const int nv = hp->n_vocab;
     clear_segments(s);
     s->n_res = 0; s->n_fallbacks = 0; s->n_decoded = 0; s->n_windows = 0; s->n_kept = 0;
+    for (int j = 0; j < WO_MAX_DECODERS; j++) { s->dec[j].min_margin = 1.0; s->dec[j].n_draws = 0; }
     if (P->n_threads > 0) {
 #ifdef _OPENMP
         int hw = omp_get_num_procs(); omp_set_num_threads(P->n_threads < hw ? P->n_threads : hw);

@@ -89,6 +89,12 @@ int  wo_n_windows(const wo_state *s);
 int  wo_n_kept_logits(const wo_state *s);
 const float *wo_kept_logits(const wo_state *s, int step); /* raw logits [n_vocab] */
 
+/* diagnostics of the t > 0 draws of the last wo_full: how many uniforms were consumed, and the smallest distance of a uniform to a
+ * boundary of the interval it fell into (cumulative probability units).  A second implementation whose probabilities differ by
+ * less than that margin must draw the same tokens. */
+double wo_min_sample_margin(const wo_state *s);
+long   wo_n_draws(const wo_state *s);
+
 /* test probe: the logits filter (whisper_process_logits) on a given history of sampled token ids and decoder timestamp
  * state; logits_out [n_vocab], -inf = masked */
 int  wo_probe_process_logits(wo_state *s, const wo_params *p, const int *ids, int n_ids, int has_ts, int seek_delta,

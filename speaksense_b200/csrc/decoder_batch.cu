@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(64) bd_cross_fold_kernel(const __grid_constant
 struct MaxIdx { float v; int i; };
 __device__ __forceinline__ MaxIdx better(MaxIdx a, MaxIdx b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
 
-struct SeqState { int pos, pos0, token, done, n_sampled, has_ts, seek_delta, result_len, last_id, penult_id, n_prompt, seek, seek_end, n_max, sample; };
+struct SeqState { int pos, pos0, token, done, n_sampled, has_ts, seek_delta, result_len, last_id, penult_id, n_prompt, seek, seek_end, n_max, sample; float temperature; };
 
 __device__ __forceinline__ bool token_masked(const BatchParams &P, const SeqState &st, int i) {
     const bool is_initial = st.n_sampled == 0;
@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __gr
         s.pos = ctl->pos; s.pos0 = ctl->pos0; s.token = ctl->token; s.done = ctl->done; s.n_sampled = ctl->n_sampled; s.has_ts = ctl->has_ts;
         s.seek_delta = ctl->seek_delta; s.result_len = ctl->result_len; s.last_id = ctl->last_id; s.penult_id = ctl->penult_id;
         s.n_prompt = ctl->n_prompt; s.seek = ctl->seek; s.seek_end = ctl->seek_end; s.n_max = ctl->n_max; s.sample = ctl->sample;
+        s.temperature = ctl->temperature;
         S = s;
     }
     __syncthreads();
@@ -432,9 +433,15 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __gr
         return;
     }
     const float *logits = P.logits + (size_t)b * P.n_vocab;
+    const bool drawn = st.sample == 3;                                  // t > 0: whisper_sample_token(best = false)
+    const float inv_div = st.temperature;                               // (the host divides: logits[i] /= temperature)
+    auto value = [&](int i) -> float {
+        if (token_masked(P, st, i)) return -INFINITY;
+        return drawn ? logits[i] / inv_div : logits[i];
+    };
     MaxIdx mt{-INFINITY, 0x7fffffff}, ms{-INFINITY, 0x7fffffff};      // best text token / best timestamp token
     for (int i = tid; i < P.n_vocab; i += kSampleWarps * 32) {
-        const float x = token_masked(P, st, i) ? -INFINITY : logits[i];
+        const float x = value(i);
         if (i < P.beg) { if (x > mt.v) mt = MaxIdx{x, i}; } else { if (x > ms.v) ms = MaxIdx{x, i}; }
     }
 #pragma unroll
@@ -449,22 +456,61 @@ __global__ void __launch_bounds__(kSampleWarps * 32) bd_sample_kernel(const __gr
     const float m_all = fmaxf(mt.v, ms.v);
     float sa = 0.f, sb = 0.f;      // sum exp over everything (relative to m_all) / over the timestamps (relative to their maximum)
     for (int i = tid; i < P.n_vocab; i += kSampleWarps * 32) {
-        const float x = token_masked(P, st, i) ? -INFINITY : logits[i];
+        const float x = value(i);
         if (x > -INFINITY) { sa += expf(x - m_all); if (i >= P.beg) sb += expf(x - ms.v); }
     }
     sa = warp_sum(sa); sb = warp_sum(sb);
     if (lane == 0) { rs[0][warp] = sa; rs[1][warp] = sb; }
     __syncthreads();
-    if (tid != 0) return;
     sa = 0.f; sb = 0.f;
     for (int w = 0; w < kSampleWarps; w++) { sa += rs[0][w]; sb += rs[1][w]; }
-    SeqState s = st;
     const float max_text = mt.v, max_ts = ms.v;
     const float lse = logf(sa) + m_all;
     const float ts_lp = sb > 0.f ? logf(sb) + (max_ts - lse) : -INFINITY;      // logsumexp of the timestamp log-probs
     const float text_lp = max_text - lse;
+    int drawn_id = -1;
+    if (drawn) {
+        // std::discrete_distribution<>(probs)(rng) of libstdc++ (whisper_sample_token, best = false): the probabilities are
+        // normalised by their sum in double, accumulated, and the first index whose cumulative probability is not below the
+        // uniform wins.  Thread t owns the contiguous slice [t * per, (t + 1) * per); slice sums are scanned across the CTA.
+        __shared__ double ds[kSampleWarps];
+        __shared__ double dtot;
+        __shared__ int dmin[kSampleWarps];
+        const bool text_off = ts_lp > text_lp;                                  // the timestamps outweigh every text token
+        auto prob = [&](int i) -> float {
+            const float x = value(i);
+            if (x == -INFINITY || (text_off && i < P.beg)) return 0.f;
+            return expf(x - lse);
+        };
+        const int per = (P.n_vocab + kSampleWarps * 32 - 1) / (kSampleWarps * 32);
+        const int i0 = tid * per, i1 = min(P.n_vocab, i0 + per);
+        double loc = 0.0;
+        for (int i = i0; i < i1; i++) loc += (double)prob(i);
+        double incl = loc;                                                      // inclusive scan of the slice sums: warp, then CTA
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) ds[warp] = incl;
+        __syncthreads();
+        if (tid == 0) { double a = 0.0; for (int w = 0; w < kSampleWarps; w++) { const double t = ds[w]; ds[w] = a; a += t; } dtot = a; }
+        __syncthreads();
+        const double total = dtot;
+        double c = (ds[warp] + incl - loc) / total;                             // cumulative probability in front of this slice
+        const double r = ctl->u[st.n_sampled < kMaxDraws ? st.n_sampled : kMaxDraws - 1];
+        int mine = 0x7fffffff;
+        for (int i = i0; i < i1; i++) { c += (double)prob(i) / total; if (!(c < r)) { mine = i; break; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+        if (lane == 0) dmin[warp] = mine;
+        __syncthreads();
+        mine = dmin[0];
+        for (int w = 1; w < kSampleWarps; w++) mine = min(mine, dmin[w]);
+        drawn_id = min(mine, P.n_vocab - 1);                                    // (rounding left the last cumulative value below r)
+    }
+    if (tid != 0) return;
+    SeqState s = st;
     TokData tk;
-    if (ts_lp > text_lp) { tk.id = ms.i; tk.plog = max_ts - lse; }              // timestamps outweigh every text token
+    if (drawn) { tk.id = drawn_id; const float x = value(drawn_id); tk.plog = x - lse; }
+    else if (ts_lp > text_lp) { tk.id = ms.i; tk.plog = max_ts - lse; }         // timestamps outweigh every text token
     else if (max_text >= max_ts) { tk.id = mt.i; tk.plog = text_lp; }
     else { tk.id = ms.i; tk.plog = max_ts - lse; }
     if (tk.id == 0x7fffffff) { tk.id = 0; tk.plog = -INFINITY; }

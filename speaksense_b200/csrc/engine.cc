@@ -830,6 +830,9 @@ int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P
                     CUDA_CHECK(cudaMemcpy(s.h_keep.data() + old, s.keep, (size_t)nk * hp.n_vocab * sizeof(float), cudaMemcpyDeviceToHost));
                     s.n_keep += nk;
                 }
+            } else if (!beam && batch_sample_enabled() && batch_beam_supported(s) && n_max <= kMaxDraws) {
+                // ------- t > 0 (default; SS_BATCH_SAMPLE=0: off): the best_of sampled decoders as sequences of one batched step -------
+                decode_sampled_batched(s, P, t_cur, n_cur, prompt, seek, seek_end, n_max, tid0_init);
             } else if (beam && batch_beam_enabled() && batch_beam_supported(s)) {
                 // ------- default (SS_BATCH_BEAM=0: off): the live beams as sequences of one batched decoder step (engine_batch.cc) -------
                 decode_beam_batched(s, P, t_cur, n_cur, prompt, seek, seek_end, n_max, tid0_init);

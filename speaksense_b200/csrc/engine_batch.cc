@@ -21,6 +21,8 @@
 
 #include "engine_internal.h"
 
+#include <random>
+
 namespace ss {
 
 Engine::~Engine() {
@@ -503,6 +505,112 @@ void decode_beam_batched(State &s, const FullParams &P, float t_cur, int n_cur, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// t > 0 fallback rungs on the batched step (default; SS_BATCH_SAMPLE=0 turns it off).
+// whisper_full runs best_of (5) sampled decoders per rung: one batch-1 launch + a 207 KB logits read-back + a 51 866-wide
+// filter / soft-max / discrete_distribution on the host PER DECODER AND TOKEN in the SS_BATCH_SAMPLE=0 path (engine.cc).  Here the
+// decoders are the sequences of ONE batched step and the whole rung runs on the device like the temperature-0 loop: the prompt goes
+// through the batch-1 kernel once (decoder 0, its self-KV rows copied to the others), then every step filters, divides by the
+// temperature, draws (bd_sample_kernel, sample == 3) and applies whisper_full's per-token bookkeeping per sequence.  The uniforms
+// come from each decoder's own std::mt19937 through std::generate_canonical<double, 53> - what std::discrete_distribution consumes -
+// generated ahead on a copy of the generator; afterwards the real generator is advanced by the draws the decoder actually used.
+// ------------------------------------------------------------------------------------------------
+bool batch_sample_enabled() {
+    const char *e = getenv("SS_BATCH_SAMPLE");
+    return !(e && e[0] == '0');
+}
+
+static void decode_sampled_batched_locked(State &s, const FullParams &P, float t_cur, int n_cur, const std::vector<int> &prompt, int seek,
+                                         int seek_end, int n_max, int tid0_init);
+void decode_sampled_batched(State &s, const FullParams &P, float t_cur, int n_cur, const std::vector<int> &prompt, int seek, int seek_end,
+                            int n_max, int tid0_init) {
+    Engine &E = *s.engine;
+    std::lock_guard<std::mutex> lk(E.batch_mu);      // the operand buffers are the engine's
+    ensure_batch_resources(E);
+    decode_sampled_batched_locked(s, P, t_cur, n_cur, prompt, seek, seek_end, n_max, tid0_init);
+}
+// (the caller holds the engine's batch mutex: transcribe_batch runs the ladder of a failed clip while it owns the operand buffers)
+static void decode_sampled_batched_locked(State &s, const FullParams &P, float t_cur, int n_cur, const std::vector<int> &prompt, int seek,
+                                         int seek_end, int n_max, int tid0_init) {
+    Engine &E = *s.engine;
+    const Model &m = E.model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
+    const int n_prompt = (int)prompt.size();
+    for (int j = 0; j < n_cur; j++) { set_sampling(*s.dec[j], P, tid0_init); ensure_params(s, *s.dec[j]); }
+    // prompt[0 .. n_prompt - 2] through the batch-1 kernel on decoder 0 (no logits needed), its self-KV rows to the other decoders;
+    // the last prompt token is the first step of the batched loop (every sequence recomputes that one row itself)
+    if (n_prompt > 1) {
+        Decoder &d0 = *s.dec[0];
+        DecCtl &c = *d0.h_ctl;
+        memset(&c, 0, offsetof(DecCtl, prompt));
+        c.pos = 0; c.pos0 = 0; c.token = prompt[0]; c.n_prompt = n_prompt; c.sample = 0; c.last_id = -1; c.penult_id = -1;   // n_prompt: no LM head before the end
+        for (int i = 0; i < n_prompt - 1; i++) c.prompt[i] = prompt[i];
+        c.prompt[n_prompt - 1] = prompt[n_prompt - 1];
+        CUDA_CHECK(cudaMemcpyAsync(d0.mp.ctl, d0.h_ctl, offsetof(DecCtl, u), cudaMemcpyHostToDevice, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));      // the pinned block is re-armed for the batched loop below
+        decode_mega_launch(d0.d_mp, d0.d_ll, d0.ll_bytes, n_prompt - 1, s.mega_grid, s.stream);
+        s.n_launches += 1;
+        for (int j = 1; j < n_cur; j++) kv_copy(s, d0, *s.dec[j], n_prompt - 1);
+    }
+    s.n_decoded += n_prompt - 1;
+    BatchParams bp{};
+    bp.B = n_cur; bp.d = hp.n_text_state; bp.H = hp.n_text_head; bp.L = hp.n_text_layer; bp.T = hp.n_audio_ctx; bp.ctx = hp.n_text_ctx; bp.n_vocab = hp.n_vocab;
+    bp.s4 = powf((float)(bp.d / bp.H), -0.25f);
+    bp.tok_emb = m.tok_emb; bp.d_pos = m.d_pos; bp.lnf_w = m.d_ln.w; bp.lnf_b = m.d_ln.b;
+    bp.eot = v.eot; bp.sot = v.sot; bp.translate = v.translate; bp.transcribe = v.transcribe; bp.solm = v.solm; bp.prev = v.prev;
+    bp.nosp = v.nosp; bp.not_ = v.not_; bp.beg = v.beg; bp.blank = v.blank;
+    bp.suppress_blank = P.suppress_blank; bp.tdrz = P.tdrz_enable; bp.tid0_init = tid0_init;
+    decode_batch_bind(bp, E.batch_scratch);
+    for (int j = 0; j < n_cur; j++) {
+        Decoder &dc = *s.dec[j];
+        DecCtl &c = *dc.h_ctl;
+        memset(&c, 0, offsetof(DecCtl, prompt));
+        c.pos = n_prompt - 1; c.pos0 = n_prompt - 1; c.token = prompt[n_prompt - 1]; c.n_prompt = 1; c.sample = 3; c.temperature = t_cur;
+        c.last_id = -1; c.penult_id = -1; c.seek = seek; c.seek_end = seek_end; c.n_max = n_max; c.seek_delta = 100 * kChunkSec;
+        c.prompt[0] = prompt[n_prompt - 1];
+        std::mt19937 ahead = dc.rng;      // a copy: the decoder's generator moves on by the draws it really consumed (below)
+        for (int i = 0; i < n_max; i++) c.u[i] = std::generate_canonical<double, 53>(ahead);
+        CUDA_CHECK(cudaMemcpyAsync(dc.mp.ctl, dc.h_ctl, sizeof(DecCtl), cudaMemcpyHostToDevice, s.stream));
+        bp.seq[j] = BatchSeq{dc.mp.ctl, dc.mp.self_k, dc.mp.self_v, s.cross_k, s.cross_v, dc.mp.tok_out};
+    }
+    for (int k = n_cur; k < kMaxBatch; k++) bp.seq[k] = bp.seq[0];
+    const MegaParams &w = s.dec[0]->mp;
+    const int xsplit = decode_batch_xsplit(n_cur, bp.H, E.sms);
+    CUDA_CHECK(cudaMemsetAsync(bp.n_done, 0, sizeof(int), s.stream));
+    E.batch_h_flags[0] = E.batch_h_flags[1] = 0;
+    for (int t = 0; t < n_max; t++) {
+        if (t % kPollEvery == 0) {
+            const int G = t / kPollEvery;
+            if (G >= 2) {
+                CUDA_CHECK(cudaEventSynchronize(E.batch_ev[G & 1]));
+                if (E.batch_h_flags[G & 1] >= n_cur) break;
+            }
+        }
+        decode_batch_step_enqueue(bp, w, /*need_logits=*/true, xsplit, s.stream, &s.n_launches);
+        if (t % kPollEvery == kPollEvery - 1) {
+            const int G = t / kPollEvery;
+            CUDA_CHECK(cudaMemcpyAsync(&E.batch_h_flags[G & 1], bp.n_done, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_CHECK(cudaEventRecord(E.batch_ev[G & 1], s.stream));
+        }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    for (int j = 0; j < n_cur; j++) {
+        Decoder &dc = *s.dec[j];
+        CUDA_CHECK(cudaMemcpyAsync(dc.h_ctl, dc.mp.ctl, offsetof(DecCtl, prompt), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        const int ns = dc.h_ctl->n_sampled;
+        if (ns > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(dc.h_tok, dc.mp.tok_out, (size_t)ns * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
+            CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        }
+        dc.seq.tokens.assign(dc.h_tok, dc.h_tok + ns);
+        for (int i = 0; i < ns; i++) dc.seq.sum_logprobs_all += dc.h_tok[i].plog;
+        dc.seq.result_len = dc.h_ctl->result_len; dc.seek_delta = dc.h_ctl->seek_delta;
+        dc.failed = dc.h_ctl->failed; dc.completed = dc.h_ctl->completed; dc.has_ts = dc.h_ctl->has_ts;
+        dc.rng.discard(2ull * (unsigned long long)ns);      // generate_canonical<double, 53> takes two 32-bit words per draw
+        s.n_decoded += ns;
+    }
+}
+
 int transcribe_batch(State *const *states, const float *const *pcm, const size_t *n, int batch, const FullParams &P, bool stream_mode) {
     if (batch <= 0) return 0;
     Engine &E = *states[0]->engine;
@@ -639,7 +747,9 @@ int transcribe_batch(State *const *states, const float *const *pcm, const size_t
                 reset_decoders(s, n_cur);
                 build_prompt(s, P, C, t_cur, r->prompt);
                 CUDA_CHECK(cudaEventRecord(s.ev[2], s.stream));
-                decode_sampled(s, P, C, t_cur, n_cur, r->prompt, r->seek, r->seek_end);
+                if (t_cur > 0.0f && batch_sample_enabled() && C.n_max <= kMaxDraws)      // (this function's batch path implies the supported shapes)
+                    decode_sampled_batched_locked(s, P, t_cur, n_cur, r->prompt, r->seek, r->seek_end, C.n_max, C.tid0_init);
+                else decode_sampled(s, P, C, t_cur, n_cur, r->prompt, r->seek, r->seek_end);
                 CUDA_CHECK(cudaEventRecord(s.ev[3], s.stream));
                 CUDA_CHECK(cudaStreamSynchronize(s.stream));
                 { float ms; cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.ms_dec += ms; }

@@ -21,6 +21,11 @@ struct BeamCandidate { int decoder_idx, seek_delta; bool has_ts; Sequence seq; }
 std::vector<TokData> sample_topk_host(const Model &m, const Decoder &dc, int k);
 void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i, int n_past);
 // (SS_BATCH_BEAM, on by default): one window's beam search with the live beams as sequences of one batched decoder step
+// (SS_BATCH_SAMPLE, on by default): the best_of sampled decoders of a t > 0 rung as sequences of one batched decoder step, drawn on the
+// device (bd_sample_kernel, sample == 3) from uniforms the host generates with each decoder's own std::mt19937
+bool batch_sample_enabled();
+void decode_sampled_batched(State &s, const FullParams &P, float t_cur, int n_cur, const std::vector<int> &prompt, int seek, int seek_end,
+                            int n_max, int tid0_init);
 bool batch_beam_enabled();
 bool batch_beam_supported(const State &s);
 void decode_beam_batched(State &s, const FullParams &P, float t_cur, int n_cur, const std::vector<int> &prompt, int seek, int seek_end,

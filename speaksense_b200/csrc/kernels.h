@@ -73,6 +73,7 @@ void f32_to_f16_enqueue(const float *x, __half *y, size_t n, cudaStream_t st, in
 // ---------------------------------------------------------------- decoder (decoder.cu)
 constexpr int kNumLangSuppress = 100;
 constexpr int kMaxPrompt = 448;
+constexpr int kMaxDraws = 256;     // uniforms a sampled decoder can consume in one window (n_max = n_text_ctx / 2 - 4 <= 252)
 
 struct TokData { int id, tid; float p, plog, pt, ptsum; };
 
@@ -84,7 +85,11 @@ struct DecCtl {   // device resident; written by dec_sample_kernel, read by ever
     int seek, seek_end, n_max;
     int sample, keep_logits, n_kept;
     int all_logits;   // compute the LM head for every token, not only from the last prompt token on
+    float temperature;   // sample == 3 (t > 0 fallback decoders on the batched step): logits are divided by it before the filter
     int prompt[kMaxPrompt];
+    // sample == 3: draw i of this window = std::generate_canonical<double, 53>(mt19937), generated by the host from the decoder's
+    // own generator (whisper.cpp: one std::mt19937 per decoder) so that host- and device-sampled paths consume the same stream
+    double u[kMaxDraws];
 };
 
 struct MegaLayer {

@@ -234,6 +234,12 @@ def write_model(path: str, shape: str = "tiny.en", family: str = "peaked", seed:
     """Write a synthetic legacy-ggml Whisper file.  Returns a small dict of metadata
     (hparams, special tokens, scripted targets) for the tests."""
     hp = hparams or SHAPES[shape]
+    # "soft<a>" = the peaked script with a target logit of only <a> (peaked: >= 30): with a ~ 10 the greedy tokens at temperature 0
+    # have log-probabilities below logprob_thold (-1.0), so whisper_full walks the temperature ladder (best_of sampled decoders at
+    # t > 0) - on a distribution that is still peaked enough for token-for-token comparison of the draws
+    peak = None
+    if family.startswith("soft"):
+        peak = float(family[4:]); family = "peaked"
     assert family in ("random", "peaked")
     rng = np.random.default_rng(seed)
     st = special_tokens(hp.n_vocab)
@@ -286,7 +292,7 @@ def write_model(path: str, shape: str = "tiny.en", family: str = "peaked", seed:
     dec_out = 0.02 / np.sqrt(3.0 * hp.n_text_layer) if family == "peaked" else 0.02
     # peaked: target logit = |e| * sqrt(d) * sqrt(d) = emb_std * d must clear logsumexp over the
     # vocabulary (~ln(51866) + var/2) by a wide margin at temperature 0 for every model width
-    emb = nrm((hp.n_vocab, dd), max(0.02, 30.0 / dd) if family == "peaked" else 0.02)
+    emb = nrm((hp.n_vocab, dd), (peak / dd if peak is not None else max(0.02, 30.0 / dd)) if family == "peaked" else 0.02)
     targets = None
     if family == "peaked":
         targets = scripted_targets(hp, seed, seg_tokens, seg_ticks)
@@ -525,7 +531,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("path")
     ap.add_argument("--shape", default="tiny.en", choices=sorted(SHAPES))
-    ap.add_argument("--family", default="peaked", choices=["random", "peaked"])
+    ap.add_argument("--family", default="peaked", help="random | peaked | soft<target logit>, e.g. soft10")
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
     m = write_model(a.path, a.shape, a.family, a.seed)
