@@ -431,6 +431,14 @@ def main():
                                                 "decode_ms": b["batched"]["decode_ms"], "gpu_launches": b["batched"]["launches"]}
             except Exception as ex:   # noqa: BLE001
                 line["next_rows"]["batch32"] = {"error": str(ex)[:200]}
+            # row a9 measured: a clip that walks the temperature ladder (n_fallbacks > 0), device-sampled against host-sampled
+            if not os.environ.get("SS_BENCH_NO_FALLBACK"):
+                try:
+                    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fallback_bench.py"), args.shape, "soft10", "2"],
+                                         capture_output=True, text=True, timeout=300)
+                    line["next_rows"]["fallback_ladder"] = json.loads(out.stdout.strip().splitlines()[-1])
+                except Exception as ex:   # noqa: BLE001
+                    line["next_rows"]["fallback_ladder"] = {"error": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     state.close()
     eng.close()
