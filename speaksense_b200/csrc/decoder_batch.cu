@@ -735,4 +735,38 @@ void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool n
     if (launches) *launches += n;
 }
 
+// ------------------------------------------------------------------------------------------------
+static bool batch_graph_enabled() {
+    static const bool on = [] { const char *e = getenv("SS_BATCH_GRAPH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+BatchStepGraph::~BatchStepGraph() {
+    for (Slot &s : slot) if (s.exec) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(s.exec));
+}
+void decode_batch_step_graph(BatchStepGraph &G, const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st,
+                             int *launches, const BeamStep *beam) {
+    if (!batch_graph_enabled()) { decode_batch_step_enqueue(P, w, need_logits, xsplit, st, launches, beam); return; }
+    BatchStepGraph::Slot &s = G.slot[need_logits ? 1 : 0];
+    const bool same = s.valid && memcmp(&s.P, &P, sizeof(BatchParams)) == 0 && s.xsplit == xsplit && s.has_beam == (beam != nullptr) &&
+                      (!beam || (s.beam.temperature == beam->temperature && s.beam.k == beam->k && s.beam.cand == beam->cand));
+    if (!same) {
+        if (s.exec) { cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(s.exec)); s.exec = nullptr; }
+        s.valid = false;
+        cudaGraph_t graph = nullptr;
+        int n = 0;
+        CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try { decode_batch_step_enqueue(P, w, need_logits, xsplit, st, &n, beam); }
+        catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) SS_THROW(-4, "cudaGraphInstantiate of the batched decoder step failed: %s", cudaGetErrorString(e));
+        s.exec = exec; s.n_launch = n; s.P = P; s.xsplit = xsplit; s.has_beam = beam != nullptr; if (beam) s.beam = *beam;
+        s.valid = true;
+    }
+    CUDA_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(s.exec), st));
+    if (launches) *launches += s.n_launch;
+}
+
 }  // namespace ss

@@ -355,6 +355,7 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
     CUDA_CHECK(cudaMemsetAsync(bp.n_done, 0, sizeof(int), bs));
     CUDA_CHECK(cudaEventRecord(E.batch_ev[2], bs));
     int launches = 0;
+    BatchStepGraph step_graph;      // the step captured once, replayed per token
     E.batch_h_flags[0] = E.batch_h_flags[1] = 0;
     for (int t = 0; t < max_steps; t++) {
         if (t % kPollEvery == 0) {
@@ -364,7 +365,7 @@ void decode_group(Engine &E, const FullParams &P, const Common &C, std::vector<C
                 if (E.batch_h_flags[G & 1] >= nb) break;
             }
         }
-        decode_batch_step_enqueue(bp, w, /*need_logits=*/t >= min_prompt - 1, xsplit, bs, &launches);
+        decode_batch_step_graph(step_graph, bp, w, /*need_logits=*/t >= min_prompt - 1, xsplit, bs, &launches);
         if (t % kPollEvery == kPollEvery - 1) {
             const int G = t / kPollEvery;
             CUDA_CHECK(cudaMemcpyAsync(&E.batch_h_flags[G & 1], bp.n_done, sizeof(int), cudaMemcpyDeviceToHost, bs));
@@ -444,6 +445,7 @@ void decode_beam_batched(State &s, const FullParams &P, float t_cur, int n_cur, 
     const MegaParams &w = s.dec[0]->mp;
     const BeamStep bstep{t_cur, K, E.beam_cand};
     std::vector<std::vector<TokData>> dev_cands(n_cur);      // candidates of decoder j from the last batched step
+    BatchStepGraph step_graph;      // re-captured only when the set of live beams changes
     std::vector<BeamCandidate> cands;
     for (int i = 0; i < n_max; i++) {
         cands.clear();
@@ -497,7 +499,7 @@ void decode_beam_batched(State &s, const FullParams &P, float t_cur, int n_cur, 
         }
         for (int k = bp.B; k < kMaxBatch; k++) bp.seq[k] = bp.seq[0];
         CUDA_CHECK(cudaMemsetAsync(bp.n_done, 0, sizeof(int), s.stream));
-        decode_batch_step_enqueue(bp, w, /*need_logits=*/true, decode_batch_xsplit(bp.B, bp.H, E.sms), s.stream, &s.n_launches, &bstep);
+        decode_batch_step_graph(step_graph, bp, w, /*need_logits=*/true, decode_batch_xsplit(bp.B, bp.H, E.sms), s.stream, &s.n_launches, &bstep);
         CUDA_CHECK(cudaMemcpyAsync(E.beam_h_cand, E.beam_cand, (size_t)bp.B * 8 * sizeof(TokData), cudaMemcpyDeviceToHost, s.stream));
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         for (int k = 0; k < bp.B; k++) dev_cands[live[k]].assign(E.beam_h_cand + (size_t)k * 8, E.beam_h_cand + (size_t)k * 8 + K);
@@ -576,6 +578,7 @@ static void decode_sampled_batched_locked(State &s, const FullParams &P, float t
     const MegaParams &w = s.dec[0]->mp;
     const int xsplit = decode_batch_xsplit(n_cur, bp.H, E.sms);
     CUDA_CHECK(cudaMemsetAsync(bp.n_done, 0, sizeof(int), s.stream));
+    BatchStepGraph step_graph;
     E.batch_h_flags[0] = E.batch_h_flags[1] = 0;
     for (int t = 0; t < n_max; t++) {
         if (t % kPollEvery == 0) {
@@ -585,7 +588,7 @@ static void decode_sampled_batched_locked(State &s, const FullParams &P, float t
                 if (E.batch_h_flags[G & 1] >= n_cur) break;
             }
         }
-        decode_batch_step_enqueue(bp, w, /*need_logits=*/true, xsplit, s.stream, &s.n_launches);
+        decode_batch_step_graph(step_graph, bp, w, /*need_logits=*/true, xsplit, s.stream, &s.n_launches);
         if (t % kPollEvery == kPollEvery - 1) {
             const int G = t / kPollEvery;
             CUDA_CHECK(cudaMemcpyAsync(&E.batch_h_flags[G & 1], bp.n_done, sizeof(int), cudaMemcpyDeviceToHost, s.stream));

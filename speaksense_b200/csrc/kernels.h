@@ -157,5 +157,16 @@ struct BeamStep { float temperature; int k; TokData *cand; };   // cand: device 
 // `beam` != nullptr (opt-in beam search on the batched step): the step ends with k candidates per sequence instead of a greedy token
 void decode_batch_step_enqueue(const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st, int *launches,
                                const BeamStep *beam = nullptr);
+// The same step as a CUDA graph: the ~390 launches (with their programmatic-dependent-launch edges) are captured once per
+// (parameters, need_logits) and replayed for every token of the round - every per-token quantity lives in device memory (control
+// blocks), so the kernel arguments do not change.  A caller keeps one BatchStepGraph per round; a change of the arguments
+// (live beams leaving, another xsplit) re-captures.  SS_BATCH_GRAPH=0: plain launches.
+struct BatchStepGraph {
+    struct Slot { void *exec = nullptr; int n_launch = 0; bool valid = false; BatchParams P; int xsplit = 0; BeamStep beam{0.f, 0, nullptr}; bool has_beam = false; };
+    Slot slot[2];      // [need_logits]
+    ~BatchStepGraph();
+};
+void decode_batch_step_graph(BatchStepGraph &G, const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st,
+                             int *launches, const BeamStep *beam = nullptr);
 
 }  // namespace ss
