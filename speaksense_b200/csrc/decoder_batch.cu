@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 template <int NW, bool STREAM>
 __device__ __forceinline__ float attend(const __half *__restrict__ Kh, const __half *__restrict__ Vh, int n, const float *q, float *sc,
-                                        float (*red)[64], float *red1, float &m_out, float &l_out) {
+                                        float (*red)[64], float *red1, float &m_out, float &l_out, int swz_row0 = -1) {
+    // swz_row0 >= 0: the rows are cross-KV cache rows starting at absolute key swz_row0 - chunk c of key m sits at c ^ (m & 7)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
     const float4 qa = *reinterpret_cast<const float4 *>(q + l8 * 8), qb = *reinterpret_cast<const float4 *>(q + l8 * 8 + 4);
     constexpr int STEP = NW * 4, U = 4;
@@ -271,7 +272,7 @@ __device__ __forceinline__ float attend(const __half *__restrict__ Kh, const __h
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = min(jb + u * STEP + warp * 4 + sub, n - 1);
-            const uint4 *p = reinterpret_cast<const uint4 *>(Kh + (size_t)j * 64) + l8;
+            const uint4 *p = reinterpret_cast<const uint4 *>(Kh + (size_t)j * 64) + (swz_row0 >= 0 ? (l8 ^ ((swz_row0 + j) & 7)) : l8);
             kv[u] = STREAM ? __ldcs(p) : __ldcg(p);
         }
 #pragma unroll
@@ -294,7 +295,7 @@ __device__ __forceinline__ float attend(const __half *__restrict__ Kh, const __h
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = min(jb + u * STEP + warp * 4 + sub, n - 1);
-            const uint4 *p = reinterpret_cast<const uint4 *>(Vh + (size_t)j * 64) + l8;
+            const uint4 *p = reinterpret_cast<const uint4 *>(Vh + (size_t)j * 64) + (swz_row0 >= 0 ? (l8 ^ ((swz_row0 + j) & 7)) : l8);
             vv[u] = STREAM ? __ldcs(p) : __ldcg(p);
         }
 #pragma unroll
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kCrossWarps * 32) bd_cross_attn_kernel(const _
     const int per = (T + S - 1) / S, j0 = min(T, sp * per), n = min(T, j0 + per) - j0;
     const size_t off = (size_t)il * 2 * T * d + ((size_t)h * T + j0) * 64;
     float m = -INFINITY, l = 0.f, o = 0.f;
-    if (n > 0) o = attend<kCrossWarps, true>(P.seq[b].cross_k + off, P.seq[b].cross_v + off, n, q, sc, red, red1, m, l);
+    if (n > 0) o = attend<kCrossWarps, true>(P.seq[b].cross_k + off, P.seq[b].cross_v + off, n, q, sc, red, red1, m, l, j0);
     if (S == 1) {
         if (tid < 64) P.att[(size_t)b * d + h * 64 + tid] = __float2half_rn(o / l);
     } else {

@@ -54,6 +54,9 @@ constexpr int kMaxJ = 5;              // flagged pairs per thread and poll batch
 #ifndef SS_XEXP_INLINE
 #define SS_XEXP_INLINE 0     // cross-attention: exp(s - m) inside the P.V loop instead of a separate pass + barrier (slower)
 #endif
+#ifndef SS_XMMA
+#define SS_XMMA 1            // cross-attention scores and P.V on the tensor cores (ldmatrix from the swizzled cross-KV rows)
+#endif
 #ifndef SS_XATTN8
 #define SS_XATTN8 0          // cross-attention: 8 lanes per key row (scores and P.V), 0: one thread per key / one lane per channel pair
 #endif
@@ -557,7 +560,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
 // scores of one query against n key rows (128 B each) at `K`: 8 lanes per row, 4 rows per warp per step.
 // FROM_RING: rows come from a ring slot (shared memory), else from L2 with 4 rows per thread in flight.
 template <bool FROM_RING>
-__device__ __forceinline__ float attn_scores(const uint8_t *K, int n, int sc_base, const float4 &qa, const float4 &qb, float lmax) {
+__device__ __forceinline__ float attn_scores(const uint8_t *K, int n, int sc_base, const float4 &qa, const float4 &qb, float lmax, int row0 = -1) {
     MegaSmem &sm = SM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
     for (int jb = 0; jb < n; jb += 128) {
@@ -565,7 +568,7 @@ __device__ __forceinline__ float attn_scores(const uint8_t *K, int n, int sc_bas
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int j = jb + u * 32 + warp * 4 + sub;
-            if (j < n) kv[u] = FROM_RING ? *reinterpret_cast<const uint4 *>(K + (size_t)j * 128 + l8 * 16) : __ldcg(reinterpret_cast<const uint4 *>(K + (size_t)j * 128 + l8 * 16));
+            if (j < n) kv[u] = FROM_RING ? *reinterpret_cast<const uint4 *>(K + (size_t)j * 128 + ((row0 >= 0 ? l8 ^ ((row0 + j) & 7) : l8) << 4)) : __ldcg(reinterpret_cast<const uint4 *>(K + (size_t)j * 128 + l8 * 16));
             else kv[u] = make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
@@ -602,15 +605,16 @@ __device__ __forceinline__ void attn_pv(const uint8_t *V, int n, int sc_base, fl
 // ---- cross-attention out of a ring slot: one thread per key for the scores (its 128-byte row is read as eight 16-byte
 // pieces in an order rotated by the key index: the 32 lanes of a load touch every bank group equally), one lane per
 // channel pair and one warp per key residue for P.V
-__device__ __forceinline__ float xattn_scores(const uint8_t *K, int n, int sc_base, float lmax) {
+__device__ __forceinline__ float xattn_scores(const uint8_t *K, int n, int sc_base, float lmax, int row0) {
     MegaSmem &sm = SM;
     for (int j = threadIdx.x; j < n; j += kConsumerThreads) {
         const uint8_t *row = K + (size_t)j * 128;
+        const int sw = (row0 + j) & 7;      // chunk c of key m sits at position c ^ (m & 7) (cross-KV cache layout)
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
             const int c0 = (c + j) & 7, c1 = (c + 1 + j) & 7;
-            const uint4 k0 = *reinterpret_cast<const uint4 *>(row + c0 * 16), k1 = *reinterpret_cast<const uint4 *>(row + c1 * 16);
+            const uint4 k0 = *reinterpret_cast<const uint4 *>(row + (c0 ^ sw) * 16), k1 = *reinterpret_cast<const uint4 *>(row + (c1 ^ sw) * 16);
             a0 = dot8(k0, *reinterpret_cast<const float4 *>(sm.qkv + c0 * 8), *reinterpret_cast<const float4 *>(sm.qkv + c0 * 8 + 4), a0);
             a1 = dot8(k1, *reinterpret_cast<const float4 *>(sm.qkv + c1 * 8), *reinterpret_cast<const float4 *>(sm.qkv + c1 * 8 + 4), a1);
         }
@@ -620,42 +624,44 @@ __device__ __forceinline__ float xattn_scores(const uint8_t *K, int n, int sc_ba
     }
     return lmax;
 }
-__device__ __forceinline__ void xattn_pv_p(const uint8_t *V, int n, int sc_base, float &o0, float &o1) {
+__device__ __forceinline__ void xattn_pv_p(const uint8_t *V, int n, int sc_base, float &o0, float &o1, int row0) {
     MegaSmem &sm = SM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint8_t *col = V + lane * 4;
+    const int cch = lane >> 2, cin = (lane & 3) * 4;      // this lane's channel pair: chunk cch, byte cin inside it
+    auto vptr = [&](int j) { return V + (size_t)j * 128 + ((cch ^ ((row0 + j) & 7)) << 4) + cin; };
     float b0 = 0.f, b1 = 0.f;
     int j = warp;
     for (; j + 8 < n; j += 16) {
-        const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)), vb = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)(j + 8) * 128));
+        const float2 va = h2f(*reinterpret_cast<const uint32_t *>(vptr(j))), vb = h2f(*reinterpret_cast<const uint32_t *>(vptr(j + 8)));
         const float pa = sm.sc[sc_base + j], pb = sm.sc[sc_base + j + 8];
         o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); b0 = fmaf(pb, vb.x, b0); b1 = fmaf(pb, vb.y, b1);
     }
-    if (j < n) { const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)); const float pa = sm.sc[sc_base + j]; o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); }
+    if (j < n) { const float2 va = h2f(*reinterpret_cast<const uint32_t *>(vptr(j))); const float pa = sm.sc[sc_base + j]; o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); }
     o0 += b0; o1 += b1;
 }
 
 // P.V with the soft-max numerator computed in place: every lane of a warp turns the warp's raw scores into exp(s - m) itself
 // (one MUFU per key and lane), so no separate exp pass / barrier; `lsum` accumulates the warp's share of the denominator
-__device__ __forceinline__ void xattn_pv(const uint8_t *V, int n, int sc_base, float m, float &o0, float &o1, float &lsum) {
+__device__ __forceinline__ void xattn_pv(const uint8_t *V, int n, int sc_base, float m, float &o0, float &o1, float &lsum, int row0) {
     MegaSmem &sm = SM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint8_t *col = V + lane * 4;
+    const int cch = lane >> 2, cin = (lane & 3) * 4;      // this lane's channel pair: chunk cch, byte cin inside it
+    auto vptr = [&](int j) { return V + (size_t)j * 128 + ((cch ^ ((row0 + j) & 7)) << 4) + cin; };
     float b0 = 0.f, b1 = 0.f, l1 = 0.f;
     int j = warp;
     for (; j + 8 < n; j += 16) {
-        const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)), vb = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)(j + 8) * 128));
+        const float2 va = h2f(*reinterpret_cast<const uint32_t *>(vptr(j))), vb = h2f(*reinterpret_cast<const uint32_t *>(vptr(j + 8)));
         const float pa = __expf(sm.sc[sc_base + j] - m), pb = __expf(sm.sc[sc_base + j + 8] - m);
         lsum += pa; l1 += pb;
         o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); b0 = fmaf(pb, vb.x, b0); b1 = fmaf(pb, vb.y, b1);
     }
-    if (j < n) { const float2 va = h2f(*reinterpret_cast<const uint32_t *>(col + (size_t)j * 128)); const float pa = __expf(sm.sc[sc_base + j] - m); lsum += pa; o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); }
+    if (j < n) { const float2 va = h2f(*reinterpret_cast<const uint32_t *>(vptr(j))); const float pa = __expf(sm.sc[sc_base + j] - m); lsum += pa; o0 = fmaf(pa, va.x, o0); o1 = fmaf(pa, va.y, o1); }
     o0 += b0; o1 += b1; lsum += l1;
 }
 
 // 8 lanes per key row, 4 rows per warp and step (as attn_scores); exp(s - m) in place; every lane of an 8-lane group adds the
 // same numerators, so `lsum` is the group's share of the denominator
-__device__ __forceinline__ void xattn_pv8(const uint8_t *V, int n, int sc_base, float m, float (&acc)[8], float &lsum) {
+__device__ __forceinline__ void xattn_pv8(const uint8_t *V, int n, int sc_base, float m, float (&acc)[8], float &lsum, int row0) {
     MegaSmem &sm = SM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
     for (int jb = 0; jb < n; jb += 128) {
@@ -663,11 +669,78 @@ __device__ __forceinline__ void xattn_pv8(const uint8_t *V, int n, int sc_base, 
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int j = jb + u * 32 + warp * 4 + sub;
-            if (j < n) { vv[u] = *reinterpret_cast<const uint4 *>(V + (size_t)j * 128 + l8 * 16); pp[u] = __expf(sm.sc[sc_base + j] - m); }
+            if (j < n) { vv[u] = *reinterpret_cast<const uint4 *>(V + (size_t)j * 128 + ((l8 ^ ((row0 + j) & 7)) << 4)); pp[u] = __expf(sm.sc[sc_base + j] - m); }
             else { vv[u] = make_uint4(0, 0, 0, 0); pp[u] = 0.f; }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) { lsum += pp[u]; axpy8(vv[u], pp[u], acc); }
+    }
+}
+// ---- cross-attention on the tensor cores.  A slot holds n key (value) rows of 128 bytes in cache layout: chunk c of key m at
+// position c ^ (m & 7), so the 8 rows of an ldmatrix 8x8 tile hit 8 different 16-byte bank groups.
+// scores: m16n8k16 tiles = {16 keys} x {q replicated on the 8 columns}; warp w takes key tiles w, w + 8, ...; thread (g, t) ends
+// up with the score of key g (c0) and key g + 8 (c2) of the tile.
+__device__ __forceinline__ float xmma_scores(const uint8_t *K, int n, int sc_base, float lmax, int row0, const uint32_t (&qb)[8]) {
+    MegaSmem &sm = SM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t kb = smem_u32(K);
+    const int lr = (lane & 7) + ((lane >> 3) & 1) * 8, lc = lane >> 4;      // ldmatrix.x4: this lane addresses row lr, chunk 2s + lc
+    for (int i = warp; i * 16 < n; i += kConsumerWarps) {
+        const int r = 16 * i + lr, sw = (row0 + r) & 7;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t a[4][4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++)      // all four loads in flight before the first mma
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(a[s4][0]), "=r"(a[s4][1]), "=r"(a[s4][2]), "=r"(a[s4][3]) : "r"(kb + (uint32_t)r * 128u + (uint32_t)(((2 * s4 + lc) ^ sw) << 4)));
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4 += 2) {   // two accumulator chains
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[s4][0]), "r"(a[s4][1]), "r"(a[s4][2]), "r"(a[s4][3]), "r"(qb[2 * s4]), "r"(qb[2 * s4 + 1]));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(c2[0]), "+f"(c2[1]), "+f"(c2[2]), "+f"(c2[3]) : "r"(a[s4 + 1][0]), "r"(a[s4 + 1][1]), "r"(a[s4 + 1][2]), "r"(a[s4 + 1][3]), "r"(qb[2 * s4 + 2]), "r"(qb[2 * s4 + 3]));
+        }
+        c[0] += c2[0]; c[2] += c2[2];
+        if (t == 0) {
+            const int j0 = 16 * i + g, j1 = j0 + 8;
+            if (j0 < n) { sm.sc[sc_base + j0] = c[0]; lmax = fmaxf(lmax, c[0]); }
+            if (j1 < n) { sm.sc[sc_base + j1] = c[2]; lmax = fmaxf(lmax, c[2]); }
+        }
+    }
+    return lmax;
+}
+// P.V: m16n8k16 with A = the probabilities (row 0 of the tile, f16 like ggml's mat-mul operand; rows 1..15 zero), B = 16 value rows x
+// 8 channels through ldmatrix.trans; warp w takes key blocks w, w + 8, ...; lanes 0..3 end up with channels 8 nt + 2 t, + 1.
+__device__ __forceinline__ void xmma_pv(const uint8_t *V, int n, int sc_base, int row0, float (&o)[8][4]) {
+    MegaSmem &sm = SM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t vb = smem_u32(V);
+    const int lr = (lane & 7) + ((lane >> 3) & 1) * 8, lc = lane >> 4;
+    for (int ks = warp; ks * 16 < n; ks += kConsumerWarps) {
+        const int k0 = 16 * ks + 2 * t;
+        uint32_t a0 = 0u, a2 = 0u;
+        if (g == 0) {
+            const float p0 = k0 < n ? sm.sc[sc_base + k0] : 0.f, p1 = k0 + 1 < n ? sm.sc[sc_base + k0 + 1] : 0.f;
+            const float p2 = k0 + 8 < n ? sm.sc[sc_base + k0 + 8] : 0.f, p3 = k0 + 9 < n ? sm.sc[sc_base + k0 + 9] : 0.f;
+            const __half2 h0 = __floats2half2_rn(p0, p1), h2 = __floats2half2_rn(p2, p3);
+            a0 = *reinterpret_cast<const uint32_t *>(&h0); a2 = *reinterpret_cast<const uint32_t *>(&h2);
+        }
+        // rows past the end of the slice hold whatever the ring slot held before (possibly NaN bit patterns): 0 * NaN must not happen
+        const uint32_t m0 = (k0 < n ? 0x0000ffffu : 0u) | (k0 + 1 < n ? 0xffff0000u : 0u), m1 = (k0 + 8 < n ? 0x0000ffffu : 0u) | (k0 + 9 < n ? 0xffff0000u : 0u);
+        const int r = 16 * ks + lr, sw = (row0 + r) & 7;
+        uint32_t b[4][4];
+#pragma unroll
+        for (int np = 0; np < 4; np++)      // all four loads in flight before the first mma
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(b[np][0]), "=r"(b[np][1]), "=r"(b[np][2]), "=r"(b[np][3]) : "r"(vb + (uint32_t)r * 128u + (uint32_t)(((2 * np + lc) ^ sw) << 4)));
+#pragma unroll
+        for (int np = 0; np < 4; np++) {
+            b[np][0] &= m0; b[np][1] &= m1; b[np][2] &= m0; b[np][3] &= m1;
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(o[2 * np][0]), "+f"(o[2 * np][1]), "+f"(o[2 * np][2]), "+f"(o[2 * np][3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b[np][0]), "r"(b[np][1]));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(o[2 * np + 1][0]), "+f"(o[2 * np + 1][1]), "+f"(o[2 * np + 1][2]), "+f"(o[2 * np + 1][3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b[np][2]), "r"(b[np][3]));
+        }
     }
 }
 // fold the per-lane P.V partial sums of the CTA into 64 channel sums (thread c < 64 returns channel c)
@@ -910,16 +983,27 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     trace_mark(-1);
     SS_STAGE(SEG_XK, 0)
     float lmax = -INFINITY;
+    uint32_t qfrag[8];      // (SS_XMMA) B fragments of q: k-step s4 covers dims 16 s4 .. 16 s4 + 15; q values are f16-valued
+    {
+        const int t = lane & 3;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; s4++) {
+            const __half2 h0 = __floats2half2_rn(sm.qkv[16 * s4 + 2 * t], sm.qkv[16 * s4 + 2 * t + 1]);
+            const __half2 h1 = __floats2half2_rn(sm.qkv[16 * s4 + 2 * t + 8], sm.qkv[16 * s4 + 2 * t + 9]);
+            qfrag[2 * s4] = *reinterpret_cast<const uint32_t *>(&h0); qfrag[2 * s4 + 1] = *reinterpret_cast<const uint32_t *>(&h1);
+        }
+    }
     for (int ch = 0; ch < sk.n_chunks; ch++) {
         const int slot = cons % kSlots;
         if (prof_on) { const long long tw0 = clock64(); mbar_wait(&sm.full[slot], (cons / kSlots) & 1); sm.prof[14] += clock64() - tw0; }
         else mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
-        if (SS_XATTN8) {
+        if (SS_XMMA) lmax = xmma_scores(sm.ring[slot], nk, kbase, lmax, sk.row0 + kbase, qfrag);
+        else if (SS_XATTN8) {
             const int l8 = lane & 7;
             const float4 qa = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8), qb = *reinterpret_cast<const float4 *>(sm.qkv + l8 * 8 + 4);
-            lmax = attn_scores<true>(sm.ring[slot], nk, kbase, qa, qb, lmax);
-        } else lmax = xattn_scores(sm.ring[slot], nk, kbase, lmax);
+            lmax = attn_scores<true>(sm.ring[slot], nk, kbase, qa, qb, lmax, sk.row0 + kbase);
+        } else lmax = xattn_scores(sm.ring[slot], nk, kbase, lmax, sk.row0 + kbase);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
@@ -929,20 +1013,24 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     const float m = consumer_max(lmax);        // its barrier also publishes the raw scores
     trace_mark(81);      // max
     float l_cta = 0.f;
-    if (!SS_XEXP_INLINE) {
+    if (SS_XMMA || !SS_XEXP_INLINE) {
         float ls = 0.f;
         for (int j = tid; j < n; j += kConsumerThreads) { const float e = __expf(sm.sc[j] - m); sm.sc[j] = e; ls += e; }
         l_cta = consumer_sum(ls);        // its barrier also publishes the probabilities
     }
     SS_STAGE(SEG_XK, 2)
     float o0 = 0.f, o1 = 0.f, lsum = 0.f, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float om[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { om[i][0] = 0.f; om[i][1] = 0.f; om[i][2] = 0.f; om[i][3] = 0.f; }
     for (int ch = 0; ch < sk.n_chunks; ch++) {     // the V slice has the same chunking as the K slice
         const int slot = cons % kSlots;
         mbar_wait(&sm.full[slot], (cons / kSlots) & 1);
         const int kbase = ch * sk.rows_per_chunk, nk = min(sk.rows_per_chunk, n - kbase);
-        if (SS_XATTN8) xattn_pv8(sm.ring[slot], nk, kbase, m, acc, lsum);
-        else if (SS_XEXP_INLINE) xattn_pv(sm.ring[slot], nk, kbase, m, o0, o1, lsum);
-        else xattn_pv_p(sm.ring[slot], nk, kbase, o0, o1);
+        if (SS_XMMA) xmma_pv(sm.ring[slot], nk, kbase, sk.row0 + kbase, om);
+        else if (SS_XATTN8) xattn_pv8(sm.ring[slot], nk, kbase, m, acc, lsum, sk.row0 + kbase);
+        else if (SS_XEXP_INLINE) xattn_pv(sm.ring[slot], nk, kbase, m, o0, o1, lsum, sk.row0 + kbase);
+        else xattn_pv_p(sm.ring[slot], nk, kbase, o0, o1, sk.row0 + kbase);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[slot]);
         cons++;
@@ -950,7 +1038,14 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     SS_STAGE(SEG_XK, 3)
     trace_mark(82);      // P.V
     float o = 0.f;
-    if (SS_XATTN8) {
+    if (SS_XMMA) {
+        if (lane < 4) {      // row 0 of the accumulator tiles: channels 8 nt + 2 lane, + 1
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) *reinterpret_cast<float2 *>(&sm.red[tid >> 5][8 * nt + 2 * lane]) = make_float2(om[nt][0], om[nt][1]);
+        }
+        consumer_sync();
+        if (tid < 64) for (int w = 0; w < kConsumerWarps; w++) o += sm.red[w][tid];
+    } else if (SS_XATTN8) {
         lsum += __shfl_xor_sync(0xffffffffu, lsum, 8); lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
         if (lane == 0) sm.red2[tid >> 5].x = lsum;
         o = attn_fold(acc);
@@ -964,7 +1059,7 @@ __device__ __noinline__ uint32_t cross_attn(uint32_t cons, uint32_t ep) {
     if (tid < 64) ll_store(out + 2 + tid, o, ep);
     if (tid == 0) {
         float l = l_cta;
-        if (SS_XEXP_INLINE || SS_XATTN8) { l = 0.f; for (int w = 0; w < kConsumerWarps; w++) l += sm.red2[w].x; }
+        if (!SS_XMMA && (SS_XEXP_INLINE || SS_XATTN8)) { l = 0.f; for (int w = 0; w < kConsumerWarps; w++) l += sm.red2[w].x; }
         ll_store(out, m, ep); ll_store(out + 1, l, ep);
     }
     trace_mark(83);      // fold + stores

@@ -170,9 +170,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
                     for (int j = 0; j < 32; j++) if (j < nvalid) v[j] += __ldg(pr + j);
                 }
                 long idx;
-                if (EPI == EPI_F16_HEADMAJOR) idx = ((long)(nb >> 6) * p.head_rows + m) * 64 + (nb & 63) + zoff;
+                if (EPI == EPI_F16_HEADMAJOR) idx = ((long)(nb >> 6) * p.head_rows + m) * 64 + zoff;      // start of row m of head nb / 64
                 else idx = (long)(m + p.out_row_offset) * p.out_ld + nb + zoff;
-                if (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU || EPI == EPI_F16_HEADMAJOR) {
+                if (EPI == EPI_F16_HEADMAJOR) {
+                    // cross-KV cache row: 64 halfs = eight 16-byte chunks, chunk c stored at position c ^ (m & 7) - the layout the
+                    // decoders' ldmatrix reads want (8 consecutive rows of one chunk column fall into 8 different bank groups)
+                    __half *o = reinterpret_cast<__half *>(p.out) + idx;
+                    const int sw = m & 7, c0 = (nb & 63) >> 3;
+                    if (nvalid == 32 && (nb & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                            uint4 u;
+                            u.x = *reinterpret_cast<uint32_t *>(&h0); u.y = *reinterpret_cast<uint32_t *>(&h1);
+                            u.z = *reinterpret_cast<uint32_t *>(&h2); u.w = *reinterpret_cast<uint32_t *>(&h3);
+                            *reinterpret_cast<uint4 *>(o + (((c0 + (j >> 3)) ^ sw) << 3)) = u;
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid; j++) { const int e = (nb & 63) + j; o[(((e >> 3) ^ sw) << 3) | (e & 7)] = __float2half_rn(v[j]); }
+                    }
+                } else if (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU) {
                     __half *o = reinterpret_cast<__half *>(p.out) + idx;
                     if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll

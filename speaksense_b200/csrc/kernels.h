@@ -47,7 +47,8 @@ struct GemmEpilogue {
     int out_type = GEMM_OUT_F16;
     void *out = nullptr;
     long out_ld = 0, out_stride0 = 0, out_stride1 = 0;   // elements
-    int head_major = 0;              // out index = ((n/64) * head_rows + m) * 64 + n%64 (+ batch strides)
+    int head_major = 0;              // cross-KV cache layout: row = (n/64) * head_rows + m, 64 halfs per row as eight 16-byte chunks with
+                                     // chunk c of row m at position c ^ (m & 7) (+ batch strides)
     long head_rows = 0;
     int out_row_offset = 0;          // rows shift (padded conv layouts)
     int a_broadcast = 0;             // A has no batch dimension (B / bias / out do)
