@@ -528,10 +528,11 @@ void gemm_enqueue(const GemmOperand &A, const GemmOperand &B, int M, int N, int 
     // CTA pairs (SS_GEMM_2CTA, on by default): rounds of the persistent grid of sms / 2 pairs x relative tile cost per CTA
     // (a 256 x 128 pair tile costs each CTA what a 128 x 128 tile does, with 24 instead of 32 KB of operands per k-step;
     //  256 x 256: the work of a 128 x 256 tile with 32 instead of 48 KB)
-    static const bool pair_on = [] { const char *e = getenv("SS_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+    const char *pair_env = getenv("SS_GEMM_2CTA");      // "0": never, "2": whenever the shape allows (tests), else: by the rule below
+    const bool pair_on = !(pair_env && pair_env[0] == '0'), pair_force = pair_env && pair_env[0] == '2';
     // measured (large-v3 encoder): one clip (M = 1500, <= 240 tiles): 5.32 ms per window with 1-CTA tiles, 5.45 ms with pairs; the
     // batched pass of 32 clips (M = 48000): 103 ms vs 100 ms - pairs pay once a GEMM has several waves of tiles
-    if (pair_on && g_sms >= 2 && M > BM && t256 >= 4l * g_sms) {
+    if (pair_on && g_sms >= 2 && M > BM && (pair_force || t256 >= 4l * g_sms)) {
         const int np = g_sms / 2;
         const long p128 = (long)ceil_div(N, 128) * ceil_div(M, 2 * BM) * p.nbatch, p256 = (long)ceil_div(N, 256) * ceil_div(M, 2 * BM) * p.nbatch;
         const double d128 = (double)ceil_div<long>(p128, np), d256 = 1.6 * (double)ceil_div<long>(p256, np);

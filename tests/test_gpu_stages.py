@@ -81,3 +81,26 @@ def test_decoder_teacher_forced(pair, audio30):
         worst = max(worst, np.abs(lg - ref).max())
         assert lg.argmax() == ref.argmax() or np.sort(ref)[-1] - np.sort(ref)[-2] < 2 * LOGIT_TOL
     assert worst < LOGIT_TOL, worst
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_encoder_on_both_gemm_kernels(oracle_mod, tiny_en_peaked, audio30, mode, monkeypatch):
+    """the encoder through the 1-CTA tcgen05 GEMM only (SS_GEMM_2CTA=0) and through the CTA-pair kernel (cta_group::2, 256-row
+    tiles) wherever the shape allows (SS_GEMM_2CTA=2; by default pairs are used for multi-wave GEMMs only, i.e. the batched pass):
+    every fused epilogue (f16 bias, f16 GELU, f32 residual, f32 GELU + positional add, head-major cross-KV) against the oracle"""
+    from speaksense_b200 import AsrParams, WhisperAsr
+    monkeypatch.setenv("SS_GEMM_2CTA", mode)
+    om = oracle_mod.OracleModel(tiny_en_peaked)
+    eng = WhisperAsr(tiny_en_peaked)
+    st = eng.create_state()
+    eng.log_mel(st, audio30)
+    enc = eng.encode(st, 0)
+    ost = om.new_state()
+    mel, _, _ = om.log_mel(audio30)
+    ref = ost.encode(mel, 0)
+    assert np.abs(enc - ref).max() < ENC_TOL
+    toks = np.array([50257, 50362, 1000, 2000, 3000], np.int32)      # cross-KV through the decoder: teacher-forced logits
+    got = eng.decode(st, toks, 0)
+    want = ost.decode(toks.tolist(), 0)
+    assert np.abs(got - want).max() < LOGIT_TOL
+    st.close(); eng.close(); ost.close(); om.close()
