@@ -429,6 +429,23 @@ def main():
                 line["next_rows"]["batch32"] = {"workload": b["workload"], "rtf_host_buffers": b["batched"]["rtf"],
                                                 "wall_s": b["batched"]["wall_s"], "tokens": b["batched"]["tokens"],
                                                 "decode_ms": b["batched"]["decode_ms"], "gpu_launches": b["batched"]["launches"]}
+                # roofline of the batched decoder step (HBM): weights once + 32 x (cross-KV + self-KV) per step
+                nb, ntok = 32, b["batched"]["tokens"] / 32.0
+                n_steps = ntok + 3 - 1      # prompt [sot, lang, transcribe] + sampled tokens
+                w_only = decode_bytes_per_token(info, 0.0) - 2.0 * 2 * info["n_text_layer"] * 1500 * info["n_audio_state"]
+                per_seq = 2.0 * 2 * info["n_text_layer"] * (1500 + ntok / 2.0) * info["n_audio_state"]
+                step_bytes = w_only + nb * per_seq
+                step_ms = b["batched"]["decode_ms"] / n_steps
+                line["next_rows"]["batch32"]["roofline"] = {
+                    "bound": "hbm", "kernel": "batched decoder step (bd_* kernels of csrc/decoder_batch.cu, one CUDA graph per step)",
+                    "algorithmic_bytes_per_step": step_bytes, "ms_per_step": step_ms, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak}
+                enc_ms_b = b["batched"].get("mel_encode_host_ms")
+                if enc_ms_b:
+                    line["next_rows"]["batch32"]["roofline_encoder"] = {
+                        "bound": "tensor", "flops": nb * enc_flops, "ms_log_mel_plus_encoder_pass": enc_ms_b,
+                        "achieved": nb * enc_flops / (enc_ms_b * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                        "frac": nb * enc_flops / (enc_ms_b * 1e-3) / 1e12 / tpeak}
             except Exception as ex:   # noqa: BLE001
                 line["next_rows"]["batch32"] = {"error": str(ex)[:200]}
             # row a9 measured: a clip that walks the temperature ladder (n_fallbacks > 0), device-sampled against host-sampled

@@ -210,6 +210,31 @@ class OracleState:
             raise OracleError("wo_probe_process_logits rc=%d" % rc)
         return out
 
+    def bookkeeping(self, ids, seek=0, seek_end=3000, n_max=220, **over) -> dict:
+        """whisper_full's per-token decoder bookkeeping replayed over `ids` (test probe)"""
+        P = WoParams()
+        self.L.wo_default_params(C.byref(P))
+        for k, v in over.items():
+            setattr(P, k, v)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        out = (C.c_int * 6)()
+        self.L.wo_probe_bookkeeping.argtypes = [C.c_void_p, C.POINTER(WoParams), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        self.L.wo_probe_bookkeeping(self.h, C.byref(P), ids.ctypes.data, ids.size, seek, seek_end, n_max, out)
+        return dict(failed=bool(out[0]), completed=bool(out[1]), result_len=out[2], seek_delta=out[3], has_ts=bool(out[4]), steps=out[5])
+
+    def score(self, ids, plogs, result_len, **over) -> dict:
+        """whisper_sequence_score + the entropy statistic of the fallback gate (test probe)"""
+        P = WoParams()
+        self.L.wo_default_params(C.byref(P))
+        for k, v in over.items():
+            setattr(P, k, v)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        plogs = np.ascontiguousarray(plogs, dtype=np.float32)
+        out = (C.c_double * 4)()
+        self.L.wo_probe_score.argtypes = [C.c_void_p, C.POINTER(WoParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self.L.wo_probe_score(self.h, C.byref(P), ids.ctypes.data, plogs.ctypes.data, ids.size, result_len, out)
+        return dict(sum_logprobs=out[0], avg_logprobs=out[1], entropy=out[2], score=out[3])
+
     def kept_logits(self) -> np.ndarray:
         n = self.L.wo_n_kept_logits(self.h)
         nv = self.m.hparams["n_vocab"]

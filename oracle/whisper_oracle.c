@@ -1015,6 +1015,55 @@ static void sequence_score(const wo_params *P, sequence_t *q) {
     }
 }
 
+/* whisper_full's per-token decoder bookkeeping for the token `id` sampled at step i of a window: the timestamp
+ * / seek_delta / result_len update, the completion rule (EOT, max_tokens, a timestamp within 1 s of the end of the audio) and the
+ * two failure rules (timestamps going backwards; the token cap reached without a usable timestamp).  Used by wo_full and by the
+ * wo_probe_bookkeeping test probe. */
+static void token_bookkeeping(const wo_model *m, const wo_params *P, decoder_t *dc, int id, int i, int seek, int seek_end, int n_max) {
+    if (id > m->beg) {
+        const int sd_new = 2 * (id - m->beg);
+        if (dc->has_ts && dc->seek_delta > sd_new && dc->seq.result_len < i) { dc->failed = 1; return; }
+        dc->seek_delta = sd_new; dc->seq.result_len = i + 1; dc->has_ts = 1;
+    }
+    if (id == m->eot || (P->max_tokens > 0 && i >= P->max_tokens) || (dc->has_ts && seek + dc->seek_delta + 100 >= seek_end)) {
+        if (dc->seq.result_len == 0) {
+            if (seek + dc->seek_delta + 100 >= seek_end) dc->seq.result_len = i + 1;
+            else { dc->failed = 1; return; }
+        }
+        if (P->single_segment) { dc->seq.result_len = i + 1; dc->seek_delta = 100 * WO_CHUNK; }
+        dc->completed = 1; return;
+    }
+    if (i == n_max - 1 && (dc->seq.result_len == 0 || dc->seek_delta < 100 * WO_CHUNK / 2)) { dc->failed = 1; return; }
+}
+
+/* test probe: token_bookkeeping over a given list of sampled ids (decoder state as at the start of a window);
+ * out = {failed, completed, result_len, seek_delta, has_ts, steps consumed} */
+int wo_probe_bookkeeping(wo_state *s, const wo_params *P, const int *ids, int n, int seek, int seek_end, int n_max, int *out) {
+    decoder_t tmp; memset(&tmp, 0, sizeof tmp);
+    tmp.seek_delta = 100 * WO_CHUNK;
+    int i = 0;
+    for (; i < n && i < n_max; i++) {
+        token_bookkeeping(s->m, P, &tmp, ids[i], i, seek, seek_end, n_max);
+        if (tmp.failed || tmp.completed) { i++; break; }
+    }
+    out[0] = tmp.failed; out[1] = tmp.completed; out[2] = tmp.seq.result_len; out[3] = tmp.seek_delta; out[4] = tmp.has_ts; out[5] = i;
+    return 0;
+}
+
+/* test probe: sequence_score (whisper_sequence_score + the entropy of the last 32 tokens) on given ids / log-probs;
+ * out = {sum_logprobs, avg_logprobs, entropy, score} */
+int wo_probe_score(wo_state *s, const wo_params *P, const int *ids, const float *plogs, int n, int result_len, double *out) {
+    (void)s;
+    sequence_t q; memset(&q, 0, sizeof q);
+    q.tokens = (tokdata_t *)calloc((size_t)(n > 0 ? n : 1), sizeof(tokdata_t));
+    for (int i = 0; i < n; i++) { q.tokens[i].id = ids[i]; q.tokens[i].plog = plogs[i]; }
+    q.n = n; q.result_len = result_len;
+    sequence_score(P, &q);
+    out[0] = q.sum_logprobs; out[1] = q.avg_logprobs; out[2] = q.entropy; out[3] = q.score;
+    free(q.tokens);
+    return 0;
+}
+
 static void kv_seq_copy(wo_state *s, int from, int to) {
     if (from == to) return;
     const wo_hparams *hp = &s->m->hp;
@@ -1188,22 +1237,7 @@ int wo_full(wo_state *s, const float *pcm, size_t n_samples, const wo_params *P)
                 for (int j = 0; j < n_cur; j++) {
                     decoder_t *dc = &s->dec[j];
                     if (dc->completed || dc->failed) continue;
-                    const tokdata_t *tk = &dc->seq.tokens[dc->seq.n - 1];
-                    if (tk->id > m->beg) {
-                        const int sd_new = 2 * (tk->id - m->beg);
-                        if (dc->has_ts && dc->seek_delta > sd_new && dc->seq.result_len < i) { dc->failed = 1; continue; }
-                        dc->seek_delta = sd_new; dc->seq.result_len = i + 1; dc->has_ts = 1;
-                    }
-                    if (tk->id == m->eot || (P->max_tokens > 0 && i >= P->max_tokens) ||
-                        (dc->has_ts && seek + dc->seek_delta + 100 >= seek_end)) {
-                        if (dc->seq.result_len == 0) {
-                            if (seek + dc->seek_delta + 100 >= seek_end) dc->seq.result_len = i + 1;
-                            else { dc->failed = 1; continue; }
-                        }
-                        if (P->single_segment) { dc->seq.result_len = i + 1; dc->seek_delta = 100 * WO_CHUNK; }
-                        dc->completed = 1; continue;
-                    }
-                    if (i == n_max - 1 && (dc->seq.result_len == 0 || dc->seek_delta < 100 * WO_CHUNK / 2)) { dc->failed = 1; continue; }
+                    token_bookkeeping(m, P, dc, dc->seq.tokens[dc->seq.n - 1].id, i, seek, seek_end, n_max);
                 }
                 {
                     int all = 1;

@@ -100,6 +100,11 @@ long   wo_n_draws(const wo_state *s);
 int  wo_probe_process_logits(wo_state *s, const wo_params *p, const int *ids, int n_ids, int has_ts, int seek_delta,
                              const float *raw, float temperature, float *logits_out);
 
+/* test probes: whisper_full's per-token bookkeeping over a list of sampled ids (out = failed, completed, result_len, seek_delta,
+ * has_ts, steps consumed) and whisper_sequence_score + the entropy gate's statistic (out = sum_logprobs, avg_logprobs, entropy, score) */
+int  wo_probe_bookkeeping(wo_state *s, const wo_params *p, const int *ids, int n, int seek, int seek_end, int n_max, int *out);
+int  wo_probe_score(wo_state *s, const wo_params *p, const int *ids, const float *plogs, int n, int result_len, double *out);
+
 /* test probe: draws of the restated std::mt19937 + std::discrete_distribution<> pair */
 int  wo_probe_sample(wo_state *s, uint32_t seed, const float *probs, int n, int count, int *out);
 
