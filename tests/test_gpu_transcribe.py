@@ -184,3 +184,31 @@ def test_turbo_like_asymmetric_layers(oracle_mod, audio30):
     assert toks == ref["tokens"] and len(toks) > 10
     assert float(np.abs(st.debug_logits() - ost.kept_logits()).max()) < 1e-2
     ost.close(); om.close(); st.close(); eng.close()
+
+
+def test_token_cap_then_context_window(oracle_mod, tmp_path):
+    """a window that ends on the 220-token cap (not on EOT / the completion rule) followed by a window prompted with [prev] + 209
+    context tokens: the device-side cap rule of decode_mega_kernel and the long prompt against the oracle, token for token (the
+    oracle itself is held to an HF-built golden on this case: tests/test_oracle_golden.py)"""
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    path = str(tmp_path / "ggml-tiny.en-peaked-seg175.bin")
+    synth.write_model(path, "tiny.en", "peaked", 0, seg_ticks=175)
+    pcm = synth.synth_audio(45 * 16000, seed=1234)
+    om = oracle_mod.OracleModel(path)
+    ost = om.new_state()
+    ref = ost.full(pcm, stream_mode=False)
+    assert ref["n_windows"] == 2 and len(ref["tokens"]) == 209 + 24
+    eng = WhisperAsr(path)
+    st = eng.create_state()
+    eng.transcribe_with_state(st, pcm, AsrParams(stream_mode=False))
+    assert st.result_tokens()[0] == ref["tokens"]
+    assert [(s["t0"], s["t1"], s["text"]) for s in st.raw_segments()] == [(s["t0"], s["t1"], s["text"]) for s in ref["segments"]]
+    assert st.stats()["n_windows"] == 2 and st.stats()["n_fallbacks"] == 0
+    # the same through the batched path (two such clips + two ordinary ones: sequences with different prompt lengths in one round)
+    clips = [pcm, synth.synth_audio(seed=7), pcm, synth.synth_audio(20 * 16000, seed=8)]
+    sts = [eng.create_state() for _ in clips]
+    eng.transcribe_batch(sts, clips, AsrParams(stream_mode=False))
+    assert sts[0].result_tokens()[0] == ref["tokens"] and sts[2].result_tokens()[0] == ref["tokens"]
+    for s in sts + [st]:
+        s.close()
+    eng.close(); ost.close(); om.close()
