@@ -260,3 +260,28 @@ def test_failing_clip_fails_alone_in_a_batch(batch_on, tiny_en_peaked, tmp_path)
     for st in states:
         st.close()
     eng.close()
+
+
+def test_batched_path_against_the_oracle_on_large_v3_shapes(batch_on, oracle_mod):
+    """the batched decoder step (and the batched encoder pass) against the ORACLE directly - not through the single-clip path - on every
+    large-v3 kernel shape (d = 1280, 20 heads, 128 mels, 51866 vocabulary; 2 + 2 layers): tokens, segments, teacher-forced logits"""
+    from tests.conftest import model_path
+    from speaksense_b200 import AsrParams, WhisperAsr, synth
+    path = model_path("large-v3-l2", "peaked", 0)
+    clips = [synth.synth_audio(seed=1234 + i) for i in range(3)] + [synth.synth_audio(12 * 16000, seed=5), synth.synth_audio(45 * 16000, seed=11)]
+    om = oracle_mod.OracleModel(path)
+    refs = []
+    for c in clips:
+        ost = om.new_state()
+        refs.append(ost.full(c, language="en", stream_mode=False))
+        ost.close()
+    eng = WhisperAsr(path)
+    sts = [eng.create_state() for _ in clips]
+    eng.transcribe_batch(sts, clips, AsrParams(language="en", stream_mode=False))
+    for st, r in zip(sts, refs):
+        assert st.result_tokens()[0] == r["tokens"]
+        assert [(s["t0"], s["t1"], s["text"]) for s in st.raw_segments()] == [(s["t0"], s["t1"], s["text"]) for s in r["segments"]]
+        assert st.stats()["n_fallbacks"] == r["n_fallbacks"] == 0
+        assert st.stats()["n_launches"] > 100      # the batched kernels ran
+        st.close()
+    eng.close(); om.close()
