@@ -39,6 +39,19 @@ enum : int { EPI_QKV = 0, EPI_RES, EPI_Q, EPI_GELU, EPI_LOGITS };
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Loads whose position in the instruction stream matters (issued right behind the wait, BEFORE the branch on a sequence's finished
+// flag, so that no L2 round trip waits for another): volatile asm keeps program order against the wait and against each other.
+__device__ __forceinline__ int ldp_s32(const int *p) { int v; asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ float ldp_f32(const float *p) { float v; asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+__device__ __forceinline__ unsigned short ldp_u16(const void *p) { unsigned short v; asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p)); return v; }
+template <bool STREAM>
+__device__ __forceinline__ uint4 ldp_v4(const uint4 *p) {
+    uint4 v;
+    if (STREAM) asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    else asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 __device__ __forceinline__ float gelu16(float x) {
     const float xh = r16(x);
@@ -113,20 +126,22 @@ __global__ void __launch_bounds__(kLnThreads) bd_ln_kernel(const __grid_constant
     for (int k = 0; k < kLnPer; k++) { const int i = min(tid + k * kLnThreads, d - 1); w[k] = __ldg(lw + i); bb[k] = __ldg(lb + i); }
     pdl_wait();
     const DecCtl *ctl = P.seq[b].ctl;
-    if (ctl->done) return;
     float *x = P.x + (size_t)b * d;
     float v[kLnPer];
+    if (!embed) {      // the row is requested together with the finished flag (one L2 round trip, not two)
+#pragma unroll
+        for (int k = 0; k < kLnPer; k++) v[k] = ldp_f32(x + min(tid + k * kLnThreads, d - 1));
+    }
+    const int done = ldp_s32(&ctl->done), tok = ldp_s32(&ctl->token), pos = ldp_s32(&ctl->pos);
+    if (done) return;
     float s = 0.f;
-    const int tok = ctl->token, pos = ctl->pos;
 #pragma unroll
     for (int k = 0; k < kLnPer; k++) {
         const int i = tid + k * kLnThreads;
-        v[k] = 0.f;
         if (i < d) {
             if (embed) { v[k] = __half2float(P.tok_emb[(size_t)tok * d + i]) + P.d_pos[(size_t)pos * d + i]; x[i] = v[k]; }
-            else v[k] = x[i];
             s += v[k];
-        }
+        } else v[k] = 0.f;
     }
     const float mean = block_sum<8>(s, red[0]) / (float)d;
     float s2 = 0.f;
@@ -164,12 +179,19 @@ __device__ __forceinline__ void bd_epilogue(const BatchParams &P, int il, int ro
 }
 
 constexpr int kGemmThreads = 256;
-constexpr int kGemmU = 5;      // 32-wide K blocks in flight per warp (5 KB of weights): K = 1280 split 8 ways is one round
+constexpr int kGemmU = 5;      // 32-wide K blocks per warp and round (5 KB of weights in registers): K = 1280 split 8 ways is one round
+constexpr int kGemmXD = 3;     // x blocks in flight per warp (registers; the weights of the NEXT round refill a block's registers as soon as
+                               // its products are issued, so neither operand's latency is paid once per block)
+// Latency structure (round 2, from the SASS of the first version: one L2 round trip for the finished counter, then one per K block
+// because the tail guard put every block's x loads behind the previous block's MMAs, then one HBM round trip per extra round):
+// everything the kernel needs from its predecessor is now requested right behind the wait - the counter, the live flags, the
+// residual, the first kGemmXD blocks of x - and the body of a round is branch-free (blocks past the end of a short tail multiply
+// zeroed weights), so a round costs about two dependent L2 round trips instead of six.
 template <int WR, int WK, int NT, int EPI>
-__global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_constant__ BatchParams P, const __half *__restrict__ W,
-                                                               const float *__restrict__ bias, const __half *__restrict__ X, int N, int K, int il) {
+__global__ void __launch_bounds__(kGemmThreads, 2) bd_gemm_kernel(const __grid_constant__ BatchParams P, const __half *__restrict__ W,
+                                                                  const float *__restrict__ bias, const __half *__restrict__ X, int N, int K, int il) {
     static_assert(WR * WK == 8, "8 warps per CTA");
-    constexpr int U = kGemmU;
+    constexpr int U = kGemmU, XD = kGemmXD < kGemmU ? kGemmXD : kGemmU;
     constexpr int TOTAL = WR * 16 * 8 * NT;                                   // outputs of the CTA
     constexpr int NOUT = (TOTAL + kGemmThreads - 1) / kGemmThreads;           // per thread in the epilogue
     __shared__ float red[WR][WK][8 * NT][17];
@@ -185,7 +207,7 @@ __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_cons
     uint4 a[U], c[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {      // first round of weight fragments: static data, in flight while the predecessor still runs
-        const int bi = min(blk0 + u, blk1 - 1);      // a short tail re-reads the last block; its products are skipped below
+        const int bi = min(blk0 + u, blk1 - 1);      // a short tail re-reads the last block; its products are zeroed below
         a[u] = __ldcs(wa + bi * 4); c[u] = __ldcs(wb + bi * 4);
     }
     float pb[NOUT];
@@ -196,8 +218,15 @@ __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_cons
         pb[k] = (EPI != EPI_LOGITS && idx < TOTAL && row < N) ? __ldg(bias + row) : 0.f;
     }
     pdl_wait();
-    if (*P.n_done >= P.B) return;
-    // what the epilogue needs from the predecessor (finished flags, the residual): fetched now, used after the tiles
+    // ---- what the predecessor wrote, requested all at once
+    uint4 xq[XD][NT];
+#pragma unroll
+    for (int u = 0; u < XD; u++) {
+        const int bi = min(blk0 + u, blk1 - 1);
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) xq[u][nt] = __ldg(xp + (size_t)nt * K + bi * 4);
+    }
+    const int n_done = *P.n_done;      // (all sequences finished: nothing is stored - tested after the tiles, so that no load waits for it)
     bool live[2];
     float pr[NOUT];
 #pragma unroll
@@ -215,25 +244,33 @@ __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_cons
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
     for (int blk = blk0; blk < blk1; blk += U) {
-        if (blk != blk0) {
+        const bool more = blk + U < blk1;      // (warp-uniform) another round follows
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int bi = min(blk + u, blk1 - 1);
+        for (int u = 0; u < U; u++) {
+            const bool on = blk + u < blk1;    // blocks past the end of a short tail: zero weights, so the body has no branch
+            const uint4 au = on ? a[u] : make_uint4(0u, 0u, 0u, 0u), cu = on ? c[u] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+                const uint4 xv = xq[u % XD][nt];
+                mma16816(acc[nt], au.x, cu.x, au.y, cu.y, xv.x, xv.y);
+                mma16816(acc[nt], au.z, cu.z, au.w, cu.w, xv.z, xv.w);
+            }
+            // refill slot u % XD: x of the block XD ahead in this round, else of the block of the NEXT round that uses this slot
+            // (block u' < XD of a round sits in slot u'); the weights of the same block of the next round
+            {
+                const int bx = u + XD < U ? blk + u + XD : blk + U + (u % XD);
+                if (bx < blk1) {      // (warp-uniform; nothing is fetched past the end)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++) xq[u % XD][nt] = __ldg(xp + (size_t)nt * K + bx * 4);
+                }
+            }
+            if (more) {
+                const int bi = min(blk + U + u, blk1 - 1);
                 a[u] = __ldcs(wa + bi * 4); c[u] = __ldcs(wb + bi * 4);
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (blk + u < blk1) {      // warp-uniform
-#pragma unroll
-                for (int nt = 0; nt < NT; nt++) {
-                    const uint4 xv = __ldg(xp + (size_t)nt * K + (blk + u) * 4);
-                    mma16816(acc[nt], a[u].x, c[u].x, a[u].y, c[u].y, xv.x, xv.y);
-                    mma16816(acc[nt], a[u].z, c[u].z, a[u].w, c[u].w, xv.z, xv.w);
-                }
-            }
-        }
     }
+    if (n_done >= P.B) return;
     // C fragment: c0/c1 = (row g, sequences 2t, 2t+1), c2/c3 = (row g + 8, ...)
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
@@ -259,18 +296,36 @@ __global__ void __launch_bounds__(kGemmThreads) bd_gemm_kernel(const __grid_cons
 // 8 lanes per key row (16 bytes each), 4 keys per warp and step, 4 steps in flight.
 // Returns in thread c < 64 the UNNORMALISED output channel c; m / l are the softmax maximum and sum.
 // ------------------------------------------------------------------------------------------------
+constexpr int kAttU = 4;
+// the first batch of key and value rows (NW * 16 of each), requested before the query / the sequence's position are known: rows are
+// clamped to the ALLOCATION (n_alloc rows exist behind Kh / Vh), not to the number of valid keys
 template <int NW, bool STREAM>
+__device__ __forceinline__ void attend_prefetch(const __half *__restrict__ Kh, const __half *__restrict__ Vh, int n_alloc, uint4 (&k0)[kAttU],
+                                                uint4 (&v0)[kAttU], int swz_row0 = -1) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+#pragma unroll
+    for (int u = 0; u < kAttU; u++) {
+        const int j = min(u * NW * 4 + warp * 4 + sub, n_alloc - 1);
+        const int ch = swz_row0 >= 0 ? (l8 ^ ((swz_row0 + j) & 7)) : l8;
+        k0[u] = ldp_v4<STREAM>(reinterpret_cast<const uint4 *>(Kh + (size_t)j * 64) + ch);
+        v0[u] = ldp_v4<STREAM>(reinterpret_cast<const uint4 *>(Vh + (size_t)j * 64) + ch);
+    }
+}
+// PRE: the first batch of rows comes from attend_prefetch (k0 / v0); otherwise the two arrays are ignored
+template <int NW, bool STREAM, bool PRE>
 __device__ __forceinline__ float attend(const __half *__restrict__ Kh, const __half *__restrict__ Vh, int n, const float *q, float *sc,
-                                        float (*red)[64], float *red1, float &m_out, float &l_out, int swz_row0 = -1) {
+                                        float (*red)[64], float *red1, float &m_out, float &l_out, const uint4 (&k0)[kAttU],
+                                        const uint4 (&v0)[kAttU], int swz_row0 = -1) {
     // swz_row0 >= 0: the rows are cross-KV cache rows starting at absolute key swz_row0 - chunk c of key m sits at c ^ (m & 7)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
     const float4 qa = *reinterpret_cast<const float4 *>(q + l8 * 8), qb = *reinterpret_cast<const float4 *>(q + l8 * 8 + 4);
-    constexpr int STEP = NW * 4, U = 4;
+    constexpr int STEP = NW * 4, U = kAttU;
     float lmax = -INFINITY;
     for (int jb = 0; jb < n; jb += STEP * U) {
         uint4 kv[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
+            if (PRE && jb == 0) { kv[u] = k0[u]; continue; }      // (prefetched; rows >= n hold allocated, unused data and are skipped below)
             const int j = min(jb + u * STEP + warp * 4 + sub, n - 1);
             const uint4 *p = reinterpret_cast<const uint4 *>(Kh + (size_t)j * 64) + (swz_row0 >= 0 ? (l8 ^ ((swz_row0 + j) & 7)) : l8);
             kv[u] = STREAM ? __ldcs(p) : __ldcg(p);
@@ -294,6 +349,7 @@ __device__ __forceinline__ float attend(const __half *__restrict__ Kh, const __h
         uint4 vv[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
+            if (PRE && jb == 0) { vv[u] = v0[u]; continue; }
             const int j = min(jb + u * STEP + warp * 4 + sub, n - 1);
             const uint4 *p = reinterpret_cast<const uint4 *>(Vh + (size_t)j * 64) + (swz_row0 >= 0 ? (l8 ^ ((swz_row0 + j) & 7)) : l8);
             vv[u] = STREAM ? __ldcs(p) : __ldcg(p);
@@ -326,15 +382,19 @@ __global__ void __launch_bounds__(kSelfWarps * 32) bd_self_attn_kernel(const __g
     __shared__ float red1[2 * kSelfWarps];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, d = P.d;
     pdl_trigger();
-    pdl_wait();
     const DecCtl *ctl = P.seq[b].ctl;
-    if (ctl->done) return;
-    const int n = ctl->pos + 1;
-    if (tid < 64) q[tid] = __half2float(P.q[(size_t)b * d + h * 64 + tid]);
-    __syncthreads();
     const size_t off = (size_t)il * P.ctx * d + (size_t)h * P.ctx * 64;
+    pdl_wait();
+    // one L2 round trip for everything: the first 64 key / value rows, the query, the finished flag and the position
+    uint4 k0[kAttU], v0[kAttU];
+    attend_prefetch<kSelfWarps, false>(P.seq[b].self_k + off, P.seq[b].self_v + off, P.ctx, k0, v0);
+    const unsigned short qh = ldp_u16(P.q + (size_t)b * d + h * 64 + (tid & 63));
+    const int done = ldp_s32(&ctl->done), n = ldp_s32(&ctl->pos) + 1;
+    if (done) return;
+    if (tid < 64) q[tid] = __half2float(__ushort_as_half(qh));
+    __syncthreads();
     float m, l;
-    const float o = attend<kSelfWarps, false>(P.seq[b].self_k + off, P.seq[b].self_v + off, n, q, sc, red, red1, m, l);
+    const float o = attend<kSelfWarps, false, true>(P.seq[b].self_k + off, P.seq[b].self_v + off, n, q, sc, red, red1, m, l, k0, v0);
     if (tid < 64) P.att[(size_t)b * d + h * 64 + tid] = __float2half_rn(o / l);
 }
 
@@ -347,15 +407,20 @@ __global__ void __launch_bounds__(kCrossWarps * 32) bd_cross_attn_kernel(const _
     __shared__ float red1[2 * kCrossWarps];
     const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x, d = P.d, T = P.T;
     pdl_trigger();
-    pdl_wait();
     const DecCtl *ctl = P.seq[b].ctl;
-    if (ctl->done) return;
-    if (tid < 64) q[tid] = __half2float(P.q[(size_t)b * d + h * 64 + tid]);
-    __syncthreads();
     const int per = (T + S - 1) / S, j0 = min(T, sp * per), n = min(T, j0 + per) - j0;
     const size_t off = (size_t)il * 2 * T * d + ((size_t)h * T + j0) * 64;
+    // (no key / value prefetch here: 32 more registers would take the kernel from 5 to 3 CTAs per SM and B x H = 640 CTAs out of one
+    //  wave - measured: 432 -> 522 ms of decode time for 32 clips)
+    const uint4 k0[kAttU] = {}, v0[kAttU] = {};
+    pdl_wait();
+    const unsigned short qh = ldp_u16(P.q + (size_t)b * d + h * 64 + (tid & 63));
+    const int done = ldp_s32(&ctl->done);
+    if (done) return;
+    if (tid < 64) q[tid] = __half2float(__ushort_as_half(qh));
+    __syncthreads();
     float m = -INFINITY, l = 0.f, o = 0.f;
-    if (n > 0) o = attend<kCrossWarps, true>(P.seq[b].cross_k + off, P.seq[b].cross_v + off, n, q, sc, red, red1, m, l, j0);
+    if (n > 0) o = attend<kCrossWarps, true, false>(P.seq[b].cross_k + off, P.seq[b].cross_v + off, n, q, sc, red, red1, m, l, k0, v0, j0);
     if (S == 1) {
         if (tid < 64) P.att[(size_t)b * d + h * 64 + tid] = __float2half_rn(o / l);
     } else {

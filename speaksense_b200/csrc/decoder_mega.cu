@@ -66,7 +66,25 @@ constexpr int kMaxJ = 5;              // flagged pairs per thread and poll batch
 #ifndef SS_KG
 #define SS_KG 2
 #endif
-constexpr int kG = SS_KG;                 // chunks of a phase that are in flight together (their reductions and epilogues overlap): FC1 / FC2 have 3 per CTA on 148 SMs
+// chunks of a phase that go through the tensor cores together (their slice reductions and epilogues overlap), per phase kind.  On 148
+// SMs with d = 1280 a CTA owns 1 chunk of O / CQ / CO, 2 of QKV, 3 of FC1 / FC2 and 22 of the LM head.  Measured (same-box A/B, ms per
+// token): groups of 2 everywhere 0.679; 1 for the one-chunk phases 0.670; 3 for FC1 / FC2 0.685 (slower: the third chunk's arrival no
+// longer overlaps the first group's reductions); 4 for the LM head: no change.
+#ifndef SS_KG_SMALL
+#define SS_KG_SMALL 1
+#endif
+#ifndef SS_KG_FC1
+#define SS_KG_FC1 SS_KG
+#endif
+#ifndef SS_KG_FC2
+#define SS_KG_FC2 SS_KG
+#endif
+#ifndef SS_KG_LM
+#define SS_KG_LM SS_KG
+#endif
+#ifndef SS_RED3
+#define SS_RED3 1            // slice reductions in 3 shuffle levels over the 8 diagonal lanes instead of 5 over the warp (-0.5 %)
+#endif
 typedef unsigned long long u64;
 constexpr int kProfN = 96;
 #ifndef SS_MEGA_PROFILE
@@ -326,6 +344,7 @@ __device__ __forceinline__ int tile_row(int ch, int warp, int l01) {
 template <int KS, int KIND>
 __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_in, uint32_t ep_out, uint32_t ph) {
     constexpr int D = KS * 128;
+    constexpr int kG = KIND == SEG_QKV ? SS_KG : KIND == SEG_FC1 ? SS_KG_FC1 : KIND == SEG_FC2 ? SS_KG_FC2 : KIND == SEG_LM ? SS_KG_LM : SS_KG_SMALL;
     constexpr bool has_ln = KIND == SEG_QKV || KIND == SEG_CQ || KIND == SEG_FC1 || KIND == SEG_LM;
     constexpr int widx = KIND == SEG_QKV ? 0 : KIND == SEG_O ? 1 : KIND == SEG_CQ ? 2 : KIND == SEG_CO ? 3 : KIND == SEG_FC1 ? 4 : 5;
     constexpr int lidx = KIND == SEG_QKV ? 0 : KIND == SEG_CQ ? 1 : 2;
@@ -339,13 +358,15 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
 #define SS_STAGE(k) if (prof_on) { const long long tn = clock64(); sm.prof[24 + KIND * 8 + (k)] += tn - tq; tq = tn; }
     // ---- static / already-valid operands of the epilogue, fetched now so that their L2 latency hides behind the poll
     // epilogue role of this lane inside a group of kG chunks: lanes 2g, 2g+1 finish rows 2w, 2w+1 of the group's chunk g
-    const int eg = lane >> 1, el = lane & 1;
+    // (SS_RED3: the slice sums are folded over the 8 diagonal lanes only - xor masks 4, 9, 18 - and diagonal lane number e finishes)
+    const int e_idx = SS_RED3 ? ((lane & 3) == (lane >> 3) ? (lane >> 2) : 64) : lane;
+    const int eg = e_idx >> 1, el = e_idx & 1;
     float pb = 0.f, pr = 0.f;      // bias / residual of the row this lane publishes in the phase's first group
     float fb = 0.f, fr = 0.f;      // FC2: bias and residual of output row `tid` (folded after the tiles)
     const int tok = sm.st.token, pos = sm.st.pos;
     if (KIND == SEG_FC2) {
         if (tid < sm.seg[KIND].rows) { fb = __ldg(P.layer[il].b[5] + row0 + tid); fr = ll_value(P.xC + row0 + tid); }
-    } else if (KIND != SEG_LM && lane < 2 * kG) {
+    } else if (KIND != SEG_LM && e_idx < 2 * kG) {
         const int R = tile_row<KIND>(eg, warp, el);
         if (R < prows) {
             pb = __ldg(P.layer[il].b[widx] + row0 + R);
@@ -500,20 +521,29 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
             }
         }
         trace_mark(KIND * 8 + 0);      // B fragments, ldmatrix, mma of the group
+        if (SS_RED3) {      // diagonal lane of slice g = (a b c): lane bits (a b c a b): flipping c / b / a = xor 4 / 9 / 18
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+            for (int lv = 0; lv < 3; lv++) {
+                const int o = lv == 0 ? 4 : lv == 1 ? 9 : 18;
 #pragma unroll
-            for (int g = 0; g < kG; g++) { v0[g] += __shfl_xor_sync(0xffffffffu, v0[g], o); v1[g] += __shfl_xor_sync(0xffffffffu, v1[g], o); }
+                for (int g = 0; g < kG; g++) { v0[g] += __shfl_xor_sync(0xffffffffu, v0[g], o); v1[g] += __shfl_xor_sync(0xffffffffu, v1[g], o); }
+            }
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int g = 0; g < kG; g++) { v0[g] += __shfl_xor_sync(0xffffffffu, v0[g], o); v1[g] += __shfl_xor_sync(0xffffffffu, v1[g], o); }
+            }
         }
         if (SS_MEGA_TRACE) { float z = 0.f; for (int g = 0; g < kG; g++) z += v0[g] + v1[g]; asm volatile("" ::"f"(z)); }
         trace_mark(KIND * 8 + 1);      // slice reductions
-        // every lane now holds every row sum of the group: lanes 2g, 2g+1 finish chunk c0 + g
+        // every (SS_RED3: every diagonal) lane now holds every row sum of the group: finishing lanes 2g, 2g+1 take chunk c0 + g
         float val = el ? v1[0] : v0[0];
 #pragma unroll
         for (int g = 1; g < kG; g++) if (eg == g) val = el ? v1[g] : v0[g];
         const int ch = c0 + eg;
         const int R = tile_row<KIND>(ch, warp, el);
-        const bool mine = lane < 2 * kG && ch < n_chunks && R < prows;
+        const bool mine = e_idx < 2 * kG && ch < n_chunks && R < prows;
         float b = pb, r = pr;
         if (c0 > 0 && mine && KIND != SEG_FC2 && KIND != SEG_LM) {      // more chunks per phase than one group (fewer SMs than the design point)
             b = __ldg(P.layer[il].b[widx] + row0 + R); r = 0.f;
@@ -523,7 +553,7 @@ __device__ __noinline__ uint32_t gemv_phase(uint32_t cons, int il, uint32_t ep_i
         float hid = 0.f, hid_hi = 0.f;
         if (KIND == SEG_FC1) {       // hidden units leave in pairs (this CTA's slice starts and ends on even rows)
             hid = gelu16(val + b);
-            hid_hi = __shfl_down_sync(0xffffffffu, hid, 1);
+            hid_hi = __shfl_down_sync(0xffffffffu, hid, SS_RED3 ? 4 : 1);      // the finishing lane of the pair's odd row
         }
         if (mine) {
             if (KIND == SEG_FC2) sm.p4[R] = val;

@@ -72,3 +72,34 @@ def test_permuted_k_fragments_form_every_product_once(WR, WK, NT, N, K, B):
     out, ref = _emulate(WR, WK, NT, N, K, B, np.random.default_rng(N + K))
     assert not np.isnan(out).any()
     np.testing.assert_allclose(out, ref, rtol=0, atol=2e-4)
+
+
+def _simulate_x_pipeline(n_blocks, U=5, XD=3):
+    """Emulates the register pipeline of bd_gemm_kernel's main loop (decoder_batch.cu): XD x-slots, U weight registers per round,
+    refills behind the products.  Returns the list of (x block, weight block) pairs that were multiplied."""
+    blk0, blk1 = 0, n_blocks
+    a = [min(blk0 + u, blk1 - 1) for u in range(U)]                 # weight block held by register u
+    xq = [min(blk0 + u, blk1 - 1) for u in range(XD)]               # x block held by slot u
+    done = []
+    blk = blk0
+    while blk < blk1:
+        more = blk + U < blk1
+        for u in range(U):
+            on = blk + u < blk1
+            if on:
+                done.append((xq[u % XD], a[u]))
+            bx = blk + u + XD if u + XD < U else blk + U + (u % XD)
+            if bx < blk1:
+                xq[u % XD] = bx
+            if more:
+                a[u] = min(blk + U + u, blk1 - 1)
+        blk += U
+    return done
+
+
+def test_batched_gemm_x_pipeline_schedule():
+    """Every K block of a warp is multiplied exactly once, x block against the weight block of the same index - for one round (5 blocks:
+    d = 1280 split 8 ways), whole rounds (10, 20: QKV / FC1 / FC2 of large-v3) and short tails (1, 2, 3, 6, 7, 12: the small models)."""
+    for n in (1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 15, 20, 23):
+        done = _simulate_x_pipeline(n)
+        assert done == [(b, b) for b in range(n)], (n, done)

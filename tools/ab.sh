@@ -7,7 +7,7 @@ cp $MAIN /tmp/main.so
 for rep in $(seq 1 ${2:-2}); do
 for v in speaksense_b200/lib/variants/*.so; do
   cp $v $MAIN
-  echo "== $(basename $v) $(SS_NO_PROF=1 python tools/mega_prof.py large-v3 ${1:-64} 2>&1 | grep ms/step | tail -2 | tr '\n' ' ')"
+  echo "== $(basename $v) $(SS_NO_PROF=1 python tools/mega_prof.py large-v3 ${1:-64} 2>&1 | grep -E "ms/step|result-hash" | tail -4 | tr '\n' ' ')"
 done
 done
 cp /tmp/main.so $MAIN

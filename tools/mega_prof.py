@@ -15,6 +15,8 @@ synth.ensure_model(path, shape=shape, family="peaked", seed=0)
 eng = WhisperAsr(path)
 st = eng.create_state()
 eng.upload_pcm(st, synth.synth_audio(seed=1234))
-eng.transcribe_resident(st, AsrParams(language=None if shape.endswith(".en") else "en", stream_mode=True))
+res = eng.transcribe_resident(st, AsrParams(language=None if shape.endswith(".en") else "en", stream_mode=True))
+import hashlib  # noqa: E402
+print("result-hash", hashlib.md5(repr([(s.start, s.end, s.text) for s in res.segments]).encode()).hexdigest()[:12], len(res.segments), flush=True)
 for i in range(3):
     print("ms/step", eng.bench_decode_steps(st, steps, 0), flush=True)
