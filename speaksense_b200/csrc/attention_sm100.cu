@@ -8,9 +8,9 @@
 //   warp 1     : TMEM allocator + single-thread MMA issuer
 //                  S_j  = Q . K_j^T         (M128 x N128 x K64,  A,B K-major)   -> TMEM S[j & 1]
 //                  PV_j = P_j . V_j         (M128 x N64  x K128, B = V MN-major) -> TMEM O[j & 1]
-//   warps 2..9 : softmax / correction, TWO threads per query row (warps w and w + 4 share a TMEM lane quarter: one takes
-//                keys 0..63 and output channels 0..31 of every block, the other keys 64..127 and channels 32..63; the
-//                block maximum is exchanged through shared memory + a 64-thread named barrier): tcgen05.ld S_j, running
+//   warps 2..  : softmax / correction, NS = 2 or 4 threads per query row (the NS warps w, w + 4, .. share a TMEM lane quarter: part
+//                p takes keys [p * 128 / NS, ..) and output channels [p * 64 / NS, ..) of every block; the block maximum is
+//                exchanged through shared memory + a named barrier of the row's NS warps): tcgen05.ld S_j, running
 //                max and sum (exp2), P_j (f16) written into shared memory in the 128-byte-swizzled K-major layout the
 //                MMA reads, and the rescaled accumulation of PV_{j-1} in registers.  (One thread per row - 4 softmax
 //                warps, one per scheduler - left the kernel exp / issue bound at 7 % tensor-pipe activity.)
@@ -19,6 +19,8 @@
 //
 // Arithmetic: f16 Q/K/V, f32 scores and running statistics, P rounded to f16 before P.V (ggml rounds the
 // normalised probabilities to f16; here the un-normalised ones - same relative rounding), f32 accumulate.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "sm100_ptx.cuh"
 
@@ -31,12 +33,18 @@ using namespace ptx;
 constexpr int kBQ = 128;          // queries per CTA
 constexpr int kBK = 128;          // keys per block
 constexpr int kD = 64;            // head dim
-constexpr int kAttnThreads = 320;
+constexpr int attn_threads(int ns) { return 64 + ns * 128; }      // TMA warp, MMA warp, NS x 4 softmax warps
 constexpr uint32_t kQBytes = kBQ * kD * 2;        // 16 KB
 constexpr uint32_t kKBytes = kBK * kD * 2;        // 16 KB
 constexpr uint32_t kVBytes = kBK * kD * 2;        // 16 KB
 constexpr uint32_t kPBytes = kBQ * kBK * 2;       // 32 KB (two 64-wide K halves)
 constexpr uint32_t kTmemCols = 512;               // S[2] at 0 / 128, O[2] at 256 / 320
+#ifndef SS_ATTN_LSUM_F32
+#define SS_ATTN_LSUM_F32 0
+#endif
+#ifndef SS_ATTN_SPLIT_DEFAULT
+#define SS_ATTN_SPLIT_DEFAULT 2
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -48,7 +56,8 @@ struct AttnDev {
     long out_ld, out_clip_stride;
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
+template <int NS>
+__global__ void __launch_bounds__(attn_threads(NS), 1) attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                              const __grid_constant__ CUtensorMap tmK,
                                                                              const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -60,8 +69,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
     uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
     uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *p_full = bars + 7, *o_full = bars + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
-    float *xmax = reinterpret_cast<float *>(bars + 16);      // [2 blocks in flight][2 halves][128 rows] block maxima
-    float *xsum = xmax + 2 * 2 * kBQ;                        // [2 halves][128 rows] final partial row sums
+    float *xmax = reinterpret_cast<float *>(bars + 16);      // [2 blocks in flight][NS parts][128 rows] block maxima
+    float *xsum = xmax + 2 * NS * kBQ;                       // [NS parts][128 rows] final partial row sums
+    constexpr int KP = kBK / NS, CP = kD / NS;               // keys per block / output channels of one softmax thread
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBQ, h = blockIdx.y, clip = blockIdx.z;
@@ -73,7 +83,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&o_full[s], 1); }
-        mbar_init(p_full, 256);
+        mbar_init(p_full, 128 * NS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -84,6 +94,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // (programmatic dependent launch: the prologue overlaps the tail of the QKV GEMM; see gemm_sm100.cu)
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -134,59 +146,70 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             }
         }
     } else {
-        // ---------------- softmax / correction: two threads per query row ----------------
-        const int q = warp & 3, half = (warp - 2) >> 2;     // TMEM lane quarter; which 64 keys / 32 channels of the row
+        // ---------------- softmax / correction: NS threads per query row ----------------
+        const int q = warp & 3, part = (warp - 2) >> 2;     // TMEM lane quarter; which KP keys / CP channels of the row
         const int row = q * 32 + lane;                      // row inside the tile == TMEM lane
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t pair_bar = 1u + (uint32_t)q;         // named barrier of the two warps of this lane quarter
-        const int k0 = half * 64;
+        const uint32_t row_bar = 1u + (uint32_t)q;          // named barrier of the NS warps of this lane quarter
+        const int k0 = part * KP;
         float m = -INFINITY, l = 0.f;
-        float acc[kD / 2];
+        float acc[CP];
 #pragma unroll
-        for (int c = 0; c < kD / 2; c++) acc[c] = 0.f;
+        for (int c = 0; c < CP; c++) acc[c] = 0.f;
+        auto load_o = [&](int s, float (&a)[CP]) {          // += this thread's CP channels of O[s]
+            if constexpr (CP == 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(lane_base + 256u + (uint32_t)(s * 64 + part * CP), r);
+#pragma unroll
+                for (int i = 0; i < 32; i++) a[i] += __uint_as_float(r[i]);
+            } else {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(lane_base + 256u + (uint32_t)(s * 64 + part * CP), r);
+#pragma unroll
+                for (int i = 0; i < 16; i++) a[i] += __uint_as_float(r[i]);
+            }
+        };
         for (int j = 0; j < nb; j++) {
             const int s = j & 1;
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tcgen05_fence_after();
-            // pass 1: maximum of this thread's 64 keys (scores scaled into the exp2 domain), then the partner's.
-            // The 64 scores stay in registers for pass 2 (one TMEM read per block instead of two).
+            // pass 1: maximum of this thread's KP keys (scores scaled into the exp2 domain), then the other parts'.
+            // The scores stay in registers for pass 2 (one TMEM read per block instead of two).
             float mj = -INFINITY;
             const int kvalid = min(kBK, p.T - j * kBK);
-            uint32_t sr[2][32];
-            tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + k0), sr[0]);
-            tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + k0 + 32), sr[1]);
+            uint32_t sr[KP / 32][32];
+#pragma unroll
+            for (int u = 0; u < KP / 32; u++) tmem_ld_32x32b_x32(lane_base + (uint32_t)(s * 128 + k0 + 32 * u), sr[u]);
             const bool full = kvalid == kBK;      // every block but the last: no per-key predicates (the softmax warps are issue-bound)
             if (full) {
                 float mr = -INFINITY;             // maximum of the raw scores; the (positive) scale is applied once
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < KP / 32; u++) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) mr = fmaxf(mr, __uint_as_float(sr[u][i]));
                 }
                 mj = mr * p.scale_log2;
             } else {
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < KP / 32; u++) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) if (k0 + 32 * u + i < kvalid) mj = fmaxf(mj, __uint_as_float(sr[u][i]) * p.scale_log2);
                 }
             }
-            xmax[(s * 2 + half) * kBQ + row] = mj;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            mj = fmaxf(mj, xmax[(s * 2 + (half ^ 1)) * kBQ + row]);
+            xmax[(s * NS + part) * kBQ + row] = mj;
+            asm volatile("bar.sync %0, %1;" ::"r"(row_bar), "n"(32 * NS) : "memory");
+#pragma unroll
+            for (int o = 1; o < NS; o++) mj = fmaxf(mj, xmax[(s * NS + ((part + o) % NS)) * kBQ + row]);
             const float m_new = fmaxf(m, mj);
             const float alpha = exp2f(m - m_new);          // 0 on the first block (m = -inf)
-            // fold the previous block's P.V (this thread's 32 channels) into the accumulator, then rescale to the new maximum
+            // fold the previous block's P.V (this thread's CP channels) into the accumulator, then rescale to the new maximum
             if (j > 0) {
                 mbar_wait(&o_full[s ^ 1], ((j - 1) >> 1) & 1);
                 tcgen05_fence_after();
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(lane_base + 256u + (uint32_t)((s ^ 1) * 64 + half * 32), r);
-#pragma unroll
-                for (int i = 0; i < 32; i++) acc[i] += __uint_as_float(r[i]);
+                load_o(s ^ 1, acc);
             }
 #pragma unroll
-            for (int c = 0; c < kD / 2; c++) acc[c] *= alpha;
+            for (int c = 0; c < CP; c++) acc[c] *= alpha;
             // pass 2: probabilities -> shared memory (f16, swizzled K-major A operand), partial row sum
             float lsum = 0.f;
             auto store_p = [&](int c, const uint32_t (&pk)[16]) {
@@ -200,21 +223,25 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             if (full) {
                 const float nm = -m_new;
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < KP / 32; u++) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
                         const float p0 = ex2_approx(fmaf(__uint_as_float(sr[u][i]), p.scale_log2, nm));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(sr[u][i + 1]), p.scale_log2, nm));
                         __half2 hp = __floats2half2_rn(p0, p1);
+#if SS_ATTN_LSUM_F32
+                        lsum += p0 + p1;                                 // (ggml normalises with the f32 sum of the unrounded exponentials)
+#else
                         lsum += __low2float(hp) + __high2float(hp);      // sum what the MMA will actually see
+#endif
                         pk[i >> 1] = *reinterpret_cast<uint32_t *>(&hp);
                     }
                     store_p(k0 + 32 * u, pk);
                 }
             } else {
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < KP / 32; u++) {
                     const int c = k0 + 32 * u;
                     uint32_t pk[16];
 #pragma unroll
@@ -238,20 +265,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
             const int s = (nb - 1) & 1;
             mbar_wait(&o_full[s], ((nb - 1) >> 1) & 1);
             tcgen05_fence_after();
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(lane_base + 256u + (uint32_t)(s * 64 + half * 32), r);
-#pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] += __uint_as_float(r[i]);
+            load_o(s, acc);
         }
-        xsum[half * kBQ + row] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        l += xsum[(half ^ 1) * kBQ + row];
+        xsum[part * kBQ + row] = l;
+        asm volatile("bar.sync %0, %1;" ::"r"(row_bar), "n"(32 * NS) : "memory");
+#pragma unroll
+        for (int o = 1; o < NS; o++) l += xsum[((part + o) % NS) * kBQ + row];
         const int t = q0 + row;
         if (t < p.T) {
             const float inv = 1.0f / l;
-            __half *o = p.out + (size_t)clip * p.out_clip_stride + (size_t)t * p.out_ld + h * kD + half * (kD / 2);
+            __half *o = p.out + (size_t)clip * p.out_clip_stride + (size_t)t * p.out_ld + h * kD + part * CP;
 #pragma unroll
-            for (int c = 0; c < kD / 2; c += 8) {
+            for (int c = 0; c < CP; c += 8) {
                 __half2 h0 = __floats2half2_rn(acc[c] * inv, acc[c + 1] * inv), h1 = __floats2half2_rn(acc[c + 2] * inv, acc[c + 3] * inv);
                 __half2 h2 = __floats2half2_rn(acc[c + 4] * inv, acc[c + 5] * inv), h3 = __floats2half2_rn(acc[c + 6] * inv, acc[c + 7] * inv);
                 uint4 u;
@@ -269,12 +294,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tcgen05_kernel(cons
     }
 }
 
-constexpr size_t kAttnSmem = 1024 + kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 16 * 8 + (2 * 2 + 2) * kBQ * 4;
+constexpr size_t attn_smem(int ns) { return 1024 + kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes + 16 * 8 + (size_t)(2 * ns + ns) * kBQ * 4; }
+// threads per query row: 2 (8 softmax warps) or 4 (16); SS_ATTN_SPLIT overrides
+int attn_split() {
+    static const int ns = [] { const char *e = getenv("SS_ATTN_SPLIT"); return e && e[0] == '4' ? 4 : e && e[0] == '2' ? 2 : SS_ATTN_SPLIT_DEFAULT; }();
+    return ns;
+}
 
 }  // namespace
 
 void attention_init() {
-    CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(2)));
+    CUDA_CHECK(cudaFuncSetAttribute(attention_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(4)));
 }
 
 // qkv: [clips][T][3*H*64] f16 (Q | K | V); out: [clips][T][H*64] f16
@@ -290,7 +321,8 @@ void attention_enqueue(const __half *qkv, __half *out, int clips, int T, int H, 
     AttnDev p{};
     p.T = T; p.H = H; p.scale_log2 = scale * 1.4426950408889634f; p.out = out; p.out_ld = d; p.out_clip_stride = (long)T * d;
     dim3 grid(ceil_div(T, kBQ), H, clips);
-    attention_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, p);
+    if (attn_split() == 4) launch_pdl(encoder_pdl_enabled(), attention_tcgen05_kernel<4>, grid, dim3(attn_threads(4)), attn_smem(4), st, tq, tk, tv, p);
+    else launch_pdl(encoder_pdl_enabled(), attention_tcgen05_kernel<2>, grid, dim3(attn_threads(2)), attn_smem(2), st, tq, tk, tv, p);
     CUDA_CHECK(cudaGetLastError());
     (*launches)++;
 }

@@ -36,8 +36,7 @@ enum : int { EPI_QKV = 0, EPI_RES, EPI_Q, EPI_GELU, EPI_LOGITS };
 // waits for its predecessor (wait) only where it first touches something the predecessor wrote.  What a GEMM does before
 // the wait - issuing the loads of its first weight fragments, which are static - overlaps the predecessor's execution, and
 // every kernel's launch latency and ramp-up hide behind the previous one.  Without the launch attribute both are no-ops.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (pdl_trigger / pdl_wait: kernels.h)
 
 // Loads whose position in the instruction stream matters (issued right behind the wait, BEFORE the branch on a sequence's finished
 // flag, so that no L2 round trip waits for another): volatile asm keeps program order against the wait and against each other.
@@ -718,13 +717,7 @@ bool pdl_enabled() {
 }
 template <typename... KArgs, typename... Args>
 void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+    launch_pdl(pdl_enabled(), kernel, grid, block, 0, st, std::forward<Args>(args)...);
 }
 
 template <int WR, int WK, int EPI>

@@ -1,6 +1,9 @@
 // encoder.cu - the non-GEMM pieces of the audio encoder: LayerNorm (ggml_norm + affine, eps 1e-5,
 // resources/ggml-metal.metal:571-621) producing the f16 GEMM operand, the attention itself is
 // attention_sm100.cu and everything else in the encoder is a tcgen05 GEMM epilogue (gemm_sm100.cu).
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace ss {
@@ -17,6 +20,8 @@ template <int NV, bool OUT_F16>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, void *__restrict__ y, int rows,
                                                          const float *__restrict__ w, const float *__restrict__ b) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();      // x is the predecessor's output, y may still be read by it
     if (row >= rows) return;
     constexpr int d = NV * 128;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * d);
@@ -53,7 +58,7 @@ template <bool OUT_F16>
 void ln_dispatch(const float *x, void *y, int rows, int d, const LNp &ln, cudaStream_t st) {
     const int grid = ceil_div(rows, 8);
     switch (d / 128) {
-#define CASE(NV) case NV: layernorm_kernel<NV, OUT_F16><<<grid, 256, 0, st>>>(x, y, rows, ln.w, ln.b); break;
+#define CASE(NV) case NV: launch_pdl(encoder_pdl_enabled(), layernorm_kernel<NV, OUT_F16>, dim3(grid), dim3(256), 0, st, x, y, rows, ln.w, ln.b); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(10)
 #undef CASE
         default: SS_THROW(-9, "unsupported model width %d", d);
@@ -62,10 +67,17 @@ void ln_dispatch(const float *x, void *y, int rows, int d, const LNp &ln, cudaSt
 }
 
 __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float *__restrict__ x, __half *__restrict__ y, size_t n) {
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2half_rn(x[i]);
 }
 
 }  // namespace
+
+bool encoder_pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("SS_ENC_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 void layernorm_f16_enqueue(const float *x, __half *y, int rows, int d, const LNp &ln, cudaStream_t st, int *launches) {
     ln_dispatch<true>(x, y, rows, d, ln, st); (*launches)++;
@@ -74,7 +86,7 @@ void layernorm_f32_enqueue(const float *x, float *y, int rows, int d, const LNp 
     ln_dispatch<false>(x, y, rows, d, ln, st); (*launches)++;
 }
 void f32_to_f16_enqueue(const float *x, __half *y, size_t n, cudaStream_t st, int *launches) {
-    f32_to_f16_kernel<<<(unsigned)std::min<size_t>(ceil_div<size_t>(n, 256), 148 * 8), 256, 0, st>>>(x, y, n);
+    launch_pdl(encoder_pdl_enabled(), f32_to_f16_kernel, dim3((unsigned)std::min<size_t>(ceil_div<size_t>(n, 256), 148 * 8)), dim3(256), 0, st, x, y, n);
     CUDA_CHECK(cudaGetLastError()); (*launches)++;
 }
 

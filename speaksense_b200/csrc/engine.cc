@@ -273,6 +273,7 @@ State::~State() {
     engine->n_states.fetch_sub(1);
     cudaSetDevice(engine->device);
     if (stream) cudaStreamSynchronize(stream);
+    if (enc_graph) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(enc_graph));
     for (auto &d : dec) {
         MegaParams &b = d->mp;
         cudaFree(b.ctl); cudaFree(d->d_ll); cudaFree(b.logits); cudaFree(b.tok_out); if (b.prof) cudaFree(b.prof);
@@ -383,12 +384,11 @@ void run_log_mel(State &s, const float *pcm, size_t n) {
     CUDA_CHECK(cudaGetLastError());
 }
 
-void run_encode(State &s, int seek) {
+// conv stem, encoder layers, ln_post and the cross-KV projection of the window staged in s.win: every launch works on buffers the
+// State owns for its whole life, so the sequence can be captured once and replayed
+static void encode_window_enqueue(State &s, cudaStream_t st, int *nl) {
     const Model &m = s.engine->model; const HParams &hp = m.hp;
-    CUDA_CHECK(cudaSetDevice(s.engine->device));
-    cudaStream_t st = s.stream; int *nl = &s.n_launches;
     const int T = hp.n_audio_ctx, d = hp.n_audio_state, H = hp.n_audio_head, C = hp.n_mels;
-    mel_window_enqueue(m, s.d_mel, s.n_len, seek, s.win, st, nl);
     {   // conv1 (k3,s1,p1) + bias + GELU as implicit GEMM over overlapping rows of the padded window
         GemmOperand A; A.ptr = s.win; A.rows = 2 * T; A.ld = C;
         GemmOperand B; B.ptr = m.conv1.w; B.rows = d; B.ld = 3 * C;
@@ -451,6 +451,36 @@ void run_encode(State &s, int seek) {
         gemm_enqueue(A, B, T, 2 * dd, d, false, ep, st, nl);
     }
     CUDA_CHECK(cudaGetLastError());
+}
+
+static bool enc_graph_enabled() {
+    static const bool on = [] { const char *e = getenv("SS_ENC_GRAPH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+void run_encode(State &s, int seek) {
+    const Model &m = s.engine->model;
+    CUDA_CHECK(cudaSetDevice(s.engine->device));
+    cudaStream_t st = s.stream;
+    mel_window_enqueue(m, s.d_mel, s.n_len, seek, s.win, st, &s.n_launches);      // (depends on the window: stays outside the graph)
+    if (!enc_graph_enabled()) { encode_window_enqueue(s, st, &s.n_launches); return; }
+    if (!s.enc_graph) {
+        // One host thread drives a State at a time; thread-local capture leaves the other sessions' streams alone.  The tensor maps and
+        // kernel arguments are baked into the graph: one cudaGraphLaunch replaces ~340 launches and ~260 tensor-map encodes per window.
+        cudaGraph_t graph = nullptr;
+        int n = 0;
+        CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try { encode_window_enqueue(s, st, &n); }
+        catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) SS_THROW(-4, "cudaGraphInstantiate of the encoder pass failed: %s", cudaGetErrorString(e));
+        s.enc_graph = exec; s.enc_graph_launches = n;
+    }
+    CUDA_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(s.enc_graph), st));
+    s.n_launches += s.enc_graph_launches;
 }
 
 // ------------------------------------------------------------------------------------------------

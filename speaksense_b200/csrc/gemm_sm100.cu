@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: the prologue above (barriers, tensor memory, descriptor prefetch) ran while the predecessor was
+    // still finishing on other SMs; from here on the kernel reads and overwrites what the predecessor produced / still reads
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -461,7 +465,7 @@ void launch(const GemmOperand &A, const GemmOperand &B, const GemmDev &p, cudaSt
     make_map(&ta, A, p.K, A.rows, BK, BM);
     make_map(&tb, B, p.K, B.rows, BK, BN);
     const int total = ceil_div(p.N, BN) * ceil_div(p.M, BM) * p.nbatch;
-    gemm_tcgen05_kernel<BN, kStages, EPI><<<std::min(total, g_sms), kThreads, smem_bytes<BN, kStages>(), st>>>(ta, tb, p);
+    launch_pdl(encoder_pdl_enabled(), gemm_tcgen05_kernel<BN, kStages, EPI>, dim3(std::min(total, g_sms)), dim3(kThreads), smem_bytes<BN, kStages>(), st, ta, tb, p);
     CUDA_CHECK(cudaGetLastError());
 }
 template <int BN, int EPI>

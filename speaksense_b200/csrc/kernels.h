@@ -170,4 +170,25 @@ struct BatchStepGraph {
 void decode_batch_step_graph(BatchStepGraph &G, const BatchParams &P, const MegaParams &w, bool need_logits, int xsplit, cudaStream_t st,
                              int *launches, const BeamStep *beam = nullptr);
 
+// ---- programmatic dependent launch (chains of short kernels: the batched decoder step, the encoder pass of one clip) ----
+// A kernel launched with the attribute may start while its predecessor in the stream is still running; it must execute pdl_wait()
+// before it touches anything the predecessor reads or writes.  pdl_trigger() lets the successor's launch begin.  Without the
+// attribute both instructions are no-ops, and a successor without the attribute waits for full completion as usual.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+// SS_ENC_PDL=0: the encoder's kernels as plain stream-ordered launches
+bool encoder_pdl_enabled();
+
 }  // namespace ss
