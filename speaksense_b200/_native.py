@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspeaksense_whisper.so")
+# SS_LIB_PATH: another build of the same library (tools/asan_host.sh: the host side compiled with AddressSanitizer / UBSan)
+LIB_PATH = os.environ.get("SS_LIB_PATH") or os.path.join(_HERE, "lib", "libspeaksense_whisper.so")
 
 
 class SsParams(C.Structure):

@@ -319,6 +319,7 @@ void upload_pcm(State &s, const float *pcm, size_t n) {
 }
 
 int denoise_audio(State &s, const float *pcm, size_t n, int frame_size, float overlap, float strength, float *out, float *nv_out) {
+    NvtxRange nvtx("ss.denoise");
     upload_pcm(s, pcm, n);
     const size_t need = denoise_scratch_floats(n, frame_size, overlap);
     if (need > s.dn_cap || !s.d_pcm_alt) {
@@ -348,6 +349,7 @@ void denoise_frames(State &s, const float *frames, int n_frames, int frame_size,
 }
 
 void run_log_mel(State &s, const float *pcm, size_t n) {
+    NvtxRange nvtx("ss.log_mel");
     const Model &m = s.engine->model;
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     if (pcm == nullptr && n == s.n_resident && s.d_pcm) {   // PCM already resident in HBM (ss_upload_pcm)
@@ -459,6 +461,7 @@ static bool enc_graph_enabled() {
 }
 
 void run_encode(State &s, int seek) {
+    NvtxRange nvtx("ss.encode");
     const Model &m = s.engine->model;
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     cudaStream_t st = s.stream;
@@ -496,6 +499,7 @@ void ensure_params(State &s, Decoder &d) {
 
 // one launch of the persistent decode kernel: runs until the device says done or `max_steps` tokens
 static void run_steps(State &s, Decoder &d, int max_steps) {
+    NvtxRange nvtx("ss.decode");
     ensure_params(s, d);
     decode_mega_launch(d.d_mp, d.d_ll, d.ll_bytes, max_steps, s.mega_grid, s.stream);
     s.n_launches += 1;
@@ -760,6 +764,7 @@ void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i,
 // whisper_full
 // ------------------------------------------------------------------------------------------------
 int transcribe(State &s, const float *pcm, size_t n_samples, const FullParams &P, bool stream_mode) {
+    NvtxRange nvtx("ss.transcribe");
     const Model &m = s.engine->model; const HParams &hp = m.hp; const Vocab &v = m.vocab;
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     s.raw.clear(); s.out.clear(); s.full_text.clear(); s.result_tokens.clear();

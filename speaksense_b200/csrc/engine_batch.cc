@@ -247,6 +247,7 @@ EncBuf bind_enc_scratch(Engine &E) {
 // encoder + cross-KV of the current window of every clip of `grp` (<= kMaxBatch) on the engine's batch stream; every clip's
 // own stream is made to wait for the pass.  Same arithmetic, kernels and epilogues as run_encode (engine.cc).
 void run_encode_batch(Engine &E, std::vector<ClipRun *> &grp) {
+    NvtxRange nvtx("ss.batch.encode");
     const Model &m = E.model; const HParams &hp = m.hp;
     const int R = (int)grp.size(), T = hp.n_audio_ctx, d = hp.n_audio_state, H = hp.n_audio_head, C = hp.n_mels;
     const EncBuf B = bind_enc_scratch(E);
@@ -615,6 +616,7 @@ static void decode_sampled_batched_locked(State &s, const FullParams &P, float t
 }
 
 int transcribe_batch(State *const *states, const float *const *pcm, const size_t *n, int batch, const FullParams &P, bool stream_mode) {
+    NvtxRange nvtx("ss.transcribe_batch");
     if (batch <= 0) return 0;
     Engine &E = *states[0]->engine;
     const Model &m = E.model; const HParams &hp = m.hp; const Vocab &v = m.vocab;

@@ -1,8 +1,19 @@
 // engine_internal.h - helpers of engine.cc shared with engine_batch.cc (not part of the library's interface).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
+
 #include "engine.h"
 
 namespace ss {
+
+// NVTX range over a host-side stage (header-only nvtx3: a no-op unless a tool such as Nsight Systems is attached).  Ranges:
+// ss.transcribe > ss.log_mel / ss.encode / ss.decode, ss.transcribe_batch > ss.batch.encode / ss.batch.decode, ss.denoise.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 Decoder *new_decoder(State &s, bool with_keep);
 void ensure_params(State &s, Decoder &d);
