@@ -68,16 +68,18 @@ constexpr int kMaxJ = 5;              // flagged pairs per thread and poll batch
 #endif
 // chunks of a phase that go through the tensor cores together (their slice reductions and epilogues overlap), per phase kind.  On 148
 // SMs with d = 1280 a CTA owns 1 chunk of O / CQ / CO, 2 of QKV, 3 of FC1 / FC2 and 22 of the LM head.  Measured (same-box A/B, ms per
-// token): groups of 2 everywhere 0.679; 1 for the one-chunk phases 0.670; 3 for FC1 / FC2 0.685 (slower: the third chunk's arrival no
-// longer overlaps the first group's reductions); 4 for the LM head: no change.
+// token): groups of 2 everywhere 0.679; 1 for the one-chunk phases 0.670; then, one kind at a time: 3 for FC2 0.660 (its three chunks in
+// one group), 1 for FC1 0.656 (3: 0.681 - the GELU epilogue of a chunk overlaps the next chunk's tiles), 1 for QKV 0.678 (slower), 3 / 4 for
+// the LM head 0.666 (slower), three accumulator chains per tile instead of two: no change.
+// An 18-row FC1 chunk (a ninth row pair as a second tile for warp 0, so that 35 rows are 2 chunks): 0.710 - measured, removed.
 #ifndef SS_KG_SMALL
 #define SS_KG_SMALL 1
 #endif
 #ifndef SS_KG_FC1
-#define SS_KG_FC1 SS_KG
+#define SS_KG_FC1 1
 #endif
 #ifndef SS_KG_FC2
-#define SS_KG_FC2 SS_KG
+#define SS_KG_FC2 3
 #endif
 #ifndef SS_KG_LM
 #define SS_KG_LM SS_KG
