@@ -30,4 +30,4 @@ print("%-62s %-14s %5s %10s %8s %6s %s" % ("kernel", "grid", "count", "total us"
 for k, a in sorted(agg.items(), key=lambda x: -x[1]["t"]):
     n = len(a["ids"])
     print("%-62s %-14s %5d %10.1f %8.2f %5.1f%% %s" % (k[0], k[1], n, a["t"], a["t"] / n, 100 * a["t"] / tot,
-                                                        ("%.2f / %.2f" % (a["rd"] / n, a["wr"] / n)) if a["rd"] else ""))
+                                                        ("%.2f MB / %.2f MB" % (a["rd"] / n / 1e6, a["wr"] / n / 1e6)) if a["rd"] else ""))
