@@ -74,9 +74,11 @@ __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float *__restrict
 
 }  // namespace
 
+static thread_local bool t_pdl_scope = true;
+void encoder_pdl_scope(bool on) { t_pdl_scope = on; }
 bool encoder_pdl_enabled() {
     static const bool on = [] { const char *e = getenv("SS_ENC_PDL"); return !(e && e[0] == '0'); }();
-    return on;
+    return on && t_pdl_scope;
 }
 
 void layernorm_f16_enqueue(const float *x, __half *y, int rows, int d, const LNp &ln, cudaStream_t st, int *launches) {

@@ -466,6 +466,9 @@ void run_encode(State &s, int seek) {
     CUDA_CHECK(cudaSetDevice(s.engine->device));
     cudaStream_t st = s.stream;
     mel_window_enqueue(m, s.d_mel, s.n_len, seek, s.win, st, &s.n_launches);      // (depends on the window: stays outside the graph)
+    // programmatic dependent launch only while this replica serves a single session (kernels.h: encoder_pdl_enabled); the decision
+    // is baked into the graph at capture, i.e. at the session's first window
+    struct PdlScope { explicit PdlScope(bool on) { encoder_pdl_scope(on); } ~PdlScope() { encoder_pdl_scope(true); } } scope(s.engine->n_states.load() <= 1);
     if (!enc_graph_enabled()) { encode_window_enqueue(s, st, &s.n_launches); return; }
     if (!s.enc_graph) {
         // One host thread drives a State at a time; thread-local capture leaves the other sessions' streams alone.  The tensor maps and

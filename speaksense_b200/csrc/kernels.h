@@ -188,7 +188,11 @@ inline void launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
-// SS_ENC_PDL=0: the encoder's kernels as plain stream-ordered launches
+// Whether the encoder's kernels are launched with the attribute: SS_ENC_PDL (default on) AND the calling thread's scope.  A dependent
+// grid that starts early holds its SMs (a GEMM CTA: ~200 KB of shared memory) until its predecessor is done - free on a GPU that one
+// session owns, but taken from the other sessions' kernels on a shared one (measured: 8 concurrent streams 209 / 218x with, 271 /
+// 232x without; one clip alone 4.60 against 4.65 ms).  run_encode therefore narrows the scope to "this replica has one session".
 bool encoder_pdl_enabled();
+void encoder_pdl_scope(bool on);      // thread-local; true by default
 
 }  // namespace ss

@@ -1,13 +1,3 @@
 cd "$(dirname "$0")/.."
-python -c "
-import sys; sys.path.insert(0,'.')
-from speaksense_b200 import synth; import os
-synth.ensure_model('/tmp/ss_models/ggml-large-v3-peaked-s0.bin', shape='large-v3', family='peaked', seed=0)" 2>/dev/null
-for cfg in "A=1" "SS_ENC_PDL=0" "SS_ENC_PDL=0 SS_ENC_GRAPH=0" "A=2" "SS_ENC_PDL=0"; do
-  echo "== stream8 $cfg" | tee -a gpurun_out/s13_stream.txt
-  env $cfg timeout 150 python tools/stream_bench.py large-v3 120 0 8 1 2>/dev/null | head -1 | cut -c150-420 | tee -a gpurun_out/s13_stream.txt
-done
-for cfg in "A=1" "SS_ENC_PDL=0" "SS_ENC_PDL=0 SS_ENC_GRAPH=0"; do
-  echo "== beam5 $cfg" | tee -a gpurun_out/s13_stream.txt
-  env $cfg timeout 150 python tools/stream_bench.py large-v3 60 5 2>/dev/null | head -1 | cut -c150-420 | tee -a gpurun_out/s13_stream.txt
-done
+timeout 300 python -m pytest tests/test_gpu_multi_device.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/s15_tests_2gpu.txt
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/s15_bench_2gpu.json 2> gpurun_out/s15_bench_2gpu.err; echo "bench rc=$?"; tail -1 gpurun_out/s15_bench_2gpu.json | cut -c1-400
