@@ -54,7 +54,15 @@ static int batch_decode_min() {
 namespace {
 
 constexpr int kXsplitMax = 8;
-constexpr int kPollEvery = 4;      // decoder steps between two reads of the finished-sequence count
+// Decoder steps between two reads of the finished-sequence count.  The host enqueues at most two such groups ahead of the count it has
+// seen, so between kPollEvery and 3 * kPollEvery - 1 steps run after the last sequence has finished (their kernels leave early, but a
+// step of ~390 of them still costs ~1 ms).  2 keeps >= 4 steps (>= 6 ms of device work at any batch size) queued and wastes 2..5 steps
+// instead of 4..11; SS_BATCH_POLL overrides (1..16).
+static int poll_every() {
+    static const int v = [] { const char *e = getenv("SS_BATCH_POLL"); const int x = e ? atoi(e) : 2; return x >= 1 && x <= 16 ? x : 2; }();
+    return v;
+}
+#define kPollEvery (poll_every())
 
 struct ClipRun {
     State *s = nullptr;

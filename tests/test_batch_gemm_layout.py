@@ -103,3 +103,33 @@ def test_batched_gemm_x_pipeline_schedule():
     for n in (1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 15, 20, 23):
         done = _simulate_x_pipeline(n)
         assert done == [(b, b) for b in range(n)], (n, done)
+
+
+def test_decode_kernel_diagonal_reduction_lanes():
+    """decoder_mega.cu, gemv_phase: one m16n8k16 tile = {2 weight rows} x {8 K slices}; the wanted products are the diagonal
+    C[8 * row + slice][slice].  In the C fragment lane (g, t) holds C[g][2t], C[g][2t+1], C[g+8][2t], C[g+8][2t+1], so slice s of
+    both rows sits on lane 4s + (s >> 1) (element s & 1).  The kernel folds the 8 slices with xor-shuffles 4, 9, 18 and lets
+    diagonal lane number e finish row e & 1 of chunk e >> 1; the odd row's value reaches the even row's lane by shfl_down 4."""
+    lanes = []
+    for s in range(8):
+        cand = [lane for lane in range(32) if (lane >> 2) == s and (lane & 3) == (s >> 1)]      # g == s and the column pair holding column s
+        assert len(cand) == 1
+        lanes.append(cand[0])
+    assert lanes == [4 * s + (s >> 1) for s in range(8)] == [0, 4, 9, 13, 18, 22, 27, 31]
+    # the kernel's test for "diagonal lane" and its index
+    for lane in range(32):
+        diag = (lane & 3) == (lane >> 3)
+        assert diag == (lane in lanes)
+        if diag:
+            assert lanes[lane >> 2] == lane
+    # three xor levels reach every diagonal lane from every diagonal lane, and never leave the set
+    vals = np.zeros(32)
+    vals[lanes] = np.arange(1, 9) * 1.5
+    v = vals.copy()
+    for mask in (4, 9, 18):
+        v = v + v[np.arange(32) ^ mask]
+        assert all(((lane ^ mask) in lanes) for lane in lanes)
+    assert np.allclose(v[lanes], vals.sum())
+    # finishing lanes: e = 2 * chunk + row; the pair's odd row is 4 lanes further down
+    for e in range(0, 8, 2):
+        assert lanes[e + 1] - lanes[e] == 4
