@@ -92,6 +92,30 @@ def lib():
     return L
 
 
+def beam_assign(cands, live, i):
+    """One beam-search step's candidate assignment (test probe of beam_assign in whisper_oracle.c).  cands: list of
+    (token ids, sum_logprobs_all, decoder index) in the order the decoders produced them; live[j]: decoder j still running;
+    i: index of the token being sampled.  Returns, per decoder, the index into `cands` of the candidate it continues with (-1)."""
+    L = lib()
+    n = len(cands)
+    max_len = max([len(c[0]) for c in cands] + [1])
+    ids = np.zeros((max(n, 1), max_len), np.int32)
+    for k, c in enumerate(cands):
+        ids[k, :len(c[0])] = c[0]
+    lens = np.asarray([len(c[0]) for c in cands] + ([] if n else [0]), np.int32)
+    sums = np.asarray([c[1] for c in cands] + ([] if n else [0.0]), np.float64)
+    dec = np.asarray([c[2] for c in cands] + ([] if n else [0]), np.int32)
+    lv = np.asarray([1 if x else 0 for x in live], np.int32)
+    out = np.full(len(live), -2, np.int32)
+    L.wo_probe_beam_assign.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.wo_probe_beam_assign.restype = C.c_int
+    rc = L.wo_probe_beam_assign(ids.ctypes.data, lens.ctypes.data, max_len, sums.ctypes.data, dec.ctypes.data, n, lv.ctypes.data, len(live), i,
+                                out.ctypes.data)
+    if rc:
+        raise RuntimeError("wo_probe_beam_assign rc=%d" % rc)
+    return out.tolist()
+
+
 class OracleError(RuntimeError):
     pass
 

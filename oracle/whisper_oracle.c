@@ -1090,6 +1090,53 @@ static void push_result_token(wo_state *s, const tokdata_t *t) {
 
 typedef struct { int decoder_idx, seek_delta, has_ts; sequence_t seq; } beam_cand_t;
 
+/* One beam-search step's candidate assignment (whisper.cpp whisper_full_with_state, BEAM_SEARCH branch behind "update each decoder"):
+ * the candidates of all live decoders are sorted by sum_logprobs_all, descending (stable here; std::sort there), and handed to the
+ * live decoders in order; from the second sampled token on (i > 0) a decoder skips the candidates that follow its own and carry the
+ * same token sequence; the candidate cursor wraps to 0 when it runs past the end.  pick[j] = index into the SORTED array of the
+ * candidate decoder j continues with, -1 for a decoder that has completed / failed.  Factored out for wo_full and the
+ * wo_probe_beam_assign test probe. */
+static void beam_assign(beam_cand_t *cands, int n_cands, int n_cur, const int *live, int i, int *pick) {
+    for (int a = 1; a < n_cands; a++) {
+        beam_cand_t tmp = cands[a]; int b = a - 1;
+        while (b >= 0 && cands[b].seq.sum_logprobs_all < tmp.seq.sum_logprobs_all) { cands[b + 1] = cands[b]; b--; }
+        cands[b + 1] = tmp;
+    }
+    int cur_c = 0;
+    for (int j = 0; j < n_cur; j++) {
+        pick[j] = -1;
+        if (!live[j]) continue;
+        if (cur_c >= n_cands) cur_c = 0;
+        const beam_cand_t *c = &cands[cur_c];
+        pick[j] = cur_c++;
+        while (n_cands > cur_c && i > 0 && cands[cur_c].seq.n == c->seq.n) {
+            int eq = 1; for (int a = 0; a < c->seq.n; a++) if (cands[cur_c].seq.tokens[a].id != c->seq.tokens[a].id) { eq = 0; break; }
+            if (!eq) break;
+            ++cur_c;
+        }
+    }
+}
+
+/* test probe: beam_assign over n_cands candidates given as token-id rows (ids[c * max_len ..], len[c] tokens each), their
+ * sum_logprobs_all and the decoder each one came from; out[j] = ORIGINAL index of the candidate decoder j continues with (-1: not live) */
+int wo_probe_beam_assign(const int *ids, const int *len, int max_len, const double *sums, const int *decoder_idx, int n_cands,
+                         const int *live, int n_cur, int i, int *out) {
+    if (n_cands < 0 || n_cands > WO_MAX_DECODERS * WO_MAX_DECODERS || n_cur < 0 || n_cur > WO_MAX_DECODERS) return -1;
+    beam_cand_t *cands = (beam_cand_t *)calloc((size_t)(n_cands > 0 ? n_cands : 1), sizeof(beam_cand_t));
+    for (int c = 0; c < n_cands; c++) {
+        cands[c].decoder_idx = decoder_idx[c];
+        cands[c].seek_delta = c;      /* carries the original index through the sort */
+        for (int a = 0; a < len[c]; a++) { tokdata_t t = {ids[(size_t)c * max_len + a], 0, 0.f, 0.f, 0.f, 0.f}; seq_push(&cands[c].seq, t); }
+        cands[c].seq.sum_logprobs_all = sums[c];
+    }
+    int pick[WO_MAX_DECODERS];
+    beam_assign(cands, n_cands, n_cur, live, i, pick);
+    for (int j = 0; j < n_cur; j++) out[j] = pick[j] >= 0 ? cands[pick[j]].seek_delta : -1;
+    for (int c = 0; c < n_cands; c++) free(cands[c].seq.tokens);
+    free(cands);
+    return 0;
+}
+
 int wo_full(wo_state *s, const float *pcm, size_t n_samples, const wo_params *P) {
     wo_model *m = s->m; const wo_hparams *hp = &m->hp; const int nv = hp->n_vocab;
     clear_segments(s);
@@ -1205,23 +1252,13 @@ int wo_full(wo_state *s, const float *pcm, size_t n_samples, const wo_params *P)
                     }
                 }
                 if (beam) {
-                    /* stable sort by sum_logprobs_all desc */
-                    for (int a = 1; a < n_cands; a++) {
-                        beam_cand_t tmp = cands[a]; int b = a - 1;
-                        while (b >= 0 && cands[b].seq.sum_logprobs_all < tmp.seq.sum_logprobs_all) { cands[b + 1] = cands[b]; b--; }
-                        cands[b + 1] = tmp;
-                    }
-                    int cur_c = 0; int src[WO_MAX_DECODERS];
+                    int live[WO_MAX_DECODERS], pick[WO_MAX_DECODERS], src[WO_MAX_DECODERS];
+                    for (int j = 0; j < n_cur; j++) live[j] = !(s->dec[j].completed || s->dec[j].failed);
+                    beam_assign(cands, n_cands, n_cur, live, i, pick);
                     for (int j = 0; j < n_cur; j++) {
                         decoder_t *dc = &s->dec[j]; src[j] = -1;
-                        if (dc->completed || dc->failed) continue;
-                        if (cur_c >= n_cands) cur_c = 0;
-                        beam_cand_t *c = &cands[cur_c++];
-                        while (n_cands > cur_c && i > 0 && cands[cur_c].seq.n == c->seq.n) {
-                            int eq = 1; for (int a = 0; a < c->seq.n; a++) if (cands[cur_c].seq.tokens[a].id != c->seq.tokens[a].id) { eq = 0; break; }
-                            if (!eq) break;
-                            ++cur_c;
-                        }
+                        if (pick[j] < 0) continue;
+                        const beam_cand_t *c = &cands[pick[j]];
                         dc->seek_delta = c->seek_delta; dc->has_ts = c->has_ts; seq_copy(&dc->seq, &c->seq);
                         src[j] = c->decoder_idx;
                     }
