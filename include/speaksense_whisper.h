@@ -171,6 +171,12 @@ const float *ss_debug_logits(const ss_state *s, int step, int *n_vocab);  /* par
 int  ss_is_promotional_text(const char *utf8);                       /* whisper.rs:41-43 (list at :9-14) */
 int  ss_add_punctuation(const char *utf8, char *out, size_t out_cap);  /* whisper.rs:175-201; returns bytes written or <0 */
 int  ss_is_valid_utf8(const char *bytes, size_t n);                  /* what full_get_segment_text enforces, whisper.rs:85 */
+/* beam search's candidate assignment of one step (whisper_full, BEAM_SEARCH branch; the function the beam decoders run, host only):
+ * candidate c = len[c] token ids at ids[c * max_len], its sum_logprobs_all and the decoder it came from, in the order the decoders
+ * produced them; live[j] = decoder j still running; i = index of the token being sampled.  out[j] = index of the candidate decoder j
+ * continues with, -1 for a decoder that is not live. */
+int  ss_debug_beam_assign(const int *ids, const int *len, int max_len, const double *sums, const int *decoder_idx, int n_cands,
+                          const int *live, int n_cur, int i, int *out);
 /* parses a ggml .bin exactly like ss_engine_open (same errors) without touching a GPU */
 int  ss_model_probe(const char *ggml_path, int hparams_out[11], int64_t *arena_bytes, uint64_t *arena_fnv1a,
                     int *token_eot, int *token_beg, int *n_vocab_strings);

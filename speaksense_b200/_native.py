@@ -82,6 +82,7 @@ SYMBOLS = [
     ("ss_encode", C.c_int, [_P, _P, C.c_int, _P, C.c_size_t]),
     ("ss_decode", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     ("ss_debug_gemm", C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("ss_debug_beam_assign", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
 ]
 
 _lib = None

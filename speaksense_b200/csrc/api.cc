@@ -7,6 +7,7 @@
 
 #include "../../include/speaksense_whisper.h"
 #include "engine.h"
+#include "engine_internal.h"
 
 using namespace ss;
 
@@ -356,6 +357,28 @@ int ss_decode(ss_engine *e, ss_state *s, const int *tokens, int n, int n_past, f
     return guard([&]() -> int {
         if (!e || !s || !tokens) SS_THROW(SS_ERR_INVALID, "null argument");
         run_decode_forced(*s->s, tokens, n, n_past, logits_out);
+        return 0;
+    });
+}
+
+int ss_debug_beam_assign(const int *ids, const int *len, int max_len, const double *sums, const int *decoder_idx, int n_cands,
+                         const int *live, int n_cur, int i, int *out) {
+    return guard([&]() -> int {
+        if (n_cands < 0 || n_cur < 0 || max_len < 0 || !out || (n_cands > 0 && (!ids || !len || !sums || !decoder_idx)) || (n_cur > 0 && !live))
+            SS_THROW(SS_ERR_INVALID, "bad argument");
+        std::vector<BeamCandidate> cands((size_t)n_cands);
+        for (int c = 0; c < n_cands; c++) {
+            if (len[c] < 0 || len[c] > max_len) SS_THROW(SS_ERR_INVALID, "candidate %d: length %d outside [0, %d]", c, len[c], max_len);
+            cands[c].decoder_idx = decoder_idx[c];
+            cands[c].seek_delta = c;      // carries the original index through the sort
+            cands[c].has_ts = false;
+            for (int a = 0; a < len[c]; a++) { TokData t{}; t.id = ids[(size_t)c * max_len + a]; cands[c].seq.tokens.push_back(t); }
+            cands[c].seq.sum_logprobs_all = sums[c];
+        }
+        std::vector<char> lv((size_t)n_cur);
+        for (int j = 0; j < n_cur; j++) lv[j] = live[j] != 0;
+        const std::vector<int> pick = beam_pick(cands, lv, i);
+        for (int j = 0; j < n_cur; j++) out[j] = pick[j] >= 0 ? cands[pick[j]].seek_delta : -1;
         return 0;
     });
 }

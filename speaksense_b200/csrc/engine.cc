@@ -724,23 +724,37 @@ static bool same_tokens(const Sequence &a, const Sequence &b) {
     return true;
 }
 
+// which candidate each live decoder continues with (engine_internal.h; pure host logic, probed on the CPU by ss_debug_beam_assign)
+std::vector<int> beam_pick(std::vector<BeamCandidate> &cands, const std::vector<char> &live, int i) {
+    std::stable_sort(cands.begin(), cands.end(), [](const BeamCandidate &a, const BeamCandidate &b) {
+        return a.seq.sum_logprobs_all > b.seq.sum_logprobs_all;
+    });
+    std::vector<int> pick(live.size(), -1);
+    size_t cur_c = 0;
+    for (size_t j = 0; j < live.size(); j++) {
+        if (!live[j] || cands.empty()) continue;
+        if (cur_c >= cands.size()) cur_c = 0;
+        const BeamCandidate &c = cands[cur_c];
+        pick[j] = (int)cur_c++;
+        while (cands.size() > cur_c && i > 0 && same_tokens(cands[cur_c].seq, c.seq)) ++cur_c;
+    }
+    return pick;
+}
+
 // hand the best candidates to the live decoders (skipping duplicates of the one just taken) and move each decoder's
 // self-attention cache to follow its new sequence. The shuffle is two-phase like whisper.cpp's temporary sequence ids:
 // every moved cache is first copied into the destination decoder's second buffer, then the buffers are swapped.
 void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i, int n_past) {
-    std::stable_sort(cands.begin(), cands.end(), [](const BeamCandidate &a, const BeamCandidate &b) {
-        return a.seq.sum_logprobs_all > b.seq.sum_logprobs_all;
-    });
+    std::vector<char> live(n_cur);
+    for (int j = 0; j < n_cur; j++) live[j] = !(s.dec[j]->completed || s.dec[j]->failed);
+    const std::vector<int> pick = beam_pick(cands, live, i);
     const HParams &hp = s.engine->model.hp;
     const size_t kv = (size_t)hp.n_text_layer * hp.n_text_ctx * hp.n_text_state;
-    size_t cur_c = 0;
     std::vector<int> src(n_cur, -1);
     for (int j = 0; j < n_cur; j++) {
+        if (pick[j] < 0) continue;
         Decoder &dc = *s.dec[j];
-        if (dc.completed || dc.failed) continue;
-        if (cur_c >= cands.size()) cur_c = 0;
-        const BeamCandidate &c = cands[cur_c++];
-        while (cands.size() > cur_c && i > 0 && same_tokens(cands[cur_c].seq, c.seq)) ++cur_c;
+        const BeamCandidate &c = cands[pick[j]];
         dc.seek_delta = c.seek_delta; dc.has_ts = c.has_ts; dc.seq = c.seq;
         src[j] = c.decoder_idx;
     }

@@ -30,6 +30,10 @@ void kv_copy(State &s, Decoder &from, Decoder &to, int n_pos);
 // ---- beam search (whisper_full's BEAM_SEARCH strategy)
 struct BeamCandidate { int decoder_idx, seek_delta; bool has_ts; Sequence seq; };
 std::vector<TokData> sample_topk_host(const Model &m, const Decoder &dc, int k);
+// whisper_full's candidate assignment of one beam-search step, host only: sorts `cands` by sum_logprobs_all (descending, stable) and
+// returns, per decoder, the index of the candidate it continues with (-1: not live).  From the second sampled token on (i > 0) a
+// decoder skips the candidates behind its own that carry the same tokens; the cursor wraps.  (ss_debug_beam_assign probes it on CPU.)
+std::vector<int> beam_pick(std::vector<BeamCandidate> &cands, const std::vector<char> &live, int i);
 void beam_advance(State &s, std::vector<BeamCandidate> &cands, int n_cur, int i, int n_past);
 // (SS_BATCH_BEAM, on by default): one window's beam search with the live beams as sequences of one batched decoder step
 // (SS_BATCH_SAMPLE, on by default): the best_of sampled decoders of a t > 0 rung as sequences of one batched decoder step, drawn on the

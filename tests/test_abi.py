@@ -185,3 +185,28 @@ def test_cpp_trait_mirror_compiles_and_reports_errors(tmp_path):
     assert out[0] == "promo 1 0"
     assert out[1] == "punct [hello ]"
     assert out[2].startswith("error -") and "failed to open whisper model: " in out[2]
+
+
+def test_engine_beam_candidate_assignment_hand_derived_cases(L):
+    """The function the engine's beam decoders run (beam_pick, csrc/engine.cc) against the hand-derived cases of tests/beam_cases.py -
+    on the CPU, through the C ABI, independently of the oracle."""
+    import ctypes as C
+    import numpy as np
+    from tests.beam_cases import CASES
+    for name, cands, live, i, want in CASES:
+        n = len(cands)
+        max_len = max(len(c[0]) for c in cands)
+        ids = np.zeros((n, max_len), np.int32)
+        for k, c in enumerate(cands):
+            ids[k, :len(c[0])] = c[0]
+        lens = np.asarray([len(c[0]) for c in cands], np.int32)
+        sums = np.asarray([c[1] for c in cands], np.float64)
+        dec = np.asarray([c[2] for c in cands], np.int32)
+        lv = np.asarray([1 if x else 0 for x in live], np.int32)
+        out = np.full(len(live), -2, np.int32)
+        rc = L.ss_debug_beam_assign(ids.ctypes.data, lens.ctypes.data, max_len, sums.ctypes.data, dec.ctypes.data, n, lv.ctypes.data, len(live), i,
+                                    out.ctypes.data)
+        assert rc == 0, name
+        assert out.tolist() == want, name
+    bad = np.zeros(1, np.int32)
+    assert L.ss_debug_beam_assign(None, None, 0, None, None, 1, bad.ctypes.data, 1, 0, bad.ctypes.data) < 0      # null candidate arrays

@@ -121,41 +121,9 @@ def test_entropy_and_logprob_statistics(st):
     assert r["entropy"] == pytest.approx(math.log(3.0), rel=1e-12)
 
 
-# ---- beam search: candidate assignment (whisper.cpp whisper_full_with_state, BEAM_SEARCH branch: candidates sorted by
-# sum_logprobs_all, handed to the live decoders in order; from the second token on a decoder skips the candidates behind its own
-# that carry the same tokens; the cursor wraps).  Cases derived by hand from that rule, not from the oracle.
-def test_beam_candidates_go_to_decoders_best_first():
+# ---- beam search: candidate assignment: the hand-derived cases of tests/beam_cases.py against the oracle's beam_assign
+def test_beam_candidate_assignment_hand_derived_cases():
     from oracle import oracle
-    # two decoders, two candidates each (history + new token): sums -1.0, -3.0 (decoder 0), -2.0, -2.5 (decoder 1)
-    cands = [([10, 20], -1.0, 0), ([10, 21], -3.0, 0), ([11, 30], -2.0, 1), ([11, 31], -2.5, 1)]
-    assert oracle.beam_assign(cands, [True, True], i=1) == [0, 2]          # best overall, then second best
-    assert oracle.beam_assign(cands, [True, True, True, True], i=1) == [0, 2, 3, 1]
-
-
-def test_beam_duplicates_are_skipped_after_the_first_token():
-    from oracle import oracle
-    # both decoders carry the same history and propose the same best token: the second decoder must not continue with the copy
-    cands = [([10, 20], -1.0, 0), ([10, 21], -2.0, 0), ([10, 20], -1.0, 1), ([10, 22], -3.0, 1)]
-    assert oracle.beam_assign(cands, [True, True], i=1) == [0, 1]
-    # ... but at the first sampled token (i == 0) whisper.cpp does not look for duplicates: every decoder starts from the same
-    # logits, the sorted list begins with one copy of the best token per decoder, and all beams take it
-    first = [([20], -1.0, 0), ([21], -2.0, 0), ([20], -1.0, 1), ([21], -2.0, 1)]
-    assert oracle.beam_assign(first, [True, True], i=0) == [0, 2]
-    # a run of three copies is skipped as a whole
-    three = [([10, 20], -1.0, 0), ([10, 20], -1.0, 1), ([10, 20], -1.0, 2), ([10, 23], -4.0, 2), ([10, 21], -2.0, 0)]
-    assert oracle.beam_assign(three, [True, True, True], i=2) == [0, 4, 3]
-
-
-def test_beam_same_length_different_tokens_are_not_duplicates_and_finished_decoders_keep_out():
-    from oracle import oracle
-    cands = [([10, 20], -1.0, 0), ([10, 25], -1.0, 1), ([10, 21], -2.0, 0)]
-    assert oracle.beam_assign(cands, [True, True], i=3) == [0, 1]          # equal score, different tokens: both survive (stable order)
-    # decoder 1 has completed: it gets nothing and does not consume a candidate; decoder 2 takes the second best
-    assert oracle.beam_assign(cands, [True, False, True], i=3) == [0, -1, 1]
-
-
-def test_beam_cursor_wraps_when_the_candidates_run_out():
-    from oracle import oracle
-    # three live decoders, but after duplicate skipping only two distinct candidates: the cursor wraps to the best one
-    cands = [([10, 20], -1.0, 0), ([10, 20], -1.0, 1), ([10, 21], -2.0, 2)]
-    assert oracle.beam_assign(cands, [True, True, True], i=1) == [0, 2, 0]
+    from tests.beam_cases import CASES
+    for name, cands, live, i, want in CASES:
+        assert oracle.beam_assign(cands, live, i) == want, name
