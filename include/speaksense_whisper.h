@@ -171,6 +171,14 @@ const float *ss_debug_logits(const ss_state *s, int step, int *n_vocab);  /* par
 int  ss_is_promotional_text(const char *utf8);                       /* whisper.rs:41-43 (list at :9-14) */
 int  ss_add_punctuation(const char *utf8, char *out, size_t out_cap);  /* whisper.rs:175-201; returns bytes written or <0 */
 int  ss_is_valid_utf8(const char *bytes, size_t n);                  /* what full_get_segment_text enforces, whisper.rs:85 */
+/* whisper_process_logits as the engine's host-side decoders run it (process_logits_host: host-stepped fallback decoders, the first
+ * step of a beam search), on a given history of sampled token ids and raw logits [n_vocab] of the model file's vocabulary, with
+ * build_params' constants; out = the filtered logits (-inf = masked) */
+int  ss_debug_process_logits(const char *ggml_path, const int *ids, int n_ids, int has_ts, int seek_delta, const float *raw,
+                             float temperature, float *out);
+/* whisper_sequence_score + the entropy of the last 32 tokens (the temperature ladder's gates), engine version:
+ * out = {sum_logprobs, avg_logprobs, entropy, score} over the first result_len tokens */
+int  ss_debug_sequence_score(const int *ids, const float *plogs, int n, int result_len, float length_penalty, double out[4]);
 /* beam search's candidate assignment of one step (whisper_full, BEAM_SEARCH branch; the function the beam decoders run, host only):
  * candidate c = len[c] token ids at ids[c * max_len], its sum_logprobs_all and the decoder it came from, in the order the decoders
  * produced them; live[j] = decoder j still running; i = index of the token being sampled.  out[j] = index of the candidate decoder j

@@ -82,6 +82,8 @@ SYMBOLS = [
     ("ss_encode", C.c_int, [_P, _P, C.c_int, _P, C.c_size_t]),
     ("ss_decode", C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     ("ss_debug_gemm", C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("ss_debug_process_logits", C.c_int, [C.c_char_p, _P, C.c_int, C.c_int, C.c_int, _P, C.c_float, _P]),
+    ("ss_debug_sequence_score", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P]),
     ("ss_debug_beam_assign", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
 ]
 

@@ -361,6 +361,35 @@ int ss_decode(ss_engine *e, ss_state *s, const int *tokens, int n, int n_past, f
     });
 }
 
+int ss_debug_process_logits(const char *path, const int *ids, int n_ids, int has_ts, int seek_delta, const float *raw, float temperature,
+                            float *out) {
+    return guard([&]() -> int {
+        if (!path || !raw || !out || n_ids < 0 || (n_ids > 0 && !ids)) SS_THROW(SS_ERR_INVALID, "bad argument");
+        Model m;
+        load_model_meta(path, m);
+        Decoder dc;
+        for (int k = 0; k < n_ids; k++) { TokData t{}; t.id = ids[k]; dc.seq.tokens.push_back(t); }
+        dc.has_ts = has_ts != 0; dc.seek_delta = seek_delta;
+        const FullParams P;      // build_params' constants (whisper.rs:131-173)
+        process_logits_host(m, P, dc, raw, temperature);
+        memcpy(out, dc.logits.data(), (size_t)m.hp.n_vocab * sizeof(float));
+        return 0;
+    });
+}
+
+int ss_debug_sequence_score(const int *ids, const float *plogs, int n, int result_len, float length_penalty, double out[4]) {
+    return guard([&]() -> int {
+        if (!ids || !plogs || !out || n < 0 || result_len < 0 || result_len > n) SS_THROW(SS_ERR_INVALID, "bad argument");
+        Sequence q;
+        for (int k = 0; k < n; k++) { TokData t{}; t.id = ids[k]; t.plog = plogs[k]; q.tokens.push_back(t); }
+        q.result_len = result_len;
+        FullParams P; P.length_penalty = length_penalty;
+        sequence_score(P, q);
+        out[0] = q.sum_logprobs; out[1] = q.avg_logprobs; out[2] = q.entropy; out[3] = q.score;
+        return 0;
+    });
+}
+
 int ss_debug_beam_assign(const int *ids, const int *len, int max_len, const double *sums, const int *decoder_idx, int n_cands,
                          const int *live, int n_cur, int i, int *out) {
     return guard([&]() -> int {

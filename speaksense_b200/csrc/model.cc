@@ -329,6 +329,14 @@ std::vector<unsigned char> build_arena_image(const std::string &path) {
     return img;
 }
 
+void load_model_meta(const std::string &path, Model &m) {
+    ParsedFile pf;
+    parse_file(path, pf);
+    std::vector<std::string> toks;
+    parse_meta(pf.buf.data(), pf.meta_len, m.hp, nullptr, &toks);
+    fill_vocab(m, std::move(toks));
+}
+
 ModelProbe probe_model(const std::string &path) {
     std::vector<unsigned char> img = build_arena_image(path);
     ModelProbe pr{};

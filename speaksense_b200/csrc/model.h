@@ -62,6 +62,9 @@ struct ModelProbe { HParams hp; size_t arena_bytes; uint64_t fnv1a; int eot, beg
 // host-only: parse + pack like engine_open would, report sizes / checksum (no device)
 ModelProbe probe_model(const std::string &path);
 
+// host-only: hparams + vocabulary of a ggml file into `m` (what the host-side decode logic needs; no tensors, no device)
+void load_model_meta(const std::string &path, Model &m);
+
 // Build the host image of the arena from a ggml file (rank 0 / single GPU).
 std::vector<unsigned char> build_arena_image(const std::string &path);
 // Bind a Model to an arena image already resident on `device` (all ranks): parses the meta prefix

@@ -210,3 +210,73 @@ def test_engine_beam_candidate_assignment_hand_derived_cases(L):
         assert out.tolist() == want, name
     bad = np.zeros(1, np.int32)
     assert L.ss_debug_beam_assign(None, None, 0, None, None, 1, bad.ctypes.data, 1, 0, bad.ctypes.data) < 0      # null candidate arrays
+
+
+def test_engine_logits_filter_matches_hf_timestamp_processor(L, micro_v3_random):
+    """The ENGINE's host-side whisper_process_logits (process_logits_host, csrc/engine.cc, through ss_debug_process_logits on the CPU)
+    against HuggingFace's WhisperTimeStampLogitsProcessor (tests/golden/logits_filter.npz, tools/make_golden_logits_filter.py) - the
+    comparison tests/test_oracle_golden.py makes for the oracle, with the same two documented exceptions (W: tokens only whisper.cpp
+    suppresses in this function; D: the open timestamp OpenAI forbids repeating), made for the product's own function."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "logits_filter.npz"))
+    nv, beg, eot = int(g["n_vocab"]), int(g["beg"]), int(g["eot"])
+    sot = eot + 1
+    W = np.zeros(nv, bool)
+    W[sot:sot + 101] = True                      # sot + the language table
+    W[beg - 6:beg - 1] = True                    # translate, transcribe, solm, prev, nosp
+    path = micro_v3_random.encode()
+    for name in [str(x) for x in g["names"]]:
+        ids = np.asarray(g[name + "_ids"], np.int32)
+        rng = np.random.default_rng(int(g[name + "_seed"]))
+        raw = rng.standard_normal(nv).astype(np.float32) * 2.0
+        raw[beg:] += np.float32(g[name + "_boost"])
+        has_ts, seek_delta = 0, 0
+        for t in ids.tolist():                   # the decoder state whisper_full keeps beside the history
+            if t > beg:
+                has_ts, seek_delta = 1, 2 * (t - beg)
+        out = np.empty(nv, np.float32)
+        rc = L.ss_debug_process_logits(path, ids.ctypes.data if ids.size else None, int(ids.size), has_ts, seek_delta, raw.ctypes.data, 0.0,
+                                       out.ctypes.data)
+        assert rc == 0, name
+        got = np.isneginf(out)
+        want = np.unpackbits(g[name + "_masked"])[:nv].astype(bool)
+        D = np.zeros(nv, bool)
+        il = ids.tolist()
+        ts = [t for t in il if t >= beg]
+        if ts and not (il[-1] >= beg and (len(il) >= 2 and il[-2] < beg)):
+            D[ts[-1]] = True
+        cmp = ~(W | D)
+        assert np.array_equal(got[cmp], want[cmp]), name
+        assert got[W].all(), name
+        assert np.array_equal(out[~got], raw[~got]), name      # what is not masked passes through unchanged (temperature 0)
+
+
+def test_engine_sequence_score_hand_derived_cases(L):
+    """sequence_score of the engine (whisper_sequence_score + the entropy gate of the temperature ladder) on the hand-derived cases
+    tests/test_oracle_rules.py holds the oracle to."""
+    import math
+    import numpy as np
+    import pytest
+
+    def score(ids, plogs, result_len, length_penalty=-1.0):
+        a = np.asarray(ids, np.int32); p = np.asarray(plogs, np.float32)
+        import ctypes as C
+        out = (C.c_double * 4)()
+        assert L.ss_debug_sequence_score(a.ctypes.data, p.ctypes.data, int(a.size), result_len, length_penalty, out) == 0
+        return dict(sum_logprobs=out[0], avg_logprobs=out[1], entropy=out[2], score=out[3])
+
+    r = score([7] * 40, [-0.5] * 40, 40)                                     # one token repeated: entropy 0 (the repetition detector)
+    assert r["entropy"] == pytest.approx(0.0, abs=1e-12) and r["avg_logprobs"] == pytest.approx(-0.5, rel=1e-6)
+    assert r["sum_logprobs"] == pytest.approx(-20.0, rel=1e-6)
+    assert score(list(range(100, 132)), [-1.0] * 32, 32)["entropy"] == pytest.approx(math.log(32.0), rel=1e-12)
+    ids = [5] * 8 + list(range(100, 132))                                    # only the LAST 32 tokens of the first result_len count
+    assert score(ids, [-0.25] * len(ids), len(ids))["entropy"] == pytest.approx(math.log(32.0), rel=1e-12)
+    r = score([9] * 16 + list(range(200, 216)), [-0.1] * 32, 32)             # (1/2) ln 2 + (1/2) ln 32 = 3 ln 2 < 2.4
+    assert r["entropy"] == pytest.approx(3.0 * math.log(2.0), rel=1e-12)
+    r = score([1, 2, 3, 4, 5], [-0.1, -0.2, -0.3, -5.0, -5.0], 3)             # statistics over the first result_len tokens only
+    assert r["sum_logprobs"] == pytest.approx(-0.6, rel=1e-6) and r["avg_logprobs"] == pytest.approx(-0.2, rel=1e-6)
+    assert r["score"] == pytest.approx(-0.2, rel=1e-6) and r["entropy"] == pytest.approx(math.log(3.0), rel=1e-12)
+    # length_penalty > 0: score = sum / ((5 + len) / 6) ^ penalty  (whisper_sequence_score)
+    r = score([1, 2, 3, 4], [-1.0] * 4, 4, length_penalty=1.0)
+    assert r["score"] == pytest.approx(-4.0 / ((5.0 + 4.0) / 6.0), rel=1e-6)
