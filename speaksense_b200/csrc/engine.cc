@@ -472,7 +472,7 @@ void run_encode(State &s, int seek) {
     if (!enc_graph_enabled()) { encode_window_enqueue(s, st, &s.n_launches); return; }
     if (!s.enc_graph) {
         // One host thread drives a State at a time; thread-local capture leaves the other sessions' streams alone.  The tensor maps and
-        // kernel arguments are baked into the graph: one cudaGraphLaunch replaces ~340 launches and ~260 tensor-map encodes per window.
+        // kernel arguments are baked into the graph: one cudaGraphLaunch replaces ~230 launches and ~360 tensor-map encodes per window.
         cudaGraph_t graph = nullptr;
         int n = 0;
         CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));

@@ -81,7 +81,7 @@ struct State {
     __half *win = nullptr, *x1 = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *enc16 = nullptr;
     float *x = nullptr, *enc_out = nullptr;
     __half *cross_k = nullptr, *cross_v = nullptr;
-    // the encoder pass of one window (conv stem .. cross-KV: ~340 launches over buffers that never move) captured as a CUDA graph at
+    // the encoder pass of one window (conv stem .. cross-KV: ~230 launches over buffers that never move) captured as a CUDA graph at
     // the first window and replayed afterwards (SS_ENC_GRAPH=0: plain launches)
     void *enc_graph = nullptr; int enc_graph_launches = 0;
     // decoders
